@@ -1,0 +1,92 @@
+/*
+ * batchIntegrator.h -- the NEW batched entry of the library (C ABI).
+ *
+ * It replaces the serial design-point loop of the reference,
+ *     for i in designpoints: setVariableValue x nvary; integrateOneStep until
+ *     timeCourseCompleted; harvest; reset          (src/odeSolver.c:313-330,
+ *                                                   examples/ParameterScanner.c:136-163)
+ * by one kernel launch per device in which every trajectory is integrated by
+ * a CVODE-style variable-order BDF (vendored SUNDIALS 2.1.1:
+ * Win32/WinCVODE/sundials/cvode/source/cvode.c:875-2713, cvdense.c:368-441).
+ * Per set the semantics are exactly `reset; setVariableValue x nvary;
+ * integrate` including the output-time event handling of
+ * src/integratorInstance.c:1029-1237.
+ *
+ * All pointers are plain host pointers unless named "device".  No torch types.
+ * Every function returns 1 on success and 0 on failure (a SolverError is
+ * pushed, codes 14XXXX) unless stated otherwise.  There is no CPU fallback:
+ * without a CUDA device every launch entry fails with
+ * SOLVER_ERROR_CUDA_UNAVAILABLE.
+ */
+#ifndef ODES_B200_BATCHINTEGRATOR_H
+#define ODES_B200_BATCHINTEGRATOR_H
+#include "sbmlsolver/integratorInstance.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct odesBatch odesBatch_t;
+
+/* per-trajectory work counters, CVODE naming (cvode_statistics.txt of the reference) */
+enum { ODES_STAT_NST = 0, ODES_STAT_NFE, ODES_STAT_NSETUPS, ODES_STAT_NJE, ODES_STAT_NNI,
+       ODES_STAT_NCFN, ODES_STAT_NETF, ODES_NUM_STATS };
+
+/* One-shot drop-in for the batch loop.  values: [nsets][nvary] row-major, the
+   varySettings_t.params layout (src/sbmlsolver/odeSolver.h:53-65).  out: NULL or
+   [nsets][nout+1][nvalues] (per set: time-major rows of all model values, as the
+   reference stores them in cvodeResults_t).  status: NULL or [nsets] CVODE flags
+   (0 ok, -4 too much work, -5 too much accuracy, -6 error test failures, -7
+   convergence failures, ... numbering of cvode.h:712-725 of the vendored tree).
+   Returns the number of failed sets, or -1 if nothing could be launched. */
+int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int nsets, int nvary,
+                                      variableIndex_t *const *vi, const double *values,
+                                      double *out, int *status);
+
+/* Plan API (device-resident use; what the one-shot call is built from). */
+odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex,
+                              int nstore, const int *storeIndex /* NULL: all values */, int device);
+void ODESBatch_free(odesBatch_t *);
+int ODESBatch_reserve(odesBatch_t *, int capacity);
+int ODESBatch_getCapacity(const odesBatch_t *);
+int ODESBatch_getNout(const odesBatch_t *);        /* number of stored rows = PrintStep+1 */
+int ODESBatch_getNstore(const odesBatch_t *);
+const char *ODESBatch_getSource(const odesBatch_t *);   /* generated CUDA source */
+const char *ODESBatch_getCompileLog(const odesBatch_t *);
+int ODESBatch_getKernelInfo(const odesBatch_t *, int *regsPerThread, int *sharedBytesPerBlock,
+                            int *localBytesPerThread, int *threadsPerBlock, int *blocksPerSM);
+
+/* inputs: host row-major [nsets][nvary] -> device SoA [nvary][capacity] */
+int ODESBatch_setValues(odesBatch_t *, int nsets, const double *values);
+/* synthetic inputs generated on the device: value = base[j] * 2^u, u ~ U(lo[j], hi[j]),
+   Philox4x32-10 keyed by seed, counter = (firstSet + set, j)   */
+int ODESBatch_generateValues(odesBatch_t *, int nsets, unsigned long long seed, long long firstSet,
+                             const double *base, const double *lo, const double *hi, int log10Scale);
+double *ODESBatch_deviceValues(odesBatch_t *);     /* [nvary][capacity] */
+double *ODESBatch_deviceResults(odesBatch_t *);    /* [nout+1][nstore][capacity] */
+
+/* run: asynchronous launch on the plan's stream, then explicit synchronisation */
+int ODESBatch_integrate(odesBatch_t *, int nsets);
+int ODESBatch_synchronize(odesBatch_t *);
+float ODESBatch_getLastKernelMs(const odesBatch_t *);   /* CUDA events on the launching stream */
+int ODESBatch_getNumLaunches(const odesBatch_t *);
+
+/* outputs: device SoA -> host.  results: [nout+1][nstore][nsets] (batch fastest). */
+int ODESBatch_getResults(odesBatch_t *, int nsets, double *results);
+int ODESBatch_getTrajectory(odesBatch_t *, int set, double *traj /* [nout+1][nstore] */);
+int ODESBatch_getStatus(odesBatch_t *, int nsets, int *status);
+int ODESBatch_getStats(odesBatch_t *, int nsets, int *stats /* [ODES_NUM_STATS][nsets] */);
+int ODESBatch_getEventLog(odesBatch_t *, int nsets, unsigned int *fired /* [nout+1][nsets] bitmasks */);
+/* pipelined end-to-end helper: chunks the batch, overlaps H2D / kernel / D2H on three streams */
+int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *results, int *status,
+                      int chunk);
+
+/* device utilities */
+int ODES_deviceCount(void);
+int ODES_deviceName(int device, char *buf, int len);
+/* FP64 FMA micro-benchmark: returns measured TFLOP/s (2 flop per FMA), 0 on failure */
+double ODES_measureFP64Peak(int device, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

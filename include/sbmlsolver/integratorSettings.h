@@ -1,0 +1,80 @@
+/*
+ * integratorSettings.h -- cvodeSettings_t, field-for-field the reference's
+ * src/sbmlsolver/integratorSettings.h:56-148 for the forward path (adjoint and
+ * sensitivity switches are kept as inert fields so callers compile).
+ * Functions: reference integratorSettings.h:172-245.
+ */
+#ifndef ODES_B200_INTEGRATORSETTINGS_H
+#define ODES_B200_INTEGRATORSETTINGS_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvodeSettings cvodeSettings_t;
+struct cvodeSettings {
+  double Time; int PrintStep; int StepResolution; double *TimePoints; int Indefinitely;
+  double Error; double RError; int Mxstep; int DetectNegState;
+  int CvodeMethod; int IterMethod; int MaxOrder; int ResetCvodeOnEvent; int SetTStop;
+  int Sensitivity; char **sensIDs; int nsens; int SensMethod;
+  int HaltOnEvent; int SteadyState; double ssThreshold;
+  int UseJacobian; int StoreResults; int compileFunctions;
+  int observation_data_type; int DoAdjoint;
+};
+
+cvodeSettings_t *CvodeSettings_create(void);
+cvodeSettings_t *CvodeSettings_createWithTime(double Time, int PrintStep);
+cvodeSettings_t *CvodeSettings_createWith(double EndTime, int PrintStep, double Error, double RError,
+    int Mxstep, int Method, int IterMethod, int UseJacobian, int Indefinitely, int HaltOnEvent,
+    int SteadyState, int StoreResults, int Sensitivity, int SensMethod);
+int CvodeSettings_setTime(cvodeSettings_t *, double EndTime, int PrintStep);
+int CvodeSettings_setTimeStep(cvodeSettings_t *, int, double);
+int CvodeSettings_setTimeSeries(cvodeSettings_t *, double *timeseries, int PrintStep);
+void CvodeSettings_setSwitches(cvodeSettings_t *, int UseJacobian, int Indefinitely, int HaltOnEvent,
+    int SteadyState, int StoreResults, int Sensitivity, int SensMethod);
+void CvodeSettings_setErrors(cvodeSettings_t *, double Error, double RError, int Mxstep);
+void CvodeSettings_setError(cvodeSettings_t *, double);
+void CvodeSettings_setRError(cvodeSettings_t *, double);
+void CvodeSettings_setMxstep(cvodeSettings_t *, int);
+void CvodeSettings_setDetectNegState(cvodeSettings_t *, int);
+void CvodeSettings_setTStop(cvodeSettings_t *, int);
+void CvodeSettings_setCompileFunctions(cvodeSettings_t *, int);
+void CvodeSettings_setMethod(cvodeSettings_t *, int, int);
+void CvodeSettings_setIterMethod(cvodeSettings_t *, int);
+void CvodeSettings_setMaxOrder(cvodeSettings_t *, int);
+void CvodeSettings_setJacobian(cvodeSettings_t *, int);
+void CvodeSettings_setIndefinitely(cvodeSettings_t *, int);
+void CvodeSettings_setHaltOnEvent(cvodeSettings_t *, int);
+void CvodeSettings_setResetCvodeOnEvent(cvodeSettings_t *, int);
+void CvodeSettings_setHaltOnSteadyState(cvodeSettings_t *, int);
+void CvodeSettings_setSteadyStateThreshold(cvodeSettings_t *, double);
+void CvodeSettings_setStoreResults(cvodeSettings_t *, int);
+void CvodeSettings_setSensitivity(cvodeSettings_t *, int);
+void CvodeSettings_setSensMethod(cvodeSettings_t *, int);
+void CvodeSettings_dump(cvodeSettings_t *);
+void CvodeSettings_free(cvodeSettings_t *);
+cvodeSettings_t *CvodeSettings_clone(cvodeSettings_t *);
+double CvodeSettings_getEndTime(cvodeSettings_t *);
+int CvodeSettings_getPrintsteps(cvodeSettings_t *);
+double CvodeSettings_getTimeStep(cvodeSettings_t *);
+double CvodeSettings_getTime(cvodeSettings_t *, int);
+double CvodeSettings_getError(cvodeSettings_t *);
+double CvodeSettings_getRError(cvodeSettings_t *);
+int CvodeSettings_getMxstep(cvodeSettings_t *);
+const char *CvodeSettings_getMethod(const cvodeSettings_t *);
+const char *CvodeSettings_getIterMethod(const cvodeSettings_t *);
+int CvodeSettings_getMaxOrder(cvodeSettings_t *);
+int CvodeSettings_getCompileFunctions(cvodeSettings_t *);
+int CvodeSettings_getResetCvodeOnEvent(cvodeSettings_t *);
+int CvodeSettings_getJacobian(cvodeSettings_t *);
+int CvodeSettings_getIndefinitely(cvodeSettings_t *);
+int CvodeSettings_getHaltOnEvent(cvodeSettings_t *);
+int CvodeSettings_getHaltOnSteadyState(cvodeSettings_t *);
+double CvodeSettings_getSteadyStateThreshold(cvodeSettings_t *);
+int CvodeSettings_getStoreResults(cvodeSettings_t *);
+int CvodeSettings_getSensitivity(cvodeSettings_t *);
+const char *CvodeSettings_getSensMethod(const cvodeSettings_t *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

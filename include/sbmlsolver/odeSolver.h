@@ -1,0 +1,53 @@
+/*
+ * odeSolver.h -- high-level batch interface: varySettings_t and
+ * Model_odeSolverBatch.  Reference: src/sbmlsolver/odeSolver.h:53-92,
+ * src/odeSolver.c:235-352 (batch loop), :354-440 (globalize/localize).
+ * Model_odeSolverBatch keeps its meaning but runs all design points in one
+ * batched device launch and returns the results as a batchResults_t.
+ */
+#ifndef ODES_B200_ODESOLVER_H
+#define ODES_B200_ODESOLVER_H
+#include "sbmlsolver/batchIntegrator.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct varySettings varySettings_t;
+struct varySettings {
+  int nrdesignpoints; int nrparams; char **id; char **rid; double **params;
+  int cnt_params; int cnt_points;
+};
+
+/* results of a batch run: all model values at all output times for every design point */
+typedef struct batchResults {
+  int nsets, nout, nvalues;      /* nout = number of time points (PrintStep+1) */
+  char **names;                  /* [nvalues] */
+  double *time;                  /* [nout] */
+  double *value;                 /* [nout][nvalues][nsets] */
+  int *status;                   /* [nsets] */
+} batchResults_t;
+
+varySettings_t *VarySettings_allocate(int nrparams, int nrdesignpoints);
+int VarySettings_addDesignPoint(varySettings_t *, const double *);
+int VarySettings_addParameter(varySettings_t *, const char *, const char *);
+int VarySettings_setName(varySettings_t *, int, const char *, const char *);
+int VarySettings_setValue(varySettings_t *, int, int, double);
+double VarySettings_getValue(varySettings_t *, int, int);
+int VarySettings_setValueByID(varySettings_t *, int, const char *, const char *, double);
+double VarySettings_getValueByID(varySettings_t *, int, const char *, const char *);
+const char *VarySettings_getName(const varySettings_t *, int);
+const char *VarySettings_getReactionName(const varySettings_t *, int);
+void VarySettings_dump(varySettings_t *);
+void VarySettings_free(varySettings_t *);
+
+batchResults_t *Model_odeSolverBatch(Model_t *, cvodeSettings_t *, varySettings_t *);
+batchResults_t *SBML_odeSolverBatch(SBMLDocument_t *, cvodeSettings_t *, varySettings_t *);
+double BatchResults_getValue(const batchResults_t *, int set, const char *name, int timestep);
+void BatchResults_free(batchResults_t *);
+int Model_globalizeParameter(Model_t *m, const char *id, const char *rid);
+int Model_localizeParameter(Model_t *m, const char *id, const char *rid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
