@@ -1,0 +1,462 @@
+/*
+ * emit.c -- code generation: formula trees -> compilable source text.
+ *
+ * Reference seam (kept): src/processAST.c:2057-2311 generateMacros/generateAST
+ * turn an indexed AST into a C expression over value[]; src/odeModel.c:2600-2918
+ * wrap those into ode_f / jacobi_f / event_f which src/compiler.c builds with
+ * g++ and dlopen's.  Here the same traversal emits
+ *   (1) CUDA device functions for sm_100a that are inlined into the batched
+ *       BDF kernel (ODEModel_generateCUDASource), and
+ *   (2) the host-C flavour of ode_f / jacobi_f (ODEModel_generateCSource) that
+ *       corresponds to the reference's compiled mode (used by tests and by the
+ *       CPU baseline harness only).
+ * Differences to the reference emitter, on purpose: constants are printed
+ * with "%.17g" (the reference's "%g" truncates to 6 digits, src/charBuffer.c:103-112),
+ * piecewise supports any number of pieces, root() handles odd degrees of
+ * negative radicands like evaluateAST does, and the event function follows
+ * the interpreter semantics (src/integratorInstance.c:1029-1077), not the
+ * re-arming variant of the reference's generated event_f.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sbmlsolver/odeModel.h"
+#include "sbmlsolver/processAST.h"
+#include "sbmlsolver/solverError.h"
+
+/* ----------------------------------------------------------- charBuffer */
+struct charBuffer { char *b; size_t len, cap; };
+charBuffer_t *CharBuffer_create(void) { charBuffer_t *c = (charBuffer_t *)calloc(1, sizeof *c); c->cap = 1024; c->b = (char *)malloc(c->cap); c->b[0] = 0; return c; }
+void CharBuffer_free(charBuffer_t *c) { if (c) { free(c->b); free(c); } }
+void CharBuffer_append(charBuffer_t *c, const char *s)
+{
+  size_t n = strlen(s);
+  if (c->len + n + 1 > c->cap) { c->cap = 2 * (c->len + n + 1); c->b = (char *)realloc(c->b, c->cap); }
+  memcpy(c->b + c->len, s, n + 1); c->len += n;
+}
+void CharBuffer_appendInt(charBuffer_t *c, long v) { char t[32]; snprintf(t, sizeof t, "%ld", v); CharBuffer_append(c, t); }
+void CharBuffer_appendDouble(charBuffer_t *c, double v)
+{
+  char t[64];
+  if (isnan(v)) strcpy(t, "(0.0/0.0)");
+  else if (isinf(v)) strcpy(t, v > 0 ? "(1.0/0.0)" : "(-1.0/0.0)");
+  else {
+    snprintf(t, sizeof t, "%.17g", v);
+    if (!strpbrk(t, ".eEn")) strcat(t, ".0");
+  }
+  CharBuffer_append(c, t);
+}
+const char *CharBuffer_getBuffer(charBuffer_t *c) { return c->b; }
+static void cbprintf(charBuffer_t *c, const char *fmt, ...)
+{
+  char t[2048]; va_list ap;
+  va_start(ap, fmt); vsnprintf(t, sizeof t, fmt, ap); va_end(ap);
+  CharBuffer_append(c, t);
+}
+
+/* --------------------------------------------------------- expressions */
+typedef struct emit_ctx {
+  int cuda;                       /* 1: device flavour with exact-case strength reduction */
+  /* resolves value[idx] to source text */
+  void (*name)(charBuffer_t *, int idx, const struct emit_ctx *);
+  const char *time;               /* text of the current time */
+  const void *info;
+} emit_ctx_t;
+
+static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c);
+
+static int is_const_tree(const ASTNode_t *n)
+{
+  unsigned int i;
+  if (ASTNode_isName(n) || n->type == AST_FUNCTION || n->type == AST_FUNCTION_DELAY) return 0;
+  for (i = 0; i < n->nchildren; i++) if (!is_const_tree(n->children[i])) return 0;
+  return 1;
+}
+static void gen_nested(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
+{
+  switch (n->type) {
+  case AST_PLUS: case AST_MINUS: case AST_TIMES: case AST_DIVIDE:
+  case AST_LOGICAL_AND: case AST_LOGICAL_OR: case AST_LOGICAL_NOT:
+  case AST_RELATIONAL_EQ: case AST_RELATIONAL_GEQ: case AST_RELATIONAL_GT:
+  case AST_RELATIONAL_LEQ: case AST_RELATIONAL_LT: case AST_RELATIONAL_NEQ:
+    CharBuffer_append(s, "("); gen(s, n, c); CharBuffer_append(s, ")"); break;
+  default: gen(s, n, c);
+  }
+}
+static void gen_nary(charBuffer_t *s, const ASTNode_t *n, const char *op, const emit_ctx_t *c)
+{
+  unsigned int i;
+  for (i = 0; i < n->nchildren; i++) {
+    gen_nested(s, n->children[i], c);
+    if (i + 1 != n->nchildren) { CharBuffer_append(s, " "); CharBuffer_append(s, op); CharBuffer_append(s, " "); }
+  }
+}
+static void gen_call(charBuffer_t *s, const ASTNode_t *n, const char *fn, const emit_ctx_t *c)
+{
+  unsigned int i;
+  CharBuffer_append(s, fn); CharBuffer_append(s, "(");
+  for (i = 0; i < n->nchildren; i++) { gen(s, n->children[i], c); if (i + 1 != n->nchildren) CharBuffer_append(s, ", "); }
+  CharBuffer_append(s, ")");
+}
+/* n-ary relational chain a < b < c  ->  ((a < b) && (b < c)) as doubles; children are pure */
+static void gen_chain(charBuffer_t *s, const ASTNode_t *n, const char *op, const emit_ctx_t *c)
+{
+  unsigned int i;
+  if (n->nchildren <= 1) { CharBuffer_append(s, "1.0"); return; }
+  CharBuffer_append(s, "(double)(");
+  for (i = 0; i + 1 < n->nchildren; i++) {
+    if (i) CharBuffer_append(s, " && ");
+    CharBuffer_append(s, "("); gen_nested(s, n->children[i], c); cbprintf(s, " %s ", op); gen_nested(s, n->children[i + 1], c); CharBuffer_append(s, ")");
+  }
+  CharBuffer_append(s, ")");
+}
+static void gen_piecewise(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
+{
+  /* evaluateAST lets the LAST true piece win, falls back to the odd trailing child, else 0:
+     nest so that later pieces are tested first */
+  unsigned int np = n->nchildren / 2, i;
+  int opened = 0;
+  for (i = np; i-- > 0;) {
+    CharBuffer_append(s, "(("); gen(s, n->children[2 * i + 1], c); CharBuffer_append(s, ") != 0.0 ? ("); gen(s, n->children[2 * i], c); CharBuffer_append(s, ") : ");
+    opened++;
+  }
+  if (n->nchildren % 2) { CharBuffer_append(s, "("); gen(s, n->children[n->nchildren - 1], c); CharBuffer_append(s, ")"); }
+  else CharBuffer_append(s, "0.0");
+  while (opened--) CharBuffer_append(s, ")");
+}
+
+static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
+{
+  unsigned int i;
+  /* constant sub-expressions of numbers are folded at emit time with the host evaluator
+     (same IEEE operations the interpreter would perform at run time) */
+  if (c->cuda && n->nchildren > 0 && is_const_tree(n) && !ASTNode_isLogical(n) && !ASTNode_isRelational(n) && n->type != AST_FUNCTION_PIECEWISE) {
+    CharBuffer_appendDouble(s, evaluateAST((ASTNode_t *)n, NULL));
+    return;
+  }
+  switch (n->type) {
+  case AST_PLUS: gen_nary(s, n, "+", c); break;
+  case AST_TIMES: gen_nary(s, n, "*", c); break;
+  case AST_MINUS:
+    if (n->nchildren == 1) { CharBuffer_append(s, "-"); gen_nested(s, n->children[0], c); }
+    else gen_nary(s, n, "-", c);
+    break;
+  case AST_DIVIDE: gen_nary(s, n, "/", c); break;
+  case AST_POWER: case AST_FUNCTION_POWER:
+    if (c->cuda && n->nchildren == 2 && is_const_tree(n->children[1])) {
+      double e = evaluateAST(n->children[1], NULL);
+      if (e == 0.0) { CharBuffer_append(s, "1.0"); break; }               /* pow(x,0) == 1 exactly  */
+      if (e == 1.0) { gen_nested(s, n->children[0], c); break; }          /* pow(x,1) == x exactly  */
+      if (e == 2.0) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
+    }
+    gen_call(s, n, "pow", c); break;
+  case AST_INTEGER: CharBuffer_appendDouble(s, (double)n->ival); break;
+  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: CharBuffer_appendDouble(s, ASTNode_getReal(n)); break;
+  case AST_NAME:
+    if (ASTNode_isSetIndex(n)) c->name(s, (int)ASTNode_getIndex(n), c);
+    else {
+      SolverError_error(FATAL_ERROR_TYPE, SOLVER_ERROR_AST_COMPILATION_FAILED_MISSING_VALUE,
+                        "generateAST: No value found for AST_NAME %s. Defaults to Zero to avoid program crash", ASTNode_getName(n));
+      CharBuffer_append(s, "0.0");
+    }
+    break;
+  case AST_NAME_TIME: CharBuffer_append(s, c->time); break;
+  case AST_CONSTANT_E: CharBuffer_appendDouble(s, exp(1.)); break;
+  case AST_CONSTANT_FALSE: CharBuffer_append(s, "0.0"); break;
+  case AST_CONSTANT_PI: CharBuffer_appendDouble(s, 4. * atan(1.)); break;
+  case AST_CONSTANT_TRUE: CharBuffer_append(s, "1.0"); break;
+  case AST_FUNCTION_ABS: gen_call(s, n, "fabs", c); break;
+  case AST_FUNCTION_ARCCOS: gen_call(s, n, "acos", c); break;
+  case AST_FUNCTION_ARCCOSH: gen_call(s, n, "odes_acosh", c); break;
+  case AST_FUNCTION_ARCCOT: gen_call(s, n, "odes_acot", c); break;
+  case AST_FUNCTION_ARCCOTH: gen_call(s, n, "odes_acoth", c); break;
+  case AST_FUNCTION_ARCCSC: gen_call(s, n, "odes_acsc", c); break;
+  case AST_FUNCTION_ARCCSCH: gen_call(s, n, "odes_acsch", c); break;
+  case AST_FUNCTION_ARCSEC: gen_call(s, n, "odes_asec", c); break;
+  case AST_FUNCTION_ARCSECH: gen_call(s, n, "odes_asech", c); break;
+  case AST_FUNCTION_ARCSIN: gen_call(s, n, "asin", c); break;
+  case AST_FUNCTION_ARCSINH: gen_call(s, n, "odes_asinh", c); break;
+  case AST_FUNCTION_ARCTAN: gen_call(s, n, "atan", c); break;
+  case AST_FUNCTION_ARCTANH: gen_call(s, n, "odes_atanh", c); break;
+  case AST_FUNCTION_CEILING: gen_call(s, n, "ceil", c); break;
+  case AST_FUNCTION_COS: gen_call(s, n, "cos", c); break;
+  case AST_FUNCTION_COSH: gen_call(s, n, "cosh", c); break;
+  case AST_FUNCTION_COT: gen_call(s, n, "odes_cot", c); break;
+  case AST_FUNCTION_COTH: gen_call(s, n, "odes_coth", c); break;
+  case AST_FUNCTION_CSC: gen_call(s, n, "odes_csc", c); break;
+  case AST_FUNCTION_CSCH: gen_call(s, n, "odes_csch", c); break;
+  case AST_FUNCTION_EXP: gen_call(s, n, "exp", c); break;
+  case AST_FUNCTION_FACTORIAL: gen_call(s, n, "odes_factorial", c); break;
+  case AST_FUNCTION_FLOOR: gen_call(s, n, "floor", c); break;
+  case AST_FUNCTION_LN: gen_call(s, n, "log", c); break;
+  case AST_FUNCTION_LOG: gen_call(s, n, "odes_logbase", c); break;
+  case AST_FUNCTION_PIECEWISE: gen_piecewise(s, n, c); break;
+  case AST_FUNCTION_ROOT: gen_call(s, n, "odes_root", c); break;
+  case AST_FUNCTION_SEC: gen_call(s, n, "odes_sec", c); break;
+  case AST_FUNCTION_SECH: gen_call(s, n, "odes_sech", c); break;
+  case AST_FUNCTION_SIN: gen_call(s, n, "sin", c); break;
+  case AST_FUNCTION_SINH: gen_call(s, n, "sinh", c); break;
+  case AST_FUNCTION_TAN: gen_call(s, n, "tan", c); break;
+  case AST_FUNCTION_TANH: gen_call(s, n, "tanh", c); break;
+  case AST_LOGICAL_AND: case AST_LOGICAL_OR: case AST_LOGICAL_XOR: {
+      /* evaluateAST sums the (int-truncated) truth values: and = all, or = any, xor = odd count */
+      CharBuffer_append(s, "(double)((");
+      for (i = 0; i < n->nchildren; i++) { if (i) CharBuffer_append(s, " + "); CharBuffer_append(s, "(int)("); gen(s, n->children[i], c); CharBuffer_append(s, ")"); }
+      if (n->nchildren == 0) CharBuffer_append(s, "0");
+      if (n->type == AST_LOGICAL_AND) cbprintf(s, ") == %u)", n->nchildren);
+      else if (n->type == AST_LOGICAL_OR) CharBuffer_append(s, ") > 0)");
+      else CharBuffer_append(s, ") % 2 != 0)");
+      break;
+    }
+  case AST_LOGICAL_NOT: CharBuffer_append(s, "(double)(!("); gen(s, n->children[0], c); CharBuffer_append(s, "))"); break;
+  case AST_RELATIONAL_EQ:
+    if (n->nchildren <= 1) { CharBuffer_append(s, "1.0"); break; }
+    CharBuffer_append(s, "(double)(");
+    for (i = 1; i < n->nchildren; i++) { if (i > 1) CharBuffer_append(s, " && "); CharBuffer_append(s, "("); gen_nested(s, n->children[0], c); CharBuffer_append(s, " == "); gen_nested(s, n->children[i], c); CharBuffer_append(s, ")"); }
+    CharBuffer_append(s, ")");
+    break;
+  case AST_RELATIONAL_GEQ: gen_chain(s, n, ">=", c); break;
+  case AST_RELATIONAL_GT: gen_chain(s, n, ">", c); break;
+  case AST_RELATIONAL_LEQ: gen_chain(s, n, "<=", c); break;
+  case AST_RELATIONAL_LT: gen_chain(s, n, "<", c); break;
+  case AST_RELATIONAL_NEQ: CharBuffer_append(s, "(double)("); gen_nested(s, n->children[0], c); CharBuffer_append(s, " != "); gen_nested(s, n->children[1], c); CharBuffer_append(s, ")"); break;
+  default:
+    SolverError_error(FATAL_ERROR_TYPE, SOLVER_ERROR_AST_COMPILATION_FAILED_STRANGE_NODE_TYPE,
+                      "Found strange node type %d whilst generating code.", (int)n->type);
+    CharBuffer_append(s, "0.0");
+  }
+}
+
+/* the reference's public entry: value[] naming, C flavour */
+static void name_value(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "value[%d]", idx); }
+void generateAST(charBuffer_t *s, const ASTNode_t *node)
+{
+  emit_ctx_t c; c.cuda = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  gen(s, node, &c);
+}
+
+/* helper library shared by both flavours; DEV expands to __device__ __forceinline__ or static inline */
+void generateMacros(charBuffer_t *b)
+{
+  CharBuffer_append(b,
+    "DEV double odes_sqr(double x) { return x * x; }\n"
+    "DEV double odes_acosh(double x) { return log(x + (sqrt(x - 1) * sqrt(x + 1))); }\n"
+    "DEV double odes_asinh(double x) { return log(x + sqrt((x * x) + 1)); }\n"
+    "DEV double odes_atanh(double x) { return (log(1 + x) - log(1 - x)) / 2; }\n"
+    "DEV double odes_acot(double x) { return atan(1. / x); }\n"
+    "DEV double odes_acoth(double x) { return log((x + 1) / (x - 1)) / 2; }\n"
+    "DEV double odes_acsc(double x) { return atan(1 / sqrt((x - 1) * (x + 1))); }\n"
+    "DEV double odes_acsch(double x) { return log(1 / x + sqrt(1 / (x * x) + 1)); }\n"
+    "DEV double odes_asec(double x) { return acos(1 / x); }\n"
+    "DEV double odes_asech(double x) { return odes_acosh(1. / x); }\n"
+    "DEV double odes_cot(double x) { return 1. / tan(x); }\n"
+    "DEV double odes_coth(double x) { return 1 / tanh(x); }\n"
+    "DEV double odes_csc(double x) { return 1. / sin(x); }\n"
+    "DEV double odes_csch(double x) { return 1. / sinh(x); }\n"
+    "DEV double odes_sec(double x) { return 1. / cos(x); }\n"
+    "DEV double odes_sech(double x) { return 1. / cosh(x); }\n"
+    "DEV double odes_logbase(double base, double x) { return log10(x) / log10(base); }\n"
+    "DEV double odes_root(double degree, double x)\n"
+    "{ if (degree == floor(degree) && x < 0 && ((int)degree % 2 != 0)) return -pow(fabs(x), 1. / degree); return pow(x, 1. / degree); }\n"
+    "DEV double odes_factorial(double x) { double r; int j = (int)floor(x); for (r = 1; j > 1; --j) r *= j; return r; }\n");
+}
+
+/* ------------------------------------------------------- host C flavour */
+char *ODEModel_generateCSource(odeModel_t *om)
+{
+  charBuffer_t *b = CharBuffer_create();
+  emit_ctx_t c; int i; char *out;
+  c.cuda = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  if (!om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
+  CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n");
+  generateMacros(b);
+  CharBuffer_append(b, "void ode_f(double t, const double *y, double *ydot, double *value)\n{\n  (void)t;\n");
+  for (i = 0; i < om->neq; i++) cbprintf(b, "  value[%d] = y[%d];\n", i, i);
+  for (i = 0; i < om->nassbeforeodes; i++) {
+    nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
+    cbprintf(b, "  value[%d] = ", o->i); gen(b, o->ij, &c); CharBuffer_append(b, ";\n");
+  }
+  for (i = 0; i < om->neq; i++) { cbprintf(b, "  ydot[%d] = ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "}\nvoid jacobi_f(double t, const double *y, double *J, double *value)\n{\n  (void)t;\n");
+  for (i = 0; i < om->neq; i++) cbprintf(b, "  value[%d] = y[%d];\n", i, i);
+  for (i = 0; i < om->sparsesize; i++) {
+    nonzeroElem_t *nz = om->jacobSparse[i];
+    cbprintf(b, "  J[%d] = ", nz->j * om->neq + nz->i); gen(b, nz->ij, &c); CharBuffer_append(b, ";\n");
+  }
+  CharBuffer_append(b, "}\n");
+  out = b->b; b->b = NULL; CharBuffer_free(b);
+  return out;
+}
+
+/* -------------------------------------------------------- CUDA flavour */
+/* storage classes of value[] entries inside the kernel */
+enum { K_ODE, K_ASSIGNED, K_THREAD, K_UNIFORM };
+typedef struct {
+  const odeModel_t *om;
+  int *kind;          /* [nvalues] storage class                                   */
+  int *slot;          /* [nvalues] K_THREAD: index into pv[]; K_ASSIGNED static: pv slot or -1 */
+  int *local;         /* [nvalues] 1 if an assigned value is a fresh local a[] in this function */
+} kinfo_t;
+
+static void name_cuda(charBuffer_t *s, int idx, const emit_ctx_t *c)
+{
+  const kinfo_t *k = (const kinfo_t *)c->info;
+  const odeModel_t *om = k->om;
+  switch (k->kind[idx]) {
+  case K_ODE: cbprintf(s, "y[%d]", idx); break;
+  case K_ASSIGNED:
+    if (k->local[idx]) cbprintf(s, "a[%d]", idx - om->neq);
+    else cbprintf(s, "pv[%d]", k->slot[idx]);
+    break;
+  case K_THREAD: cbprintf(s, "pv[%d]", k->slot[idx]); break;
+  default: cbprintf(s, "c_base[%d]", idx);
+  }
+}
+
+static void mark_refs(const ASTNode_t *n, int *used)
+{
+  unsigned int i;
+  if (ASTNode_isSetIndex(n)) used[ASTNode_getIndex(n)] = 1;
+  for (i = 0; i < n->nchildren; i++) mark_refs(n->children[i], used);
+}
+
+static void emit_refresh_all(charBuffer_t *b, const odeModel_t *om, const emit_ctx_t *c, const char *indent)
+{
+  int i;
+  for (i = 0; i < om->nass; i++) {
+    nonzeroElem_t *o = om->assignmentOrder[i];
+    cbprintf(b, "%sa[%d] = ", indent, o->i - om->neq); gen(b, o->ij, c); CharBuffer_append(b, ";\n");
+  }
+}
+
+char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
+                                  int nstore, const int *store)
+{
+  int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac;
+  charBuffer_t *b = CharBuffer_create();
+  kinfo_t k; emit_ctx_t c; char *out;
+  int *used_in_ode = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+  int *all_local = (int *)calloc((size_t)nvalues + 1, sizeof(int)), *ode_local = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+
+  if (opt->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
+  usejac = opt->UseJacobian && om->jacobian;
+
+  k.om = om;
+  k.kind = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+  k.slot = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+  k.local = all_local;
+  for (i = 0; i < nvalues; i++) { k.kind[i] = i < om->neq ? K_ODE : i < om->neq + om->nass ? K_ASSIGNED : K_UNIFORM; k.slot[i] = -1; }
+  /* per-trajectory constants: varied inputs and event-assignment targets */
+  for (j = 0; j < nvary; j++) if (vary[j] >= om->neq + om->nass && k.kind[vary[j]] == K_UNIFORM) { k.kind[vary[j]] = K_THREAD; k.slot[vary[j]] = npv++; }
+  for (e = 0; e < om->nevents; e++) for (j = 0; j < om->neventAss[e]; j++) {
+    int idx = om->eventIndex[e][j];
+    if (idx >= om->neq + om->nass && k.kind[idx] == K_UNIFORM) { k.kind[idx] = K_THREAD; k.slot[idx] = npv++; }
+  }
+  /* assigned values read by the ODEs but not recomputed before them keep a per-trajectory slot */
+  for (i = 0; i < om->neq; i++) mark_refs(om->ode[i], used_in_ode);
+  for (i = 0; i < om->nassbeforeodes; i++) { ode_local[om->assignmentsBeforeODEs[i]->i] = 1; mark_refs(om->assignmentsBeforeODEs[i]->ij, used_in_ode); }
+  for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) k.slot[i] = npv++; }
+
+  c.cuda = 1; c.name = name_cuda; c.time = "t"; c.info = &k;
+
+  cbprintf(b, "/* generated by ODEModel_generateCUDASource for model '%s' (sm_100a device functions) */\n",
+           om->simple && om->simple->id ? om->simple->id : "odes");
+  cbprintf(b, "#define NEQ %d\n#define NASS %d\n#define NVAL %d\n#define NEVENTS %d\n#define NPV %d\n#define NVARY %d\n#define NSTORE %d\n#define NNZ %d\n#define HAS_JAC %d\n#define USE_TSTOP %d\n",
+           om->neq, om->nass, nvalues, om->nevents, npv, nvary, nstore, usejac ? om->sparsesize : 0, usejac, (opt->SetTStop || om->npiecewise) ? 1 : 0);
+  cbprintf(b, "#define RESET_ON_EVENT %d\n#define HALT_ON_EVENT %d\n", opt->ResetCvodeOnEvent ? 1 : 0, opt->HaltOnEvent ? 1 : 0);
+  CharBuffer_append(b, "#define A1(n) ((n) > 0 ? (n) : 1)\n#define DEV __device__ __forceinline__\n");
+  CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
+  generateMacros(b);
+  if (usejac) {
+    CharBuffer_append(b, "__device__ const unsigned char NZ_ROW[A1(NNZ)] = {");
+    for (i = 0; i < om->sparsesize; i++) cbprintf(b, "%s%d", i ? "," : "", om->jacobSparse[i]->i);
+    CharBuffer_append(b, "};\n__device__ const unsigned char NZ_COL[A1(NNZ)] = {");
+    for (i = 0; i < om->sparsesize; i++) cbprintf(b, "%s%d", i ? "," : "", om->jacobSparse[i]->j);
+    CharBuffer_append(b, "};\n");
+  }
+
+  /* model_init: uniform base values, then the varied inputs of this trajectory (SoA, batch fastest) */
+  CharBuffer_append(b, "DEV void model_init(double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], const double *__restrict__ vary, size_t stride, size_t set)\n{\n");
+  for (i = 0; i < om->neq; i++) cbprintf(b, "  y[%d] = c_base[%d];\n", i, i);
+  for (i = 0; i < nvalues; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = c_base[%d];\n", k.slot[i], i);
+  for (j = 0; j < nvary; j++) {
+    int idx = vary[j];
+    if (idx < om->neq) cbprintf(b, "  y[%d] = vary[%d * stride + set];\n", idx, j);
+    else if (k.kind[idx] == K_THREAD) cbprintf(b, "  pv[%d] = vary[%d * stride + set];\n", k.slot[idx], j);
+  }
+  CharBuffer_append(b, "  (void)vary; (void)stride; (void)set; (void)pv; (void)y;\n}\n");
+
+  /* refresh of all assignment rules; static ones are written back to their slots */
+  CharBuffer_append(b, "DEV void rules_all(double t, const double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], double (&a)[A1(NASS)])\n{\n  (void)t; (void)y; (void)pv; (void)a;\n");
+  k.local = all_local;
+  emit_refresh_all(b, om, &c, "  ");
+  for (i = om->neq; i < om->neq + om->nass; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = a[%d];\n", k.slot[i], i - om->neq);
+  CharBuffer_append(b, "}\n");
+
+  /* ode_f: rules needed by the ODEs in topological order, then the right-hand sides */
+  CharBuffer_append(b, "DEV void ode_f(double t, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)], double (&ydot)[A1(NEQ)])\n{\n  double a[A1(NASS)]; (void)t; (void)pv; (void)a;\n");
+  k.local = ode_local;
+  for (i = 0; i < om->nassbeforeodes; i++) {
+    nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
+    cbprintf(b, "  a[%d] = ", o->i - om->neq); gen(b, o->ij, &c); CharBuffer_append(b, ";\n");
+  }
+  for (i = 0; i < om->neq; i++) { cbprintf(b, "  ydot[%d] = ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "}\n");
+
+  /* jacobi_f: structurally non-zero entries in jacobSparse order (rules are inlined) */
+  CharBuffer_append(b, "DEV void jacobi_f(double t, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)], double (&jnz)[A1(NNZ)])\n{\n  (void)t; (void)pv; (void)y; (void)jnz;\n");
+  k.local = ode_local;
+  if (usejac) for (i = 0; i < om->sparsesize; i++) { cbprintf(b, "  jnz[%d] = ", i); gen(b, om->jacobSparse[i]->ij, &c); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "}\n");
+
+  /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
+  CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
+                       "  unsigned int fired = 0; double a[A1(NASS)]; (void)t; (void)a; (void)y; (void)pv; (void)trigger; (void)reinit;\n");
+  k.local = all_local;
+  if (om->nevents > 0) {
+    emit_refresh_all(b, om, &c, "  ");
+    for (e = 0; e < om->nevents; e++) {
+      cbprintf(b, "  if (trigger[%d] == 0) {\n    if ((", e); gen(b, om->event[e], &c); cbprintf(b, ") != 0.0) {\n      fired |= %uu; trigger[%d] = 1;\n", 1u << e, e);
+      for (j = 0; j < om->neventAss[e]; j++) {
+        int idx = om->eventIndex[e][j];
+        if (idx >= om->neq && idx < om->neq + om->nass) continue;       /* assigned values cannot be set */
+        CharBuffer_append(b, "      { const double r = "); gen(b, om->eventAssignment[e][j], &c); CharBuffer_append(b, "; ");
+        if (idx < om->neq) cbprintf(b, "y[%d] = r; reinit = 1; }\n", idx);
+        else cbprintf(b, "pv[%d] = r; if (RESET_ON_EVENT) reinit = 1; }\n", k.slot[idx]);
+        emit_refresh_all(b, om, &c, "      ");
+      }
+      cbprintf(b, "    }\n  } else if (!((", e); gen(b, om->event[e], &c); cbprintf(b, ") != 0.0)) trigger[%d] = 0;\n", e);
+    }
+    for (i = om->neq; i < om->neq + om->nass; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = a[%d];\n", k.slot[i], i - om->neq);
+  }
+  CharBuffer_append(b, "  return fired;\n}\n");
+
+  /* store_row: refresh all rules, write the selected values (coalesced: consecutive sets are consecutive addresses) */
+  CharBuffer_append(b, "DEV void store_row(double *__restrict__ row, size_t stride, double t, const double (&y)[A1(NEQ)], double (&pv)[A1(NPV)])\n{\n  double a[A1(NASS)]; (void)t; (void)a; (void)pv; (void)y;\n");
+  {
+    int need_rules = 0;
+    for (j = 0; j < nstore; j++) if (store[j] >= om->neq && store[j] < om->neq + om->nass) need_rules = 1;
+    if (need_rules) emit_refresh_all(b, om, &c, "  ");
+    for (j = 0; j < nstore; j++) { cbprintf(b, "  row[%d * stride] = ", j); name_cuda(b, store[j], &c); CharBuffer_append(b, ";\n"); }
+  }
+  CharBuffer_append(b, "}\n");
+  /* row 0: values after initial assignments with the model's own parameters, varied entries overwritten
+     (setVariableValue at t == 0 patches results->value[idx][0] only, integratorInstance.c:1571-1572) */
+  CharBuffer_append(b, "DEV void store_row0(double *__restrict__ row, size_t stride, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)])\n{\n  (void)y; (void)pv;\n");
+  for (j = 0; j < nstore; j++) {
+    int idx = store[j], varied = 0, jj;
+    for (jj = 0; jj < nvary; jj++) if (vary[jj] == idx) varied = 1;
+    cbprintf(b, "  row[%d * stride] = ", j);
+    if (varied && idx < om->neq) cbprintf(b, "y[%d]", idx);
+    else if (varied && k.kind[idx] == K_THREAD) cbprintf(b, "pv[%d]", k.slot[idx]);
+    else cbprintf(b, "c_base[%d]", idx);
+    CharBuffer_append(b, ";\n");
+  }
+  CharBuffer_append(b, "}\n");
+
+  free(k.kind); free(k.slot); free(used_in_ode); free(all_local); free(ode_local);
+  out = b->b; b->b = NULL; CharBuffer_free(b);
+  return out;
+}
