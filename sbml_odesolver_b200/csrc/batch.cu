@@ -1,0 +1,638 @@
+/*
+ * batch.cu -- the device side of the C ABI: run-time compilation of the model
+ * kernel (NVRTC -> sm_100a cubin -> driver module), device buffers in
+ * structure-of-arrays layout, launches, result gathering.
+ *
+ * Reference seams this file replaces:
+ *   src/compiler.c:428-509   Compiler_compile / CompiledCode_getFunction / CompiledCode_free
+ *                            (g++ -shared + dlopen)  -> NVRTC + cuModuleLoadData
+ *   src/odeModel.c:3191-3299 ODEModel_compileCVODEFunctions (assemble TU, compile, look up ode_f...)
+ *   src/odeSolver.c:313-330  the serial design-point loop -> ODESBatch_integrate (one launch)
+ * No CPU fallback exists: every entry that needs the device fails with
+ * SOLVER_ERROR_CUDA_UNAVAILABLE when there is none.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <string>
+#include <vector>
+#include "sbmlsolver/batchIntegrator.h"
+#include "sbmlsolver/processAST.h"
+#include "sbmlsolver/solverError.h"
+
+extern "C" const char odes_bdf_kernel_source[];     /* bdf_kernel.cuh embedded as text (kernel_text.c) */
+
+/* argument block of the kernel; must match struct OdesArgs in bdf_kernel.cuh */
+struct OdesArgs {
+  const double *vary; double *out; int *status; int *stats; unsigned int *fired; const double *tpoints;
+  unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
+};
+
+/* --------------------------------------------------------------- driver API */
+static struct {
+  int ready;
+  CUresult (*ModuleLoadData)(CUmodule *, const void *);
+  CUresult (*ModuleUnload)(CUmodule);
+  CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+  CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *);
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+  CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+  CUresult (*MemcpyHtoD)(CUdeviceptr, const void *, size_t);
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t);
+} drv;
+
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "%s failed: %s", #call, cudaGetErrorString(e_)); return 0; } } while (0)
+#define DRV_OK(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { \
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "%s failed with CUresult %d", #call, (int)r_); return 0; } } while (0)
+
+static int load_driver(void)
+{
+  if (drv.ready) return 1;
+#define GET(field, name) do { void *p = NULL; cudaDriverEntryPointQueryResult q; \
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p) { \
+      SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_UNAVAILABLE, "CUDA driver entry point %s unavailable", name); return 0; } \
+    *(void **)(&drv.field) = p; } while (0)
+  GET(ModuleLoadData, "cuModuleLoadData");
+  GET(ModuleUnload, "cuModuleUnload");
+  GET(ModuleGetFunction, "cuModuleGetFunction");
+  GET(ModuleGetGlobal, "cuModuleGetGlobal");
+  GET(FuncSetAttribute, "cuFuncSetAttribute");
+  GET(FuncGetAttribute, "cuFuncGetAttribute");
+  GET(LaunchKernel, "cuLaunchKernel");
+  GET(MemcpyHtoD, "cuMemcpyHtoD");
+  GET(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+#undef GET
+  drv.ready = 1;
+  return 1;
+}
+
+extern "C" int ODES_deviceCount(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int ODES_deviceName(int device, char *buf, int len)
+{
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+  snprintf(buf, (size_t)len, "%s", p.name);
+  return 1;
+}
+static int need_device(int device)
+{
+  if (ODES_deviceCount() <= device) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_UNAVAILABLE,
+                      "no CUDA device %d available: the batched integrator has no CPU fallback", device);
+    return 0;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaFree(0));                       /* primary context */
+  return load_driver();
+}
+
+/* ----------------------------------------------------------- code-gen seam */
+static unsigned long long fnv1a(const char *s, unsigned long long h)
+{
+  for (; *s; s++) { h ^= (unsigned char)*s; h *= 1099511628211ULL; }
+  return h;
+}
+static std::string cache_dir(void)
+{
+  const char *env = getenv("ODES_B200_CACHE");
+  if (env && *env) return env;
+  Dl_info info;
+  if (dladdr((void *)&cache_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t k = p.rfind('/');
+    return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/_cache";
+  }
+  return "/tmp/odes_b200_cache";
+}
+
+static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+
+/* Compiles a CUDA translation unit for sm_100a.  Same three-call shape as the reference
+   (Compiler_compile / CompiledCode_getFunction / CompiledCode_free); extra NVRTC options are
+   passed in a leading "//!opts: ..." line of the source. */
+extern "C" compiled_code_t *Compiler_compile(const char *sourceCode)
+{
+  std::vector<std::string> opts;
+  opts.push_back("--gpu-architecture=sm_100a");
+  opts.push_back("-lineinfo");
+  opts.push_back("--std=c++17");
+  opts.push_back("-default-device");
+  if (strncmp(sourceCode, "//!opts:", 8) == 0) {
+    const char *e = strchr(sourceCode, '\n');
+    std::string line(sourceCode + 8, e ? (size_t)(e - sourceCode - 8) : strlen(sourceCode + 8));
+    size_t pos = 0;
+    while (pos < line.size()) {
+      while (pos < line.size() && line[pos] == ' ') pos++;
+      size_t end = line.find(' ', pos);
+      if (end == std::string::npos) end = line.size();
+      if (end > pos) opts.push_back(line.substr(pos, end - pos));
+      pos = end;
+    }
+  }
+  compiled_code_t *code = (compiled_code_t *)calloc(1, sizeof *code);
+  code->source = strdup(sourceCode);
+
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  unsigned long long h = fnv1a(sourceCode, 1469598103934665603ULL);
+  for (size_t i = 0; i < opts.size(); i++) h = fnv1a(opts[i].c_str(), h);
+  h = h * 1099511628211ULL + (unsigned long long)(major * 100 + minor);
+  char name[64]; snprintf(name, sizeof name, "/%016llx.cubin", h);
+  std::string dir = cache_dir(), path = dir + name;
+
+  if (!env_int("ODES_B200_NOCACHE", 0)) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (f) {
+      fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+      if (n > 0) {
+        code->cubin = malloc((size_t)n);
+        if (fread(code->cubin, 1, (size_t)n, f) == (size_t)n) { code->cubinSize = (unsigned long)n; code->log = strdup("(loaded from cache)"); fclose(f); return code; }
+        free(code->cubin); code->cubin = NULL;
+      }
+      fclose(f);
+    }
+  }
+
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, sourceCode, "odes_model.cu", 0, NULL, NULL) != NVRTC_SUCCESS) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_COMPILATION_FAILED, "nvrtcCreateProgram failed");
+    CompiledCode_free(code); return NULL;
+  }
+  std::vector<const char *> copts;
+  for (size_t i = 0; i < opts.size(); i++) copts.push_back(opts[i].c_str());
+  nvrtcResult res = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+  size_t logSize = 0; nvrtcGetProgramLogSize(prog, &logSize);
+  code->log = (char *)calloc(logSize + 1, 1);
+  if (logSize > 1) nvrtcGetProgramLog(prog, code->log);
+  if (res != NVRTC_SUCCESS) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_COMPILATION_FAILED, "NVRTC compilation failed (%s):\n%.1500s", nvrtcGetErrorString(res), code->log);
+    nvrtcDestroyProgram(&prog); CompiledCode_free(code); return NULL;
+  }
+  size_t n = 0; nvrtcGetCUBINSize(prog, &n);
+  code->cubin = malloc(n); code->cubinSize = (unsigned long)n;
+  nvrtcGetCUBIN(prog, (char *)code->cubin);
+  nvrtcDestroyProgram(&prog);
+
+  if (!env_int("ODES_B200_NOCACHE", 0)) {
+    mkdir(dir.c_str(), 0777);
+    std::string tmp = path + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (f) { fwrite(code->cubin, 1, n, f); fclose(f); rename(tmp.c_str(), path.c_str()); }
+  }
+  return code;
+}
+
+/* Loads the module on the current device at first use and returns the kernel (CUfunction). */
+extern "C" void *CompiledCode_getFunction(compiled_code_t *code, const char *symbol)
+{
+  CUfunction fn = NULL;
+  if (!code || !code->cubin) return NULL;
+  if (!load_driver()) return NULL;
+  if (!code->module) {
+    CUmodule m;
+    CUresult r = drv.ModuleLoadData(&m, code->cubin);
+    if (r != CUDA_SUCCESS) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_DLL_LOAD_FAILED, "cuModuleLoadData failed with CUresult %d", (int)r); return NULL; }
+    code->module = m;
+  }
+  if (drv.ModuleGetFunction(&fn, (CUmodule)code->module, symbol) != CUDA_SUCCESS) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_GET_PROC_ADDRESS_FAILED, "kernel %s not found in compiled module", symbol);
+    return NULL;
+  }
+  return (void *)fn;
+}
+extern "C" void CompiledCode_free(compiled_code_t *code)
+{
+  if (!code) return;
+  if (code->module && drv.ready) drv.ModuleUnload((CUmodule)code->module);
+  free(code->cubin); free(code->log); free(code->source); free(code);
+}
+
+/* ------------------------------------------------------------- static kernels */
+/* Philox4x32-10 (Salmon et al. 2011), counter = (set, j), key = seed */
+__device__ __forceinline__ void philox_round(unsigned int (&c)[4], unsigned int k0, unsigned int k1)
+{
+  const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const unsigned int n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ double philox_uniform(unsigned long long seed, unsigned long long set, unsigned int j)
+{
+  unsigned int c[4] = {(unsigned int)set, (unsigned int)(set >> 32), j, 0u};
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  const unsigned long long bits = ((unsigned long long)c[0] << 32) | c[1];
+  return (double)(bits >> 11) * (1.0 / 9007199254740992.0);          /* [0,1) with 53 bits */
+}
+__global__ void odes_generate_values_kernel(double *vary, size_t stride, int nsets, int nvary, unsigned long long seed,
+                                            long long firstSet, const double *base, const double *lo, const double *hi, int log10Scale)
+{
+  const size_t set = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= (size_t)nsets) return;
+  for (int j = 0; j < nvary; j++) {
+    const double u = lo[j] + (hi[j] - lo[j]) * philox_uniform(seed, (unsigned long long)(firstSet + (long long)set), (unsigned int)j);
+    vary[(size_t)j * stride + set] = log10Scale ? base[j] * pow(10.0, u) : base[j] * exp2(u);
+  }
+}
+/* host layout [nsets][nvary] (varySettings rows) -> SoA [nvary][stride] */
+__global__ void odes_rows_to_soa_kernel(const double *rows, double *vary, size_t stride, int nsets, int nvary)
+{
+  const size_t set = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= (size_t)nsets) return;
+  for (int j = 0; j < nvary; j++) vary[(size_t)j * stride + set] = rows[set * (size_t)nvary + j];
+}
+/* FP64 FMA throughput probe: 8 independent chains per thread */
+__global__ void odes_fp64_peak_kernel(double *out, int iters)
+{
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+extern "C" double ODES_measureFP64Peak(int device, int repeats)
+{
+  if (!need_device(device)) return 0.0;
+  cudaDeviceProp p; if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return 0.0;
+  const int threads = 256, blocks = p.multiProcessorCount * 8, iters = 1 << 16;
+  double *out = NULL; cudaEvent_t e0, e1; float best = 1e30f;
+  if (cudaMalloc(&out, (size_t)threads * blocks * sizeof(double)) != cudaSuccess) return 0.0;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int r = 0; r < repeats + 1; r++) {
+    cudaEventRecord(e0);
+    odes_fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  const double flop = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  return flop / (best * 1e-3) / 1e12;
+}
+
+/* ------------------------------------------------------------------ the plan */
+struct odesBatch {
+  odeModel_t *om; cvodeSettings_t *opt;
+  int device, nvary, nstore, nout, nvalues;
+  std::vector<int> vary, store;
+  compiled_code_t *code; CUfunction kernel;
+  int block, minblocks, matLocal; size_t smemBytes;
+  int capacity;
+  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired;
+  size_t rowsCap;
+  cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, evIn[2], evK[2], evOut[2];
+  float lastMs; int launches;
+  std::vector<double> base; std::vector<int> trigger0;
+};
+
+/* values after CvodeData_initialize with the model's own parameters (uniform for the whole batch) */
+static int compute_base(odeModel_t *om, cvodeSettings_t *opt, std::vector<double> &base, std::vector<int> &trig)
+{
+  cvodeData_t *data = CvodeData_create(om);
+  int store = opt->StoreResults;
+  if (!data) return 0;
+  opt->StoreResults = 0;
+  CvodeData_initialize(data, opt, om, 0);
+  opt->StoreResults = store;
+  base.assign(data->value, data->value + data->nvalues);
+  trig.assign(data->trigger, data->trigger + om->nevents);
+  CvodeData_free(data);
+  return 1;
+}
+
+extern "C" void ODESBatch_free(odesBatch_t *b)
+{
+  if (!b) return;
+  if (ODES_deviceCount() > b->device) {
+    cudaSetDevice(b->device);
+    cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
+    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copyIn) cudaStreamDestroy(b->copyIn);
+    if (b->copyOut) cudaStreamDestroy(b->copyOut);
+    if (b->e0) cudaEventDestroy(b->e0);
+    if (b->e1) cudaEventDestroy(b->e1);
+    for (int i = 0; i < 2; i++) { if (b->evIn[i]) cudaEventDestroy(b->evIn[i]); if (b->evK[i]) cudaEventDestroy(b->evK[i]); if (b->evOut[i]) cudaEventDestroy(b->evOut[i]); }
+  }
+  CompiledCode_free(b->code);
+  delete b;
+}
+
+static std::string build_source(odesBatch_t *b)
+{
+  char *model = ODEModel_generateCUDASource(b->om, b->opt, b->nvary, b->vary.data(), b->nstore, b->store.data());
+  const int neq = b->om->neq;
+  const int usejac = b->opt->UseJacobian && b->om->jacobian;
+  int npv = 0;
+  { const char *q = strstr(model, "#define NPV "); if (q) npv = atoi(q + 12); }
+  /* per-thread shared-memory words: M, saved Jacobian, LU rhs, zn[2..5], per-trajectory constants (bdf_kernel.cuh) */
+  const int words = neq * neq + (usejac ? b->om->sparsesize : neq * neq) + neq + 4 * neq + npv + neq + 19;
+  b->block = env_int("ODES_BLOCK", 64);
+  b->matLocal = env_int("ODES_MAT_LOCAL", (size_t)words * 8 * (size_t)b->block > 110 * 1024 ? 1 : 0);
+  b->smemBytes = b->matLocal ? 0 : (size_t)words * 8 * (size_t)b->block;
+  int fit = b->smemBytes ? (int)((227 * 1024) / (b->smemBytes + 1024)) : 8;
+  int want = env_int("ODES_THREADS_PER_SM", 128) / b->block;
+  b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
+  char head[512];
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d%s\n",
+           env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
+           env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
+  std::string src = head;
+  src += model;
+  src += odes_bdf_kernel_source;
+  free(model);
+  return src;
+}
+
+extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex,
+                                          int nstore, const int *storeIndex, int device)
+{
+  if (!om || !opt) return NULL;
+  if (om->hasCycle) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_ODE_MODEL_CYCLIC_DEPENDENCY_IN_RULES, "model rules contain a cycle"); return NULL; }
+  if (opt->Indefinitely || !opt->TimePoints) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "batched integration needs a finite output grid"); return NULL; }
+  if (opt->CvodeMethod != 0 || opt->IterMethod != 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the batched kernel implements BDF with Newton iteration only"); return NULL; }
+  if (om->nevents > 32) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "at most 32 events are supported"); return NULL; }
+  odesBatch_t *b = new odesBatch();
+  b->om = om; b->opt = opt; b->device = device; b->nvary = nvary; b->nout = opt->PrintStep;
+  b->nvalues = om->neq + om->nass + om->nconst;
+  for (int j = 0; j < nvary; j++) {
+    if (varyIndex[j] < 0 || varyIndex[j] >= b->nvalues) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "varied index %d out of range", varyIndex[j]); delete b; return NULL; }
+    b->vary.push_back(varyIndex[j]);
+  }
+  if (storeIndex) { for (int j = 0; j < nstore; j++) b->store.push_back(storeIndex[j]); b->nstore = nstore; }
+  else { for (int j = 0; j < b->nvalues; j++) b->store.push_back(j); b->nstore = b->nvalues; }
+  if (opt->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
+  if (!compute_base(om, opt, b->base, b->trigger0)) { delete b; return NULL; }
+
+  /* code generation + compilation need no device (NVRTC targets sm_100a explicitly) */
+  std::string src = build_source(b);
+  b->code = Compiler_compile(src.c_str());
+  if (!b->code) { delete b; return NULL; }
+  return b;
+}
+
+static int ensure_loaded(odesBatch_t *b)
+{
+  if (b->kernel) { CUDA_OK(cudaSetDevice(b->device)); return 1; }
+  if (!need_device(b->device)) return 0;
+  b->kernel = (CUfunction)CompiledCode_getFunction(b->code, "odes_bdf_kernel");
+  if (!b->kernel) return 0;
+  CUdeviceptr sym; size_t bytes;
+  DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_base"));
+  if (b->nvalues > 0) DRV_OK(drv.MemcpyHtoD(sym, b->base.data(), sizeof(double) * (size_t)b->nvalues));
+  DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
+  if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
+  if (b->smemBytes > 48 * 1024) DRV_OK(drv.FuncSetAttribute(b->kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)b->smemBytes));
+  CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&b->copyIn, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&b->copyOut, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&b->e0)); CUDA_OK(cudaEventCreate(&b->e1));
+  for (int i = 0; i < 2; i++) {
+    CUDA_OK(cudaEventCreateWithFlags(&b->evIn[i], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&b->evK[i], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&b->evOut[i], cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * (size_t)(b->opt->PrintStep + 1)));
+  CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
+  return 1;
+}
+
+extern "C" int ODESBatch_reserve(odesBatch_t *b, int capacity)
+{
+  if (!ensure_loaded(b)) return 0;
+  if (capacity <= b->capacity) return 1;
+  capacity = (capacity + 31) & ~31;            /* rows start 256-byte aligned */
+  cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired);
+  b->d_vary = b->d_out = NULL; b->d_status = b->d_stats = NULL; b->d_fired = NULL; b->capacity = 0;
+  const size_t cap = (size_t)capacity;
+  CUDA_OK(cudaMalloc(&b->d_vary, sizeof(double) * cap * (size_t)(b->nvary > 0 ? b->nvary : 1)));
+  CUDA_OK(cudaMalloc(&b->d_out, sizeof(double) * cap * (size_t)(b->opt->PrintStep + 1) * (size_t)(b->nstore > 0 ? b->nstore : 1)));
+  CUDA_OK(cudaMalloc(&b->d_status, sizeof(int) * cap));
+  CUDA_OK(cudaMalloc(&b->d_stats, sizeof(int) * cap * ODES_NUM_STATS));
+  CUDA_OK(cudaMalloc(&b->d_fired, sizeof(unsigned int) * cap * (size_t)(b->opt->PrintStep + 1)));
+  b->capacity = capacity;
+  return 1;
+}
+/* private: restart support for the single-instance driver (integrator.c) */
+extern "C" int ODESBatch_setTimeGrid(odesBatch_t *b, int nout, const double *tpoints)
+{
+  if (!ensure_loaded(b)) return 0;
+  if (nout > b->opt->PrintStep || nout < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "time grid longer than the plan's"); return 0; }
+  CUDA_OK(cudaMemcpy(b->d_tpoints, tpoints, sizeof(double) * (size_t)(nout + 1), cudaMemcpyHostToDevice));
+  b->nout = nout;
+  return 1;
+}
+extern "C" int ODESBatch_setInitialTriggers(odesBatch_t *b, const int *trigger)
+{
+  if (!ensure_loaded(b)) return 0;
+  if (b->om->nevents > 0) {
+    CUdeviceptr sym; size_t bytes;
+    DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
+    DRV_OK(drv.MemcpyHtoD(sym, trigger, sizeof(int) * (size_t)b->om->nevents));
+  }
+  return 1;
+}
+extern "C" int ODESBatch_getCapacity(const odesBatch_t *b) { return b->capacity; }
+extern "C" int ODESBatch_getNout(const odesBatch_t *b) { return b->nout + 1; }
+extern "C" int ODESBatch_getNstore(const odesBatch_t *b) { return b->nstore; }
+extern "C" const char *ODESBatch_getSource(const odesBatch_t *b) { return b->code ? b->code->source : NULL; }
+extern "C" const char *ODESBatch_getCompileLog(const odesBatch_t *b) { return b->code ? b->code->log : NULL; }
+extern "C" double *ODESBatch_deviceValues(odesBatch_t *b) { return b->d_vary; }
+extern "C" double *ODESBatch_deviceResults(odesBatch_t *b) { return b->d_out; }
+extern "C" float ODESBatch_getLastKernelMs(const odesBatch_t *b) { return b->lastMs; }
+extern "C" int ODESBatch_getNumLaunches(const odesBatch_t *b) { return b->launches; }
+
+extern "C" int ODESBatch_getKernelInfo(const odesBatch_t *cb, int *regs, int *smem, int *local, int *threads, int *blocksPerSM)
+{
+  odesBatch_t *b = (odesBatch_t *)cb;
+  if (!ensure_loaded(b)) return 0;
+  int v = 0;
+  if (regs) { DRV_OK(drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, b->kernel)); *regs = v; }
+  if (local) { DRV_OK(drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, b->kernel)); *local = v; }
+  if (smem) *smem = (int)b->smemBytes;
+  if (threads) *threads = b->block;
+  if (blocksPerSM) { DRV_OK(drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, b->kernel, b->block, b->smemBytes)); *blocksPerSM = v; }
+  return 1;
+}
+
+extern "C" int ODESBatch_setValues(odesBatch_t *b, int nsets, const double *values)
+{
+  if (!ODESBatch_reserve(b, nsets)) return 0;
+  if (b->nvary == 0 || nsets == 0) return 1;
+  const size_t n = (size_t)nsets * (size_t)b->nvary;
+  if (n > b->rowsCap) { cudaFree(b->d_rows); b->d_rows = NULL; CUDA_OK(cudaMalloc(&b->d_rows, n * sizeof(double))); b->rowsCap = n; }
+  CUDA_OK(cudaMemcpyAsync(b->d_rows, values, n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  odes_rows_to_soa_kernel<<<(nsets + 255) / 256, 256, 0, b->stream>>>(b->d_rows, b->d_vary, (size_t)b->capacity, nsets, b->nvary);
+  CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long long seed, long long firstSet,
+                                        const double *base, const double *lo, const double *hi, int log10Scale)
+{
+  if (!ODESBatch_reserve(b, nsets)) return 0;
+  if (b->nvary == 0 || nsets == 0) return 1;
+  double *d = NULL;
+  CUDA_OK(cudaMalloc(&d, 3 * sizeof(double) * (size_t)b->nvary));
+  CUDA_OK(cudaMemcpy(d, base, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d + b->nvary, lo, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d + 2 * b->nvary, hi, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
+  odes_generate_values_kernel<<<(nsets + 255) / 256, 256, 0, b->stream>>>(b->d_vary, (size_t)b->capacity, nsets, b->nvary, seed, firstSet,
+                                                                         d, d + b->nvary, d + 2 * b->nvary, log10Scale);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  cudaFree(d);
+  return 1;
+}
+
+static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed)
+{
+  OdesArgs a;
+  a.vary = b->d_vary + offset; a.out = b->d_out + offset; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
+  a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
+  a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;
+  a.reltol = b->opt->RError; a.abstol = b->opt->Error;
+  void *params[] = { &a };
+  const unsigned grid = (unsigned)((nsets + b->block - 1) / b->block);
+  if (timed) CUDA_OK(cudaEventRecord(b->e0, stream));
+  DRV_OK(drv.LaunchKernel(b->kernel, grid, 1, 1, (unsigned)b->block, 1, 1, (unsigned)b->smemBytes, (CUstream)stream, params, NULL));
+  if (timed) CUDA_OK(cudaEventRecord(b->e1, stream));
+  b->launches++;
+  return 1;
+}
+
+extern "C" int ODESBatch_integrate(odesBatch_t *b, int nsets)
+{
+  if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  if (!ensure_loaded(b)) return 0;
+  if (nsets == 0) return 1;
+  return launch(b, nsets, 0, b->stream, 1);
+}
+extern "C" int ODESBatch_synchronize(odesBatch_t *b)
+{
+  if (!b->stream) return 1;
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (b->launches) { float ms = 0; if (cudaEventElapsedTime(&ms, b->e0, b->e1) == cudaSuccess) b->lastMs = ms; else cudaGetLastError(); }
+  return 1;
+}
+
+extern "C" int ODESBatch_getResults(odesBatch_t *b, int nsets, double *results)
+{
+  CUDA_OK(cudaSetDevice(b->device));
+  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  CUDA_OK(cudaMemcpy2DAsync(results, sizeof(double) * (size_t)nsets, b->d_out, sizeof(double) * (size_t)b->capacity,
+                            sizeof(double) * (size_t)nsets, rows, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return 1;
+}
+extern "C" int ODESBatch_getTrajectory(odesBatch_t *b, int set, double *traj)
+{
+  CUDA_OK(cudaSetDevice(b->device));
+  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  CUDA_OK(cudaMemcpy2D(traj, sizeof(double), b->d_out + set, sizeof(double) * (size_t)b->capacity, sizeof(double), rows, cudaMemcpyDeviceToHost));
+  return 1;
+}
+extern "C" int ODESBatch_getStatus(odesBatch_t *b, int nsets, int *status)
+{
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaMemcpy(status, b->d_status, sizeof(int) * (size_t)nsets, cudaMemcpyDeviceToHost));
+  return 1;
+}
+extern "C" int ODESBatch_getStats(odesBatch_t *b, int nsets, int *stats)
+{
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaMemcpy2D(stats, sizeof(int) * (size_t)nsets, b->d_stats, sizeof(int) * (size_t)b->capacity, sizeof(int) * (size_t)nsets, ODES_NUM_STATS, cudaMemcpyDeviceToHost));
+  return 1;
+}
+extern "C" int ODESBatch_getEventLog(odesBatch_t *b, int nsets, unsigned int *fired)
+{
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaMemcpy2D(fired, sizeof(unsigned int) * (size_t)nsets, b->d_fired, sizeof(unsigned int) * (size_t)b->capacity,
+                       sizeof(unsigned int) * (size_t)nsets, (size_t)(b->nout + 1), cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+/* End-to-end helper with HOST buffers: the batch is cut into chunks; H2D of chunk k+1, the kernel of
+   chunk k and D2H of chunk k-1 overlap on three streams.  values: [nsets][nvary] rows,
+   results: [nout+1][nstore][nsets]. */
+extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
+{
+  if (!ODESBatch_reserve(b, nsets)) return 0;
+  if (chunk <= 0) chunk = 1 << 16;
+  chunk = (chunk + 31) & ~31;
+  const int nchunks = (nsets + chunk - 1) / chunk;
+  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  const size_t need = (size_t)nsets * (size_t)(b->nvary > 0 ? b->nvary : 1);
+  if (need > b->rowsCap) { cudaFree(b->d_rows); b->d_rows = NULL; CUDA_OK(cudaMalloc(&b->d_rows, need * sizeof(double))); b->rowsCap = need; }
+  for (int k = 0; k < nchunks; k++) {
+    const size_t off = (size_t)k * (size_t)chunk;
+    const int n = (int)((size_t)nsets - off < (size_t)chunk ? (size_t)nsets - off : (size_t)chunk);
+    const int slot = k & 1;
+    if (b->nvary > 0) {
+      CUDA_OK(cudaMemcpyAsync(b->d_rows + off * (size_t)b->nvary, values + off * (size_t)b->nvary, sizeof(double) * (size_t)n * (size_t)b->nvary, cudaMemcpyHostToDevice, b->copyIn));
+      odes_rows_to_soa_kernel<<<(n + 255) / 256, 256, 0, b->copyIn>>>(b->d_rows + off * (size_t)b->nvary, b->d_vary + off, (size_t)b->capacity, n, b->nvary);
+    }
+    CUDA_OK(cudaEventRecord(b->evIn[slot], b->copyIn));
+    CUDA_OK(cudaStreamWaitEvent(b->stream, b->evIn[slot], 0));
+    if (!launch(b, n, off, b->stream, k == 0)) return 0;
+    CUDA_OK(cudaEventRecord(b->evK[slot], b->stream));
+    CUDA_OK(cudaStreamWaitEvent(b->copyOut, b->evK[slot], 0));
+    if (results)
+      CUDA_OK(cudaMemcpy2DAsync(results + off, sizeof(double) * (size_t)nsets, b->d_out + off, sizeof(double) * (size_t)b->capacity,
+                                sizeof(double) * (size_t)n, rows, cudaMemcpyDeviceToHost, b->copyOut));
+    if (status) CUDA_OK(cudaMemcpyAsync(status + off, b->d_status + off, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, b->copyOut));
+  }
+  CUDA_OK(cudaStreamSynchronize(b->copyOut));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return 1;
+}
+
+/* pinned host buffers for callers that want full-speed host<->device copies */
+extern "C" void *ODES_hostAlloc(size_t bytes) { void *p = NULL; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; } return p; }
+extern "C" void ODES_hostFree(void *p) { if (p) cudaFreeHost(p); }
+
+/* one-shot drop-in for the reference's batch loop */
+extern "C" int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
+                                                 const double *values, double *out, int *status)
+{
+  if (!ii || nsets < 0) return -1;
+  std::vector<int> idx;
+  for (int j = 0; j < nvary; j++) idx.push_back(vi[j]->index);
+  odesBatch_t *b = ODESBatch_create(ii->om, ii->opt, nvary, idx.data(), 0, NULL, 0);
+  if (!b) return -1;
+  int failed = -1;
+  std::vector<int> st((size_t)nsets);
+  std::vector<double> soa;
+  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  if (out) soa.resize(rows * (size_t)nsets);
+  if (ODESBatch_runHost(b, nsets, values, out ? soa.data() : NULL, st.data(), 0)) {
+    failed = 0;
+    for (int s = 0; s < nsets; s++) { if (st[(size_t)s] < 0) failed++; if (status) status[s] = st[(size_t)s]; }
+    if (out)                                     /* [rows][nsets] -> [nsets][nout+1][nvalues] */
+      for (size_t r = 0; r < rows; r++) for (int s = 0; s < nsets; s++) out[(size_t)s * rows + r] = soa[r * (size_t)nsets + (size_t)s];
+  }
+  ODESBatch_free(b);
+  return failed;
+}
+
+extern "C" void ODEModel_freeKernelCache(odeModel_t *om) { (void)om; }
+extern "C" int ODEModel_compileCVODEFunctions(odeModel_t *om)
+{
+  /* kept for API compatibility: compilation happens per (model, varied set) in ODESBatch_create */
+  return om != NULL;
+}

@@ -367,18 +367,17 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
            om->neq, om->nass, nvalues, om->nevents, npv, nvary, nstore, usejac ? om->sparsesize : 0, usejac, (opt->SetTStop || om->npiecewise) ? 1 : 0);
   cbprintf(b, "#define RESET_ON_EVENT %d\n#define HALT_ON_EVENT %d\n", opt->ResetCvodeOnEvent ? 1 : 0, opt->HaltOnEvent ? 1 : 0);
   CharBuffer_append(b, "#define A1(n) ((n) > 0 ? (n) : 1)\n#define DEV __device__ __forceinline__\n");
+  /* per-trajectory constants live in strided shared memory (word k of this thread at p[k*s]) */
+  CharBuffer_append(b, "struct PvRef { double *p; unsigned int s; DEV double &operator[](int k) const { return p[(size_t)k * s]; } };\n");
   CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
   generateMacros(b);
-  if (usejac) {
-    CharBuffer_append(b, "__device__ const unsigned char NZ_ROW[A1(NNZ)] = {");
-    for (i = 0; i < om->sparsesize; i++) cbprintf(b, "%s%d", i ? "," : "", om->jacobSparse[i]->i);
-    CharBuffer_append(b, "};\n__device__ const unsigned char NZ_COL[A1(NNZ)] = {");
-    for (i = 0; i < om->sparsesize; i++) cbprintf(b, "%s%d", i ? "," : "", om->jacobSparse[i]->j);
-    CharBuffer_append(b, "};\n");
-  }
+  /* scatter of the saved sparse Jacobian into M = -gamma*J (diagonal +1 is added by the kernel) */
+  CharBuffer_append(b, "#define ODES_SCATTER_J(mg)");
+  if (usejac) for (i = 0; i < om->sparsesize; i++) cbprintf(b, " MAT(%d, %d) = SJ(%d) * (mg);", om->jacobSparse[i]->i, om->jacobSparse[i]->j, i);
+  CharBuffer_append(b, "\n");
 
   /* model_init: uniform base values, then the varied inputs of this trajectory (SoA, batch fastest) */
-  CharBuffer_append(b, "DEV void model_init(double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], const double *__restrict__ vary, size_t stride, size_t set)\n{\n");
+  CharBuffer_append(b, "DEV void model_init(double (&y)[A1(NEQ)], const PvRef pv, const double *__restrict__ vary, size_t stride, size_t set)\n{\n");
   for (i = 0; i < om->neq; i++) cbprintf(b, "  y[%d] = c_base[%d];\n", i, i);
   for (i = 0; i < nvalues; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = c_base[%d];\n", k.slot[i], i);
   for (j = 0; j < nvary; j++) {
@@ -389,14 +388,14 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   CharBuffer_append(b, "  (void)vary; (void)stride; (void)set; (void)pv; (void)y;\n}\n");
 
   /* refresh of all assignment rules; static ones are written back to their slots */
-  CharBuffer_append(b, "DEV void rules_all(double t, const double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], double (&a)[A1(NASS)])\n{\n  (void)t; (void)y; (void)pv; (void)a;\n");
+  CharBuffer_append(b, "DEV void rules_all(double t, const double (&y)[A1(NEQ)], const PvRef pv, double (&a)[A1(NASS)])\n{\n  (void)t; (void)y; (void)pv; (void)a;\n");
   k.local = all_local;
   emit_refresh_all(b, om, &c, "  ");
   for (i = om->neq; i < om->neq + om->nass; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = a[%d];\n", k.slot[i], i - om->neq);
   CharBuffer_append(b, "}\n");
 
   /* ode_f: rules needed by the ODEs in topological order, then the right-hand sides */
-  CharBuffer_append(b, "DEV void ode_f(double t, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)], double (&ydot)[A1(NEQ)])\n{\n  double a[A1(NASS)]; (void)t; (void)pv; (void)a;\n");
+  CharBuffer_append(b, "DEV void ode_f(double t, const double (&y)[A1(NEQ)], const PvRef pv, double (&ydot)[A1(NEQ)])\n{\n  double a[A1(NASS)]; (void)t; (void)pv; (void)a;\n");
   k.local = ode_local;
   for (i = 0; i < om->nassbeforeodes; i++) {
     nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
@@ -406,13 +405,13 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   CharBuffer_append(b, "}\n");
 
   /* jacobi_f: structurally non-zero entries in jacobSparse order (rules are inlined) */
-  CharBuffer_append(b, "DEV void jacobi_f(double t, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)], double (&jnz)[A1(NNZ)])\n{\n  (void)t; (void)pv; (void)y; (void)jnz;\n");
+  CharBuffer_append(b, "DEV void jacobi_f(double t, const double (&y)[A1(NEQ)], const PvRef pv, double (&jnz)[A1(NNZ)])\n{\n  (void)t; (void)pv; (void)y; (void)jnz;\n");
   k.local = ode_local;
   if (usejac) for (i = 0; i < om->sparsesize; i++) { cbprintf(b, "  jnz[%d] = ", i); gen(b, om->jacobSparse[i]->ij, &c); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "}\n");
 
   /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
-  CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], double (&pv)[A1(NPV)], int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
+  CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], const PvRef pv, int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
                        "  unsigned int fired = 0; double a[A1(NASS)]; (void)t; (void)a; (void)y; (void)pv; (void)trigger; (void)reinit;\n");
   k.local = all_local;
   if (om->nevents > 0) {
@@ -434,7 +433,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   CharBuffer_append(b, "  return fired;\n}\n");
 
   /* store_row: refresh all rules, write the selected values (coalesced: consecutive sets are consecutive addresses) */
-  CharBuffer_append(b, "DEV void store_row(double *__restrict__ row, size_t stride, double t, const double (&y)[A1(NEQ)], double (&pv)[A1(NPV)])\n{\n  double a[A1(NASS)]; (void)t; (void)a; (void)pv; (void)y;\n");
+  CharBuffer_append(b, "DEV void store_row(double *__restrict__ row, size_t stride, double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  double a[A1(NASS)]; (void)t; (void)a; (void)pv; (void)y;\n");
   {
     int need_rules = 0;
     for (j = 0; j < nstore; j++) if (store[j] >= om->neq && store[j] < om->neq + om->nass) need_rules = 1;
@@ -444,7 +443,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   CharBuffer_append(b, "}\n");
   /* row 0: values after initial assignments with the model's own parameters, varied entries overwritten
      (setVariableValue at t == 0 patches results->value[idx][0] only, integratorInstance.c:1571-1572) */
-  CharBuffer_append(b, "DEV void store_row0(double *__restrict__ row, size_t stride, const double (&y)[A1(NEQ)], const double (&pv)[A1(NPV)])\n{\n  (void)y; (void)pv;\n");
+  CharBuffer_append(b, "DEV void store_row0(double *__restrict__ row, size_t stride, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  (void)y; (void)pv;\n");
   for (j = 0; j < nstore; j++) {
     int idx = store[j], varied = 0, jj;
     for (jj = 0; jj < nvary; jj++) if (vary[jj] == idx) varied = 1;

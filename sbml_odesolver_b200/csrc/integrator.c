@@ -1,0 +1,341 @@
+/*
+ * integrator.c -- integratorInstance_t: the single-instance driver API of the
+ * reference (src/integratorInstance.c:105-1790, src/cvodeSolver.c:81-400),
+ * kept call-compatible, with the time stepping moved to the GPU.
+ *
+ * How the solver seam is honoured without a CPU integrator: when the engine
+ * is (re)validated -- first step, after IntegratorInstance_setVariableValue or
+ * after a fired event invalidated it, exactly where the reference calls
+ * CVodeInit/CVodeReInit (src/cvodeSolver.c:91-100) -- the remaining time
+ * course is integrated on the device as a batch of one, with every ODE
+ * variable and every constant passed as a per-trajectory input.  Each
+ * IntegratorInstance_cvodeOneStep then advances solver->t to solver->tout,
+ * copies the row computed for that output time into data->value and calls
+ * IntegratorInstance_updateData, as the reference's contract demands
+ * (src/cvodeSolver.c:72-79, :226-240).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sbmlsolver/batchIntegrator.h"
+#include "sbmlsolver/processAST.h"
+#include "sbmlsolver/solverError.h"
+
+/* private plan entry points (batch.cu) */
+int ODESBatch_setTimeGrid(odesBatch_t *, int nout, const double *tpoints);
+int ODESBatch_setInitialTriggers(odesBatch_t *, const int *trigger);
+
+static void drop_course(cvodeSolver_t *s)
+{
+  free(s->course); free(s->courseFired);
+  s->course = NULL; s->courseFired = NULL; s->courseLen = 0; s->courseFirst = 0; s->courseStatus = 0;
+}
+
+static int initialize_solver(integratorInstance_t *engine, cvodeData_t *data, cvodeSettings_t *opt, odeModel_t *om)
+{
+  int i; cvodeSolver_t *solver = engine->solver; cvodeResults_t *results = data->results;
+  engine->om = om; engine->opt = opt; engine->data = data; engine->results = data->results;
+  /* IntegratorInstance_initializeJacobian (integratorInstance.c:291-311) */
+  if (om->jacobianFailed > 0 || !opt->UseJacobian) engine->UseJacobian = 0;
+  else if (om->jacob != NULL) engine->UseJacobian = 1;
+  else engine->UseJacobian = ODEModel_constructJacobian(om);
+  if (opt->Indefinitely) { solver->t0 = 0; solver->t = 0; solver->tout = opt->Time; }
+  else { solver->t0 = opt->TimePoints[0]; solver->t = opt->TimePoints[0]; solver->tout = opt->PrintStep >= 1 ? opt->TimePoints[1] : opt->TimePoints[0]; }
+  solver->nout = opt->PrintStep;
+  solver->iout = 1;
+  if (opt->StoreResults && results) {
+    results->time[0] = data->currenttime;
+    for (i = 0; i < data->nvalues; i++) results->value[i][0] = data->value[i];
+  }
+  engine->run++;
+  engine->isValid = 0;
+  engine->clockStarted = 0;
+  drop_course(solver);
+  return 1;
+}
+
+integratorInstance_t *IntegratorInstance_create(odeModel_t *om, cvodeSettings_t *opt)
+{
+  cvodeData_t *data; integratorInstance_t *engine;
+  if (!om || !opt || om->hasCycle) return NULL;
+  data = CvodeData_create(om);
+  if (!data) return NULL;
+  CvodeData_initialize(data, opt, om, 0);
+  engine = (integratorInstance_t *)calloc(1, sizeof *engine);
+  engine->solver = (cvodeSolver_t *)calloc(1, sizeof(cvodeSolver_t));
+  if (!initialize_solver(engine, data, opt, om)) { IntegratorInstance_free(engine); return NULL; }
+  return engine;
+}
+int IntegratorInstance_set(integratorInstance_t *engine, cvodeSettings_t *opt)
+{
+  if (opt != engine->opt && engine->solver->plan) { ODESBatch_free(engine->solver->plan); engine->solver->plan = NULL; }
+  CvodeData_initialize(engine->data, opt, engine->om, 0);
+  return initialize_solver(engine, engine->data, opt, engine->om);
+}
+int IntegratorInstance_reset(integratorInstance_t *engine) { return IntegratorInstance_set(engine, engine->opt); }
+int IntegratorInstance_resetTime(integratorInstance_t *engine, cvodeSettings_t *opt)
+{
+  if (!opt) opt = engine->opt;
+  CvodeData_initialize(engine->data, opt, engine->om, 1);
+  return initialize_solver(engine, engine->data, opt, engine->om);
+}
+void IntegratorInstance_free(integratorInstance_t *engine)
+{
+  if (!engine) return;
+  if (engine->solver) { drop_course(engine->solver); if (engine->solver->plan) ODESBatch_free(engine->solver->plan); free(engine->solver); }
+  CvodeData_free(engine->data);
+  free(engine);
+}
+cvodeSettings_t *IntegratorInstance_getSettings(integratorInstance_t *engine) { return engine->opt; }
+cvodeData_t *IntegratorInstance_getData(integratorInstance_t *engine) { return engine->data; }
+double IntegratorInstance_getTime(const integratorInstance_t *engine) { return engine->solver->t; }
+int IntegratorInstance_setNextTimeStep(integratorInstance_t *engine, double nexttime)
+{
+  if (nexttime <= engine->solver->t) return 0;
+  engine->solver->tout = nexttime;
+  drop_course(engine->solver); engine->isValid = 0;
+  return 1;
+}
+const cvodeResults_t *IntegratorInstance_getResults(const integratorInstance_t *engine) { return engine->results; }
+int IntegratorInstance_timeCourseCompleted(const integratorInstance_t *engine)
+{ return engine->solver->iout > engine->solver->nout && !engine->opt->Indefinitely; }
+
+static void refresh_rules(integratorInstance_t *engine)
+{
+  int i; odeModel_t *om = engine->om; cvodeData_t *data = engine->data;
+  for (i = 0; i < om->nass; i++) { nonzeroElem_t *o = om->assignmentOrder[i]; data->value[o->i] = evaluateAST(o->ij, data); }
+  data->allRulesUpdated = 1;
+}
+double IntegratorInstance_getVariableValue(integratorInstance_t *engine, variableIndex_t *vi)
+{
+  if (!engine->data->allRulesUpdated) refresh_rules(engine);
+  return engine->data->value[vi->index];
+}
+static void set_value_by_index(integratorInstance_t *engine, int idx, double value)
+{
+  odeModel_t *om = engine->om; cvodeData_t *data = engine->data;
+  if (idx >= om->neq && idx < om->neq + om->nass) {
+    SolverError_error(WARNING_ERROR_TYPE, SOLVER_ERROR_ATTEMPT_TO_SET_ASSIGNED_VALUE,
+                      "Attempted to set a new value for an assigned variable: %s. This is not possible. New value ignored!", om->names[idx]);
+    return;
+  }
+  data->value[idx] = value;
+  if (engine->solver->t == 0.0 && data->results != NULL) data->results->value[idx][0] = value;
+  if (idx < om->neq || engine->opt->ResetCvodeOnEvent) engine->isValid = 0;
+  /* a changed constant alters the right-hand side of the look-ahead course as well */
+  engine->isValid = 0;
+  refresh_rules(engine);
+}
+void IntegratorInstance_setVariableValue(integratorInstance_t *engine, variableIndex_t *vi, double value) { if (vi) set_value_by_index(engine, vi->index, value); }
+void IntegratorInstance_setVariableValueByID(integratorInstance_t *engine, const char *id, double value)
+{
+  variableIndex_t *vi = ODEModel_getVariableIndex(engine->om, id);
+  if (vi) set_value_by_index(engine, vi->index, value);
+  VariableIndex_free(vi);
+}
+void IntegratorInstance_copyVariableState(integratorInstance_t *target, integratorInstance_t *source)
+{
+  int i;
+  if (target->om == source->om) for (i = 0; i < source->data->nvalues; i++) target->data->value[i] = source->data->value[i];
+  else SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_ATTEMPTING_TO_COPY_VARIABLE_STATE_BETWEEN_INSTANCES_OF_DIFFERENT_MODELS,
+                         "Attempting to copy variable state between instances of different models");
+  target->isValid = 0;
+  refresh_rules(target);
+}
+void IntegratorInstance_dumpData(const integratorInstance_t *engine)
+{
+  int i; cvodeData_t *data = engine->data;
+  printf("t = %g\n", engine->solver->t);
+  for (i = 0; i < data->nvalues; i++) printf("%s = %g\n", engine->om->names[i], data->value[i]);
+}
+
+/* device look-ahead: integrates outputs iout..nout from the current state as a batch of one */
+static int compute_course(integratorInstance_t *engine)
+{
+  odeModel_t *om = engine->om; cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data;
+  int nvalues = data->nvalues, nin = om->neq + om->nconst, i, j, nrem, st = 0;
+  double *grid, *values, *rows; unsigned int *fired; int stats[ODES_NUM_STATS];
+  if (engine->opt->Indefinitely) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "indefinite integration is not supported by the device integrator; use a finite output grid");
+    return 0;
+  }
+  if (!solver->plan) {
+    int *idx = (int *)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(int));
+    for (i = 0, j = 0; i < nvalues; i++) if (i < om->neq || i >= om->neq + om->nass) idx[j++] = i;
+    solver->plan = ODESBatch_create(om, engine->opt, nin, idx, 0, NULL, 0);
+    free(idx);
+    if (!solver->plan) return 0;
+  }
+  nrem = solver->nout - solver->iout + 1;
+  grid = (double *)malloc((size_t)(nrem + 1) * sizeof(double));
+  grid[0] = solver->t;
+  grid[1] = solver->tout;
+  for (i = 2; i <= nrem; i++) grid[i] = engine->opt->TimePoints[solver->iout + i - 1];
+  values = (double *)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(double));
+  for (i = 0, j = 0; i < nvalues; i++) if (i < om->neq || i >= om->neq + om->nass) values[j++] = data->value[i];
+  rows = (double *)malloc((size_t)(nrem + 1) * (size_t)nvalues * sizeof(double));
+  fired = (unsigned int *)malloc((size_t)(solver->nout + 2) * sizeof(unsigned int));
+  if (!ODESBatch_setTimeGrid(solver->plan, nrem, grid) || !ODESBatch_setInitialTriggers(solver->plan, data->trigger) ||
+      !ODESBatch_setValues(solver->plan, 1, values) || !ODESBatch_integrate(solver->plan, 1) || !ODESBatch_synchronize(solver->plan) ||
+      !ODESBatch_getTrajectory(solver->plan, 0, rows) || !ODESBatch_getStatus(solver->plan, 1, &st) ||
+      !ODESBatch_getEventLog(solver->plan, 1, fired) || !ODESBatch_getStats(solver->plan, 1, stats)) {
+    free(grid); free(values); free(rows); free(fired);
+    return 0;
+  }
+  drop_course(solver);
+  solver->course = rows; solver->courseFirst = solver->iout; solver->courseLen = nrem; solver->courseStatus = st;
+  solver->courseFired = (int *)malloc((size_t)(nrem + 1) * sizeof(int));
+  for (i = 0; i <= nrem; i++) solver->courseFired[i] = (int)fired[i];
+  solver->nst += stats[ODES_STAT_NST]; solver->nfe += stats[ODES_STAT_NFE]; solver->nsetups += stats[ODES_STAT_NSETUPS];
+  solver->nje += stats[ODES_STAT_NJE]; solver->nni += stats[ODES_STAT_NNI]; solver->ncfn += stats[ODES_STAT_NCFN]; solver->netf += stats[ODES_STAT_NETF];
+  free(grid); free(values); free(fired);
+  return 1;
+}
+
+int IntegratorInstance_updateData(integratorInstance_t *engine)
+{
+  int i, flag = 1; unsigned int fired = 0;
+  cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data; cvodeSettings_t *opt = engine->opt;
+  cvodeResults_t *results = engine->results; odeModel_t *om = engine->om;
+  data->currenttime = (float)solver->t;
+  /* events were processed on the device at this output time (event_f); pick up the outcome */
+  if (engine->processEvents && solver->course) {
+    int row = solver->iout - solver->courseFirst + 1;
+    if (row >= 1 && row <= solver->courseLen) fired = (unsigned int)solver->courseFired[row];
+    for (i = 0; i < data->nevents; i++) data->trigger[i] = evaluateAST(om->event[i], data) != 0.0;
+    if (fired && opt->HaltOnEvent) {
+      for (i = 0; i != data->nevents; i++)
+        if (fired & (1u << i)) {
+          char *buffer = SBML_formulaToString(om->event[i]);
+          SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_EVENT_TRIGGER_FIRED,
+                            "Event Trigger %d (%s) fired at time %g. Aborting simulation.", i, buffer, (double)data->currenttime);
+          free(buffer);
+        }
+      flag = 0;
+    }
+  }
+  data->allRulesUpdated = 1;                 /* device rows hold refreshed rules */
+  if (opt->StoreResults && results) {
+    results->nout = solver->iout;
+    results->time[solver->iout] = solver->t;
+    for (i = 0; i < data->nvalues; i++) results->value[i][solver->iout] = data->value[i];
+  }
+  if (opt->SteadyState == 1 && IntegratorInstance_checkSteadyState(engine)) flag = 0;
+  solver->iout++;
+  if (opt->Indefinitely) solver->tout += opt->Time;
+  else if (solver->iout <= solver->nout) solver->tout = opt->TimePoints[solver->iout];
+  return flag;
+}
+
+static const char *cvode_message(int flag)
+{
+  switch (flag) {
+  case -2: return "One of the inputs to CVode is illegal.";
+  case -4: return "At time %g: The solver took %d internal steps but could not compute variable values.";
+  case -5: return "The solver could not satisfy the accuracy requested for some internal step.";
+  case -6: return "Error test failures occurred too many times during one internal time step or occurred with |h| = hmin.";
+  case -7: return "Convergence test failures occurred too many times during one internal time step or occurred with |h| = hmin.";
+  case -9: return "The linear solver's setup routine failed in an unrecoverable manner.";
+  case -10: return "The linear solver's solve routine failed in an unrecoverable manner.";
+  default: return "???";
+  }
+}
+
+int IntegratorInstance_cvodeOneStep(integratorInstance_t *engine)
+{
+  cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data; int i, row;
+  if (!engine->isValid || !solver->course) {
+    solver->t0 = solver->t;
+    if (!compute_course(engine)) return 0;
+    engine->isValid = 1;
+  }
+  if (!engine->clockStarted) { engine->startTime = clock(); engine->clockStarted = 1; }
+  row = solver->iout - solver->courseFirst + 1;
+  if (row < 1 || row > solver->courseLen || isnan(solver->course[(size_t)row * (size_t)data->nvalues])) {
+    int flag = solver->courseStatus ? solver->courseStatus : -2;
+    SolverError_error(ERROR_ERROR_TYPE, (errorCode_t)flag, cvode_message(flag), solver->tout, engine->opt->Mxstep);
+    SolverError_error(WARNING_ERROR_TYPE, SOLVER_ERROR_INTEGRATION_NOT_SUCCESSFUL, "Integration not successful. Results are not complete.");
+    return 0;
+  }
+  solver->t = solver->tout;
+  for (i = 0; i < data->nvalues; i++) data->value[i] = solver->course[(size_t)row * (size_t)data->nvalues + (size_t)i];
+  /* a fired event with re-initialisation was already handled inside the device course */
+  return IntegratorInstance_updateData(engine);
+}
+int IntegratorInstance_simpleOneStep(integratorInstance_t *engine) { return IntegratorInstance_cvodeOneStep(engine); }
+int IntegratorInstance_integrateOneStep(integratorInstance_t *engine) { engine->processEvents = 1; return IntegratorInstance_cvodeOneStep(engine); }
+int IntegratorInstance_integrateOneStepWithoutEventProcessing(integratorInstance_t *engine) { engine->processEvents = 0; return IntegratorInstance_cvodeOneStep(engine); }
+int IntegratorInstance_integrate(integratorInstance_t *engine)
+{
+  while (engine->solver->iout <= engine->solver->nout) if (!IntegratorInstance_integrateOneStep(engine)) return 0;
+  return 1;
+}
+
+cvodeResults_t *IntegratorInstance_createResults(const integratorInstance_t *engine)
+{
+  int i, j; cvodeResults_t *results, *iResults = engine->results;
+  if (!engine->opt->StoreResults || iResults == NULL) return NULL;
+  results = CvodeResults_create(engine->data, engine->opt->PrintStep);
+  if (!results) return NULL;
+  results->nout = iResults->nout;
+  for (i = 0; i <= results->nout; i++) { results->time[i] = iResults->time[i]; for (j = 0; j < iResults->nvalues; j++) results->value[j][i] = iResults->value[j][i]; }
+  return results;
+}
+void IntegratorInstance_printResults(const integratorInstance_t *ii, FILE *fp)
+{
+  int n, j;
+  fprintf(fp, "#t ");
+  for (j = 0; j < ii->om->neq; j++) fprintf(fp, "%s ", ii->om->names[j]);
+  fprintf(fp, "\n");
+  for (n = 0; n < CvodeResults_getNout(ii->results); n++) {
+    fprintf(fp, "%g ", CvodeResults_getTime(ii->results, n));
+    for (j = 0; j < ii->om->neq; j++) fprintf(fp, "%g ", ii->results->value[j][n]);
+    fprintf(fp, "\n");
+  }
+}
+/* reference src/integratorInstance.c:1442-1507: mean and std of the ODE right-hand sides below threshold */
+int IntegratorInstance_checkSteadyState(integratorInstance_t *engine)
+{
+  int i; double dy_mean = 0.0, dy_var = 0.0, dy_std; cvodeData_t *data = engine->data; odeModel_t *om = engine->om;
+  double *dy;
+  if (om->neq == 0) return 0;
+  dy = (double *)malloc((size_t)om->neq * sizeof(double));
+  for (i = 0; i < om->nass; i++) { nonzeroElem_t *o = om->assignmentOrder[i]; data->value[o->i] = evaluateAST(o->ij, data); }
+  for (i = 0; i < om->neq; i++) { dy[i] = fabs(evaluateAST(om->ode[i], data)); dy_mean += dy[i]; }
+  dy_mean /= om->neq;
+  for (i = 0; i < om->neq; i++) dy_var += (dy[i] - dy_mean) * (dy[i] - dy_mean);
+  free(dy);
+  dy_var = om->neq > 1 ? dy_var / (om->neq - 1) : 0.0;
+  dy_std = sqrt(dy_var);
+  if ((dy_mean + dy_std) < engine->opt->ssThreshold) {
+    data->steadystate = 1;
+    SolverError_error(MESSAGE_ERROR_TYPE, SOLVER_ERROR_NO_ERROR, "Steady state found. Simulation aborted at %g seconds. Mean of rates: %g, std %g", (double)data->currenttime, dy_mean, dy_std);
+    return 1;
+  }
+  data->steadystate = 0;
+  return 0;
+}
+int IntegratorInstance_handleError(integratorInstance_t *engine)
+{
+  int errorCode = (int)SolverError_getLastCode(ERROR_ERROR_TYPE);
+  (void)engine;
+  return errorCode;
+}
+void IntegratorInstance_printCVODEStatistics(const integratorInstance_t *engine, FILE *f)
+{
+  const cvodeSolver_t *s = engine->solver;
+  fprintf(f, "## CVode Statistics:\n");
+  fprintf(f, "## nst = %-6ld nfe  = %-6ld nsetups = %-6ld nje = %ld\n", s->nst, s->nfe, s->nsetups, s->nje);
+  fprintf(f, "## nni = %-6ld ncfn = %-6ld netf = %ld\n", s->nni, s->ncfn, s->netf);
+}
+void IntegratorInstance_printStatistics(const integratorInstance_t *engine, FILE *f)
+{
+  odeModel_t *om = engine->om;
+  fprintf(f, "## Integration Parameters:\n");
+  fprintf(f, "## mxstep   = %d rel.err. = %g abs.err. = %g \n", engine->opt->Mxstep, engine->opt->RError, engine->opt->Error);
+  fprintf(f, "## CVode Done.\n## Model Statistics:\n## ODEs = %d assignments = %d constants = %d\n", om->neq, om->nass, om->nconst);
+  IntegratorInstance_printCVODEStatistics(engine, f);
+}
+double IntegratorInstance_getIntegrationTime(const integratorInstance_t *engine)
+{ return engine->clockStarted ? ((double)(clock() - engine->startTime)) / CLOCKS_PER_SEC : 0.0; }

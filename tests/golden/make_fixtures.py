@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Generates the committed fixtures under tests/golden/ from the reference tree.
+
+Run in the build container only (needs /root/reference); the GPU box and the
+test-suite read the committed outputs, never /root/reference.
+
+1. models/*.xml   -- the reference's example models, READ with this repo's SBML reader and
+                     re-serialised by this repo's SBML writer (Level 2 Version 1 + MathML).
+                     Content (ids, values, formulas) is the reference's test data; the text is ours.
+2. mapk_testrun.txt, mapk_*pt.dat.txt -- the golden trajectory rows of examples/testrun.out:28-129 and
+                     examples/MAPK_{10,100}pt.dat as plain number tables.
+"""
+import os
+import re
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+import sbml_odesolver_b200 as so
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+MODELS = {
+    "mapk_cascade.xml": "examples/MAPK.xml",
+    "repressilator_ring.xml": "examples/repressilator.xml",
+    "two_events_one_assignment.xml": "examples/events-2-events-1-assignment-l2.xml",
+    "one_event_one_assignment.xml": "examples/events-1-event-1-assignment-l2.xml",
+    "huang_ferrell_cascade.xml": "examples/huang96.xml",
+    "basic_reversible.xml": "examples/basic.xml",
+    "basic_forward.xml": "examples/basic-model1-forward-l2.xml",
+    "goodwin_oscillator.xml": "tutorial/Goodwin_SomoS.xml",
+}
+
+L = so.lib()
+for out, src in MODELS.items():
+    d = L.readSBML(os.path.join(REF, src).encode())
+    assert d, src
+    assert L.writeSBML(d, os.path.join(OUT, "models", out).encode())
+    L.SBMLDocument_free(d)
+    print("wrote", out)
+
+# golden trajectory of `integrate MAPK.xml 1000 100` (atol 1e-9, rtol 1e-4), species rows
+lines = open(os.path.join(REF, "examples/testrun.out")).read().split("\n")
+start = next(i for i, l in enumerate(lines) if l.startswith("#time MKKK "))
+rows = []
+for l in lines[start + 1:]:
+    if not re.match(r"^[0-9]", l):
+        break
+    rows.append(l.strip())
+assert len(rows) == 101
+open(os.path.join(OUT, "mapk_testrun.txt"), "w").write("# t MKKK MKKK_P MKK MKK_P MKK_PP MAPK MAPK_P MAPK_PP  (examples/testrun.out:28-129)\n" + "\n".join(rows) + "\n")
+for name in ("MAPK_10pt.dat", "MAPK_100pt.dat"):
+    rows = [l.strip() for l in open(os.path.join(REF, "examples", name)) if re.match(r"^[0-9]", l)]
+    open(os.path.join(OUT, name.lower() + ".txt"), "w").write(f"# rows of examples/{name}: t + 8 species\n" + "\n".join(rows) + "\n")
+    print(name, len(rows))

@@ -1,0 +1,153 @@
+"""Test helpers: oracle binding (ctypes), kernel host-emulation builder, synthetic parameter sets.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+import sbml_odesolver_b200 as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = os.path.join(ROOT, "tests", "golden", "models")
+ORACLE = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcvode_ref.so")
+PORT, REF = 0, 1
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        so.lib()
+        _oracle = C.CDLL(ORACLE)
+        _oracle.oracle_integrate_batch.restype = C.c_int
+        _oracle.oracle_integrate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_char_p, C.c_int]
+        _oracle.oracle_last_error.restype = C.c_char_p
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_LIB)
+
+
+def model_path(name):
+    return os.path.join(MODELS, name)
+
+
+def oracle_run(model, opt, vary, values, nout, backend=PORT, threads=1, compiled_so=None, want_margin=False):
+    """Returns dict(out[nsets][nout+1][nvalues], status, stats[nsets][7], fired[nsets][nout+1])."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    nsets = values.shape[0]
+    vary = np.ascontiguousarray(vary, dtype=np.int32)
+    out = np.zeros((nsets, nout + 1, model.nvalues))
+    status = np.zeros(nsets, dtype=np.int32)
+    stats = np.zeros((nsets, 7), dtype=np.int32)
+    fired = np.zeros((nsets, nout + 1), dtype=np.uint32)
+    margin = np.zeros((nsets, nout + 1)) if want_margin else None
+    r = oracle().oracle_integrate_batch(model.om, opt, nsets, len(vary), vary.ctypes.data, values.ctypes.data, out.ctypes.data,
+                                        status.ctypes.data, stats.ctypes.data, fired.ctypes.data,
+                                        None if margin is None else margin.ctypes.data, backend,
+                                        1 if compiled_so else 0, compiled_so.encode() if compiled_so else None, threads)
+    if r < 0:
+        raise RuntimeError("oracle failed: " + oracle().oracle_last_error().decode())
+    return dict(out=out, status=status, stats=stats, fired=fired, margin=margin)
+
+
+def compile_c_model(model, tag):
+    """gcc-compiles ODEModel_generateCSource (the reference's compiled mode) into a shared object."""
+    src = so.take_string(so.lib().ODEModel_generateCSource(model.om))
+    h = hashlib.sha1(src.encode()).hexdigest()[:12]
+    d = os.path.join(ROOT, "oracle", "_ref", "models")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"{tag}_{h}.so")
+    if not os.path.exists(path):
+        cpath = path[:-3] + ".c"
+        open(cpath, "w").write(src)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", cpath, "-o", path, "-lm"])
+    return path
+
+
+class Emu:
+    """Host build of the generated kernel translation unit (tests/emu/emu_harness.cpp)."""
+
+    def __init__(self, batch, tag):
+        src = batch.source()
+        h = hashlib.sha1(src.encode()).hexdigest()[:12]
+        d = os.path.join(ROOT, "tests", "emu", "_build")
+        os.makedirs(d, exist_ok=True)
+        cu = os.path.join(d, f"{tag}_{h}.cu")
+        lib = os.path.join(d, f"{tag}_{h}.so")
+        if not os.path.exists(lib):
+            open(cu, "w").write(src)
+            subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w",
+                                   f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
+        self.lib = C.CDLL(lib)
+        self.batch = batch
+
+    def run(self, base, trig0, values, tpoints, mxstep, rtol, atol):
+        b = self.batch
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        nsets = values.shape[0]
+        nout = len(tpoints) - 1
+        vary = np.ascontiguousarray(values.T)                      # SoA [nvary][nsets]
+        out = np.zeros((nout + 1, b.nstore, nsets))
+        status = np.zeros(nsets, dtype=np.int32)
+        stats = np.zeros((7, nsets), dtype=np.int32)
+        fired = np.zeros((nout + 1, nsets), dtype=np.uint32)
+        base = np.ascontiguousarray(base, dtype=np.float64)
+        trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
+        tp = np.ascontiguousarray(tpoints, dtype=np.float64)
+        self.lib.emu_run(C.c_void_p(base.ctypes.data), C.c_void_p(trig0.ctypes.data), C.c_void_p(vary.ctypes.data), C.c_void_p(out.ctypes.data),
+                         C.c_void_p(status.ctypes.data), C.c_void_p(stats.ctypes.data), C.c_void_p(fired.ctypes.data), C.c_void_p(tp.ctypes.data),
+                         C.c_ulonglong(nsets), C.c_int(nsets), C.c_int(nout), C.c_int(mxstep), C.c_double(rtol), C.c_double(atol))
+        return dict(out=out, status=status, stats=stats, fired=fired)
+
+
+def mapk_scan_model():
+    """MAPK with the 18 kinetic-law locals globalised; returns (model, vary indices, nominal values)."""
+    m = so.Model(model_path("mapk_cascade.xml"), globalize=so.MAPK_LOCALS)
+    names = ["V1", "Ki", "K1"] + m.globalized
+    vary = [m.index(n) for n in names]
+    nominal = m.base_values()[vary]
+    return m, vary, nominal
+
+
+def log_uniform_sets(nominal, nsets, seed, span=1.0):
+    """nominal * 2^u, u ~ U(-span, span)  (numpy generator for the CPU-side tests)."""
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-span, span, size=(nsets, len(nominal)))
+    return nominal[None, :] * np.exp2(u)
+
+
+def parity(gpu, ref, rtol, atol):
+    """max over points of |gpu-ref| / max(10*rtol*|ref|, 10*atol); NaN rows must coincide."""
+    nan_g, nan_r = np.isnan(gpu), np.isnan(ref)
+    if not np.array_equal(nan_g, nan_r):
+        return np.inf
+    tol = np.maximum(10 * rtol * np.abs(ref), 10 * atol)
+    with np.errstate(invalid="ignore"):
+        ratio = np.where(nan_r, 0.0, np.abs(gpu - ref) / tol)
+    return float(ratio.max()) if ratio.size else 0.0
+
+
+def parity_report(gpu, ref, gstats, rstats, rtol, atol):
+    """Per-set comparison of a device run with the oracle.
+
+    gpu/ref: [nrows][nstore][nsets]; gstats/rstats: [nsets][7] CVODE work counters.
+    Returns the per-set violation ratio |gpu-ref| / max(10 rtol |ref|, 10 atol), which sets took exactly the
+    same steps and decisions as the reference CVODE run (identical counters), and summary numbers.
+    """
+    nan_g, nan_r = np.isnan(gpu), np.isnan(ref)
+    tol = np.maximum(10 * rtol * np.abs(ref), 10 * atol)
+    with np.errstate(invalid="ignore"):
+        r = np.where(nan_r & nan_g, 0.0, np.where(nan_r | nan_g, np.inf, np.abs(gpu - ref) / tol))
+    ratio = r.max(axis=(0, 1))
+    same = (np.asarray(gstats) == np.asarray(rstats)).all(axis=1)
+    return dict(ratio=ratio, same_path=same, frac_same_path=float(same.mean()),
+                max_ratio_same_path=float(ratio[same].max()) if same.any() else 0.0,
+                max_ratio=float(ratio.max()), frac_within=float((ratio <= 1.0).mean()))
