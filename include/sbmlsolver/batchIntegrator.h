@@ -50,6 +50,9 @@ int ODESBatch_reserve(odesBatch_t *, int capacity);
 int ODESBatch_getCapacity(const odesBatch_t *);
 int ODESBatch_getNout(const odesBatch_t *);        /* number of stored rows = PrintStep+1 */
 int ODESBatch_getNstore(const odesBatch_t *);
+/* values after reset with the model's own parameters (what every trajectory starts from before its
+   varied entries are set, src/cvodeData.c:156-190) and the initial trigger flags (:377-379) */
+void ODESBatch_getBaseValues(const odesBatch_t *, double *values /* [nvalues] or NULL */, int *triggers /* [nevents] or NULL */);
 const char *ODESBatch_getSource(const odesBatch_t *);   /* generated CUDA source */
 const char *ODESBatch_getCompileLog(const odesBatch_t *);
 int ODESBatch_getKernelInfo(const odesBatch_t *, int *regsPerThread, int *sharedBytesPerBlock,

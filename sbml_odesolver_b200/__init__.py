@@ -68,7 +68,7 @@ _SIGS = {
     "ODESBatch_create": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p, c_i]), "ODESBatch_free": (None, [c_p]),
     "ODESBatch_reserve": (c_i, [c_p, c_i]), "ODESBatch_getCapacity": (c_i, [c_p]), "ODESBatch_getNout": (c_i, [c_p]),
     "ODESBatch_getNstore": (c_i, [c_p]), "ODESBatch_getSource": (c_s, [c_p]), "ODESBatch_getCompileLog": (c_s, [c_p]),
-    "ODESBatch_getKernelInfo": (c_i, [c_p] + [c_p] * 5),
+    "ODESBatch_getKernelInfo": (c_i, [c_p] + [c_p] * 5), "ODESBatch_getBaseValues": (None, [c_p, c_p, c_p]),
     "ODESBatch_setValues": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_generateValues": (c_i, [c_p, c_i, C.c_ulonglong, C.c_longlong, c_p, c_p, c_p, c_i]),
     "ODESBatch_deviceValues": (c_p, [c_p]), "ODESBatch_deviceResults": (c_p, [c_p]),
@@ -208,6 +208,13 @@ class Batch:
 
     def source(self):
         return lib().ODESBatch_getSource(self.h).decode()
+
+    def base_values(self):
+        """(value[] after reset with the model's own parameters, initial trigger flags)."""
+        v = np.zeros(max(self.model.nvalues, 1))
+        trig = np.zeros(32, dtype=np.int32)
+        lib().ODESBatch_getBaseValues(self.h, v.ctypes.data, trig.ctypes.data)
+        return v[:self.model.nvalues], trig
 
     def reserve(self, n):
         _check(lib().ODESBatch_reserve(self.h, n), "ODESBatch_reserve")

@@ -349,8 +349,9 @@ static std::string build_source(odesBatch_t *b)
   int want = env_int("ODES_THREADS_PER_SM", 128) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   char head[512];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
+           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   src += model;
@@ -446,6 +447,11 @@ extern "C" int ODESBatch_setInitialTriggers(odesBatch_t *b, const int *trigger)
     DRV_OK(drv.MemcpyHtoD(sym, trigger, sizeof(int) * (size_t)b->om->nevents));
   }
   return 1;
+}
+extern "C" void ODESBatch_getBaseValues(const odesBatch_t *b, double *values, int *triggers)
+{
+  if (values) for (size_t i = 0; i < b->base.size(); i++) values[i] = b->base[i];
+  if (triggers) for (size_t i = 0; i < b->trigger0.size(); i++) triggers[i] = b->trigger0[i];
 }
 extern "C" int ODESBatch_getCapacity(const odesBatch_t *b) { return b->capacity; }
 extern "C" int ODESBatch_getNout(const odesBatch_t *b) { return b->nout + 1; }

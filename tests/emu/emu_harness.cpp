@@ -28,6 +28,6 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   a.vary = vary; a.out = out; a.status = status; a.stats = stats; a.fired = fired; a.tpoints = tpoints;
   a.stride = stride; a.nsets = nsets; a.nout = nout; a.mxstep = mxstep; a.pad = 0; a.reltol = reltol; a.abstol = abstol;
   static double sm[ODES_SMEM_WORDS + 1];
-  for (int s = 0; s < nsets; s++) integrate_set(a, (size_t)s, sm, 1u);
+  for (int s = 0; s < nsets; s++) integrate_set(a, (size_t)s, true, sm);
   return 0;
 }

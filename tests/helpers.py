@@ -151,3 +151,61 @@ def parity_report(gpu, ref, gstats, rstats, rtol, atol):
     return dict(ratio=ratio, same_path=same, frac_same_path=float(same.mean()),
                 max_ratio_same_path=float(ratio[same].max()) if same.any() else 0.0,
                 max_ratio=float(ratio.max()), frac_within=float((ratio <= 1.0).mean()))
+
+
+# ---------------------------------------------------------------------------------------------
+# The benchmark configurations of BASELINE.json / SURVEY section 8(d) as (model, settings, varied
+# indices, value generator).  Shared by the emulation tests, the GPU parity tests and bench.py.
+# huang96: the 30 mass-action constants a/d/k are kinetic-law locals, (reaction, parameter) in model order
+HUANG_LOCALS = [(f"r{i}a", f"{c}{i}") for i in range(1, 11) for c in ("a", "d")]
+HUANG_LOCALS = sorted(HUANG_LOCALS + [("r1b", "k2")] + [(f"r{i}b", f"k{i}") for i in range(2, 11)],
+                      key=lambda rp: (int(rp[0][1:-1]), rp[0][-1], rp[1][0] != "a"))
+
+
+def workload(name, nout=None):
+    """Returns dict(model, opt, vary, nominal, span, log10, rtol, atol, nout, end, store) for a config name."""
+    rtol, atol = 1e-6, 1e-9
+    if name == "mapk":
+        m, vary, nominal = mapk_scan_model()
+        end, n_out, span, log10, kw = 1000.0, 100, (-1.0, 1.0), False, {}
+    elif name == "repressilator":
+        m = so.Model(model_path("repressilator_ring.xml"))
+        vary = [m.index(n) for n in ("x1", "x2", "x3", "y1", "y2", "y3")]
+        nominal = np.ones(6)                                  # x_i, y_i = 10^u, u ~ U(-2, 0.5)
+        end, n_out, span, log10, kw = 1000.0, 1000, (-2.0, 0.5), True, {}
+    elif name == "events":
+        m = so.Model(model_path("two_events_one_assignment.xml"))
+        vary = [m.index("S1"), m.index("S2")]
+        nominal = None                                        # S1 ~ U(0.5, 2), S2 ~ U(0, 0.4): linear ranges
+        end, n_out, span, log10, kw = 10.0, 100, None, False, {}
+    elif name == "huang":
+        m = so.Model(model_path("huang_ferrell_cascade.xml"), globalize=HUANG_LOCALS)
+        vary = [m.index(n) for n in m.globalized]
+        nominal = m.base_values()[vary]
+        end, n_out, span, log10, kw = 100.0, 100, (-1.0, 1.0), False, {}
+    elif name == "goodwin":
+        m = so.Model(model_path("goodwin_oscillator.xml"))
+        vary = [m.index(f"k{i}") for i in range(1, 11)]
+        nominal = m.base_values()[vary]
+        end, n_out, span, log10, kw = 100.0, 100, (-1.0, 1.0), False, {}
+    else:
+        raise KeyError(name)
+    if nout is not None:
+        end, n_out = end * nout / n_out, nout
+    opt = so.settings(end, n_out, atol, rtol, **kw)
+    return dict(name=name, model=m, opt=opt, vary=vary, nominal=nominal, span=span, log10=log10,
+                rtol=rtol, atol=atol, nout=n_out, end=end)
+
+
+def workload_values(w, nsets, seed):
+    """Host-side synthetic sets for a workload (numpy generator; the device-side Philox generator is used by bench.py)."""
+    rng = np.random.default_rng(seed)
+    if w["name"] == "events":
+        return np.stack([rng.uniform(0.5, 2.0, nsets), rng.uniform(0.0, 0.4, nsets)], axis=1)
+    lo, hi = w["span"]
+    u = rng.uniform(lo, hi, size=(nsets, len(w["vary"])))
+    return w["nominal"][None, :] * (np.power(10.0, u) if w["log10"] else np.exp2(u))
+
+
+def tpoints(opt, nout):
+    return np.array([so.lib().CvodeSettings_getTime(opt, i) for i in range(nout + 1)])

@@ -1,0 +1,97 @@
+"""CPU tier: the per-trajectory program of the CUDA kernel (generated model section + bdf_kernel.cuh),
+compiled for the HOST by tests/emu/emu_harness.cpp with g++ -ffp-contract=off, must reproduce the oracle.
+
+Against the oracle driven with the SAME emitted right-hand side / Jacobian (ODEModel_generateCSource, the
+reference's compiled mode) the result has to be bit-identical: same steps, same orders, same Newton and
+Jacobian decisions, same arithmetic.  Against the interpreted oracle (evaluateAST semantics) it has to
+agree within max(10 rtol |x|, 10 atol) -- the tolerance the north star states.
+The GPU tier (test_gpu_parity.py) checks the real kernel the same way."""
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+
+def _emulate(w, vals, store=None, tag=None):
+    b = so.Batch(w["model"], w["opt"], w["vary"], store=store)
+    emu = H.Emu(b, tag or w["name"])
+    base, trig = b.base_values()
+    r = emu.run(base, trig, vals, H.tpoints(w["opt"], w["nout"]), 10000, w["rtol"], w["atol"])
+    b.close()
+    return r
+
+
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 24, None), ("repressilator", 8, 200), ("goodwin", 12, None), ("events", 16, None), ("huang", 3, 20)])
+def test_emulated_kernel_is_bit_identical_to_compiled_oracle(name, nsets, nout):
+    w = H.workload(name, nout=nout)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=42)
+    got = _emulate(w, vals)
+    cso = H.compile_c_model(m, name)
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=cso)
+    want = np.transpose(ref["out"], (1, 2, 0))                       # [row][value][set]
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"].T, ref["stats"])
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert np.array_equal(got["out"], want, equal_nan=True)
+    # and within the stated tolerance of the interpreted oracle
+    refi = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"])
+    assert H.parity(got["out"], np.transpose(refi["out"], (1, 2, 0)), w["rtol"], w["atol"]) <= 1.0
+    assert np.array_equal(got["fired"].T, refi["fired"])
+
+
+def test_emulated_store_selection_and_row0():
+    """Only the requested value[] entries are stored; row 0 holds the varied entries (integratorInstance.c:1571-1572)."""
+    w = H.workload("mapk", nout=10)
+    m = w["model"]
+    vals = H.workload_values(w, 4, seed=1)
+    store = [0, 7, 8, m.index("V1")]
+    got = _emulate(w, vals, store=store, tag="mapk_sel")
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, "mapk"))
+    want = np.transpose(ref["out"][:, :, store], (1, 2, 0))
+    assert np.array_equal(got["out"], want)
+    assert np.array_equal(got["out"][0, 3], vals[:, 0])              # V1 is the first varied entry
+
+
+def test_emulated_failure_codes_and_nan_rows():
+    w = H.workload("mapk", nout=4)
+    m = w["model"]
+    vals = H.workload_values(w, 3, seed=2)
+    b = so.Batch(m, w["opt"], w["vary"])
+    emu = H.Emu(b, "mapk_all")
+    base, trig = b.base_values()
+    r = emu.run(base, trig, vals, H.tpoints(w["opt"], 4), 15, w["rtol"], w["atol"])      # mxstep 15 per interval
+    assert (r["status"] == -4).all()                                                    # CV_TOO_MUCH_WORK
+    assert not np.isnan(r["out"][0]).any() and np.isnan(r["out"][1:]).all()
+    b.close()
+
+
+def test_emulated_events_halt_and_no_reset():
+    m = so.Model(H.model_path("two_events_one_assignment.xml"))
+    vary = [m.index("S1"), m.index("S2")]
+    vals = np.array([[1.0, 0.0], [1.7, 0.3], [0.6, 0.1]])
+    for kw in (dict(halt_on_event=1), dict()):
+        opt = so.settings(10.0, 100, 1e-9, 1e-6, **kw)
+        b = so.Batch(m, opt, vary)
+        emu = H.Emu(b, "events_" + ("halt" if kw else "run"))
+        base, trig = b.base_values()
+        got = emu.run(base, trig, vals, H.tpoints(opt, 100), 10000, 1e-6, 1e-9)
+        ref = H.oracle_run(m, opt, vary, vals, 100, compiled_so=H.compile_c_model(m, "events"))
+        assert np.array_equal(got["fired"].T, ref["fired"])
+        assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+        b.close()
+    # nominal set reproduces the reference-semantics firing sequence of SURVEY appendix D
+    fired = ref["fired"][0]
+    assert [(e, i) for i in range(101) for e in (0, 1) if fired[i] >> e & 1][:4] == [(1, 7), (0, 24), (1, 25), (1, 34)]
+
+
+def test_generated_source_has_single_hot_instances():
+    """The block pipeline keeps one instance of the model functions in the instruction stream of the hot loop."""
+    w = H.workload("mapk", nout=10)
+    b = so.Batch(w["model"], w["opt"], w["vary"], store=list(range(8)))
+    src = b.source()
+    assert "sm_100a" in src and "odes_bdf_kernel" in src and "__launch_bounds__" in src
+    assert src.count("DEV void ode_f(") == 1 and src.count("DEV void jacobi_f(") == 1
+    assert "#define NEQ 8" in src and "#define NNZ 26" in src and "#define NVARY 21" in src
+    b.close()

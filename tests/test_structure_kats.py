@@ -1,0 +1,130 @@
+"""Host front-end against the reference's own known-answer tests (tests/golden/kats.json, extracted by
+tests/golden/make_kats.py from unittest/test_odeModel.c:155-358, :564-719 and unittest/test_processAST.c:135-367):
+bit-exact ODE / assignment structure, species indexing and Jacobian sparsity order."""
+import ctypes as C
+import json
+import math
+import os
+
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+KATS = json.load(open(os.path.join(H.ROOT, "tests", "golden", "kats.json")))
+
+
+@pytest.mark.parametrize("kat", KATS["structure"], ids=lambda k: k["model"])
+def test_ode_structure(kat):
+    L = so.lib()
+    m = so.Model(H.model_path(kat["model"]))
+    for fn, want in kat["counts"].items():
+        assert getattr(L, "ODEModel_" + fn)(m.om) == want, fn
+    assert L.ODEModel_hasVariable(m.om, b"no_such_variable") == 0
+    assert not L.ODEModel_hasCycle(m.om)
+    for idx, name, eq in kat["odes"]:
+        assert m.names[idx] == name
+        assert m.index(name) == idx
+        assert m.equation(idx) == eq
+    for idx, _k, name, eq in kat["assignments"]:
+        assert m.names[idx] == name
+        assert m.equation(idx) == eq
+    for idx, _k, name in kat["constants"]:
+        assert m.names[idx] == name
+
+
+@pytest.mark.parametrize("kat", KATS["jacobian"], ids=lambda k: k["model"])
+def test_jacobian_sparsity(kat):
+    m = so.Model(H.model_path(kat["model"]))
+    js = m.jacobian_structure()
+    assert len(js) == kat["nnz"]
+    for n, i, j in kat["elements"]:
+        assert (js[n][0], js[n][1]) == (i, j)
+    # row-major order of the non-zero list (src/odeModel.c:1782-1800)
+    assert [(i, j) for i, j, _ in js] == sorted((i, j) for i, j, _ in js)
+
+
+def _parse(s):
+    n = so.lib().SBML_parseFormula(s.encode())
+    assert n, s
+    return n
+
+
+def _str(node):
+    return so.take_string(so.lib().SBML_formulaToString(node))
+
+
+@pytest.mark.parametrize("inp,want", KATS["evaluate"])
+def test_evaluate_ast(inp, want):
+    L = so.lib()
+    n = _parse(inp)
+    got = L.evaluateAST(n, None)
+    L.ASTNode_free(n)
+    expect = eval(want, {"M_PI": math.pi, "log": math.log, "sqrt": math.sqrt, "cosh": math.cosh, "sinh": math.sinh})
+    assert got == pytest.approx(expect, rel=1e-12, abs=1e-12)
+
+
+@pytest.mark.parametrize("inp,want", KATS["differentiate"])
+def test_differentiate_ast(inp, want):
+    L = so.lib()
+    n = _parse(inp)
+    d = L.differentiateAST(n, b"x")
+    assert _str(d) == want
+    L.ASTNode_free(d)
+    L.ASTNode_free(n)
+
+
+@pytest.mark.parametrize("inp,want", KATS["simplify"])
+def test_simplify_ast(inp, want):
+    L = so.lib()
+    n = _parse(inp)
+    s = L.simplifyAST(n)
+    assert _str(s) == want
+    L.ASTNode_free(s)
+    L.ASTNode_free(n)
+
+
+def test_copy_and_index_ast():
+    L = so.lib()
+    for expr in ["0", "1.5", "foo", "(x + 1) * exp(y) / (pi * log(y - exponentiale))", "lambda(x, y, x + y)"]:
+        n = _parse(expr)
+        c = L.copyAST(n)
+        assert _str(c) == expr
+        L.ASTNode_free(c)
+        L.ASTNode_free(n)
+    names = (C.c_char_p * 5)(b"a", b"b", b"x", b"y", b"z")
+    n = _parse("x + tan(y) / (2 * z)")
+    idx = L.indexAST(n, 5, names)
+    assert _str(idx) == "x + tan(y) / (2 * z)"
+    L.ASTNode_free(idx)
+    L.ASTNode_free(n)
+
+
+def test_settings_defaults_and_time_grid():
+    """unittest/test_integratorSettings.c:29-87: defaults BDF / NEWTON, grid i*Time/PrintStep (integratorSettings.c:416-456)."""
+    L = so.lib()
+    cs = L.CvodeSettings_create()
+    assert L.CvodeSettings_getMethod(cs) == b"BDF"
+    assert L.CvodeSettings_getIterMethod(cs) == b"NEWTON"
+    assert L.CvodeSettings_getMaxOrder(cs) == 5
+    assert L.CvodeSettings_getResetCvodeOnEvent(cs) == 1
+    assert L.CvodeSettings_getHaltOnEvent(cs) == 0
+    assert L.CvodeSettings_getError(cs) == 1e-18 and L.CvodeSettings_getRError(cs) == 1e-10
+    assert L.CvodeSettings_getMxstep(cs) == 10000
+    L.CvodeSettings_free(cs)
+    cs = L.CvodeSettings_createWithTime(10.0, 100)
+    assert L.CvodeSettings_getEndTime(cs) == 10.0 and L.CvodeSettings_getPrintsteps(cs) == 100
+    assert [L.CvodeSettings_getTime(cs, i) for i in (0, 1, 50, 100)] == [0.0, 1 * 10.0 / 100, 50 * 10.0 / 100, 10.0]
+    L.CvodeSettings_free(cs)
+    cs = L.CvodeSettings_createWithTime(0.7, 29)
+    assert L.CvodeSettings_getEndTime(cs) == 0.7 and L.CvodeSettings_getPrintsteps(cs) == 29
+    L.CvodeSettings_free(cs)
+
+
+def test_mapk_globalised_parameters_are_appended():
+    """src/odeSolver.c:354-391: globalised kinetic-law locals get ids r_<reaction>_<param> after the existing constants."""
+    m, vary, nominal = H.mapk_scan_model()
+    assert m.neq == 8 and m.nass == 10 and m.nconst == 4 + 18
+    assert m.names[18:22] == ["uVol", "V1", "Ki", "K1"]
+    assert m.names[22:] == [f"r_{r}_{p}" for r, p in so.MAPK_LOCALS]
+    assert len(vary) == 21 and (nominal > 0).all()
