@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- trajectories/sec of the batched stiff-ODE hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--sets S] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- examples/MAPK.xml parameter scan, 10^6 random kinetic-
+parameter sets PER GPU (weak scaling: rank r integrates sets [r*S, (r+1)*S) of one global Philox-keyed batch),
+rtol 1e-6 / atol 1e-9, t = 0..1000, 100 output points, the 8 species stored.  One "step" = one pass of the hot
+path over that batch (one kernel launch per GPU).
+
+  value      whole-job trajectories/s with inputs resident in HBM (device-generated), timed with CUDA events on the
+             launching stream around exactly K launches, barrier + synchronise on both sides, max over ranks
+  e2e        the same metric through the C-ABI call with HOST buffers (ODESBatch_runHost: pinned host parameter rows
+             in, trajectories out, chunked H2D / kernel / D2H overlap), wall clock, max over ranks
+  roofline   dominant kernel odes_bdf_kernel against the FP64 FMA peak measured live on this GPU (MEASURED_PEAKS.json
+             has no FP64 figure), plus the HBM view of the algorithmic output bytes
+  cpu_baseline  the reference's own CVODE (oracle/_ref, vendored SUNDIALS 2.1.1 compiled unmodified) + the emitted C
+             right-hand side, on all host cores, on a bounded sample of the same seeded sets
+
+--impl reference times only that CPU path (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20261019
+METRIC = "trajectories/sec (MAPK param scan, rtol 1e-6)"
+UNIT = "trajectories/s"
+
+
+def philox_sets(nominal, first, count, lo=-1.0, hi=1.0):
+    """Host restatement of odes_generate_values_kernel (Philox4x32-10, counter = (set, j), key = SEED)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    nv = len(nominal)
+    sets = np.arange(first, first + count, dtype=np.uint64)[:, None] + np.zeros((1, nv), dtype=np.uint64)
+    c = [(sets & 0xFFFFFFFF), (sets >> np.uint64(32)), np.arange(nv, dtype=np.uint64)[None, :] + np.zeros((count, 1), dtype=np.uint64),
+         np.zeros((count, nv), dtype=np.uint64)]
+    k0, k1 = SEED & 0xFFFFFFFF, SEED >> 32
+    for _ in range(10):
+        p0, p1 = c[0] * np.uint64(M0), c[2] * np.uint64(M1)
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & np.uint64(0xFFFFFFFF), p1 >> np.uint64(32), p1 & np.uint64(0xFFFFFFFF)
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    bits = (c[0] << np.uint64(32)) | c[1]
+    u = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return nominal[None, :] * np.exp2(lo + (hi - lo) * u)
+
+
+def count_ops(src):
+    """Arithmetic operations (+ - * / and function calls, one each) in the emitted ode_f and jacobi_f bodies."""
+    out = {}
+    for fn in ("ode_f", "jacobi_f"):
+        m = re.search(r"DEV void %s\(.*?\n\{(.*?)\n\}\n" % fn, src, re.S)
+        body = re.sub(r"\(void\)\w+;", "", m.group(1))
+        stmts = [l.split("=", 1)[1] for l in body.split("\n") if "=" in l and not l.strip().startswith("double")]
+        txt = " ".join(stmts)
+        txt = re.sub(r"\[[0-9]+\]", "", txt)                         # indices
+        txt = re.sub(r"[0-9.]+e[-+][0-9]+", "1", txt)                # exponents of literals
+        out[fn] = len(re.findall(r"[-+*/]", txt)) + len(re.findall(r"\b(pow|exp|log|sqrt|sin|cos|tan|odes_\w+)\(", txt))
+    return out["ode_f"], out["jacobi_f"]
+
+
+def algorithmic_flops(neq, Ff, FJ, mean_stats, qbar=4.0):
+    """F = nfe*F_f + nje*F_J + nsetups*(2n^3/3 + 2n^2) + nni*(2n^2 + 6n) + nst*n*(q(q+1)/2 + 2(q+1) + 10)."""
+    nst, nfe, nsetups, nje, nni = (mean_stats[k] for k in ("nst", "nfe", "nsetups", "nje", "nni"))
+    n = neq
+    return nfe * Ff + nje * FJ + nsetups * (2 * n ** 3 / 3 + 2 * n * n) + nni * (2 * n * n + 6 * n) + nst * n * (qbar * (qbar + 1) / 2 + 2 * (qbar + 1) + 10)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md, clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def reference_arm(args, rank):
+    """The reference's CPU implementation of the path (vendored CVODE 2.3.0 via oracle/_ref when it was built in the
+    container, else the restated port) with all host threads, on bounded samples of the same seeded workload."""
+    if rank != 0:
+        return
+    import helpers as H
+    import sbml_odesolver_b200 as so
+    w = H.workload("mapk")
+    m = w["model"]
+    cores = os.cpu_count() or 1
+    kind = "reference" if H.have_ref() else "port"
+    backend = H.REF if kind == "reference" else H.PORT
+    cso = H.compile_c_model(m, "mapk")
+    per_step = args.ref_sets or max(2048, min(4000 * cores, 400_000))
+    times = []
+    for step in range(args.warmup + args.steps):
+        vals = philox_sets(w["nominal"], step * per_step, per_step)
+        t0 = time.perf_counter()
+        r = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=backend, threads=cores, compiled_so=cso)
+        dt = time.perf_counter() - t0
+        assert (r["status"] == 0).all()
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_step * len(times) / total
+    sample = f"{per_step} sets/step x {len(times)} steps of the seeded MAPK batch (Philox seed {SEED}), {cores} threads, gcc -O2 -ffp-contract=off, emitted C rhs + analytic Jacobian"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "MAPK.xml parameter scan, rtol 1e-6 atol 1e-9, t=0..1000, 100 output points (CPU: bounded sample per step)",
+                       "sets_per_step": per_step, "nvary": len(w["vary"])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sets", type=int, default=1_000_000, help="trajectories per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-sets", type=int, default=0, help="sets per step of the CPU arm (default: scaled to the core count)")
+    ap.add_argument("--cpu-sets", type=int, default=0, help="sample size of the cpu_baseline leg (default: scaled to the core count)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+
+    import helpers as H
+    import sbml_odesolver_b200 as so
+    L = so.lib()
+    if L.ODES_deviceCount() <= local:
+        raise SystemExit("bench.py: no CUDA device for this rank -- the batched integrator has no CPU fallback")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = H.workload("mapk")
+    m, nv, n = w["model"], len(w["vary"]), args.sets
+    store = list(range(m.neq))
+    b = so.Batch(m, w["opt"], w["vary"], store=store, device=local)
+    b.reserve(n)
+    lo, hi = -np.ones(nv), np.ones(nv)
+    first = rank * n
+    b.generate_values(n, SEED, first, w["nominal"], lo, hi)
+    fp64_peak = L.ODES_measureFP64Peak(local, 5) if rank == 0 else 0.0
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        b.integrate(n)
+    launches0 = L.ODESBatch_getNumLaunches(b.h)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    L.ODESBatch_synchronize(b.h)
+    L.ODESBatch_timerStart(b.h)
+    for _ in range(args.steps):
+        b.integrate(n, sync=False)
+    ms = L.ODESBatch_timerStop(b.h)
+    L.ODESBatch_synchronize(b.h)
+    barrier()
+    clocks = sampler.summary()
+    launches = L.ODESBatch_getNumLaunches(b.h) - launches0
+    ms_total = max_over_ranks(ms)
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+    kernel_ms = ms / args.steps                                     # rank-local average launch duration
+    st = b.status(n)
+    stats = b.stats(n)
+    failed = int((st != 0).sum())
+    mean_stats = dict(zip("nst nfe nsetups nje nni ncfn netf".split(), [float(x) for x in stats.mean(axis=1)]))
+
+    # ---------------- end to end through the C ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        rows = b.nrows * b.nstore
+        hv = L.ODES_hostAlloc(n * nv * 8)
+        hr = L.ODES_hostAlloc(rows * n * 8)
+        hs = L.ODES_hostAlloc(n * 4)
+        if not (hv and hr and hs):
+            raise SystemExit("bench.py: pinned host allocation failed")
+        import ctypes as C
+        vals = np.ctypeslib.as_array(C.cast(hv, C.POINTER(C.c_double)), shape=(n, nv))
+        res = np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_double)), shape=(b.nrows, b.nstore, n))
+        hst = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_int)), shape=(n,))
+        chunk = 1 << 16
+        vals[:] = b.get_values(n)                                  # this step's device-generated sets, as host rows
+        for _ in range(2):
+            b.run_host(vals, res, hst, chunk=chunk)
+        launches1 = L.ODESBatch_getNumLaunches(b.h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            b.run_host(vals, res, hst, chunk=chunk)
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt)
+        e2e_launches = L.ODESBatch_getNumLaunches(b.h) - launches1
+        assert int((hst != 0).sum()) == failed
+        # the host-buffer path must deliver the device-resident results (same seeded sets)
+        probe = b.results(min(n, 4096))
+        assert np.array_equal(probe, res[:, :, :probe.shape[2]]), "host path and device-resident path disagree"
+        e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * nv * 8, "d2h_bytes_per_step": rows * n * 8 + n * 4,
+               "ms_per_step": 1e3 * dt / args.steps, "chunk": chunk, "gpu_launches": e2e_launches}
+        L.ODES_hostFree(hv); L.ODES_hostFree(hr); L.ODES_hostFree(hs)
+
+    # ---------------- CPU baseline on the same seeded sets (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        kind = "reference" if H.have_ref() else "port"
+        ns = args.cpu_sets or max(2048, min(4000 * cores, 400_000, n))
+        vals = b.get_values(ns)
+        cso = H.compile_c_model(m, "mapk")
+        t0 = time.perf_counter()
+        ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
+        dt = time.perf_counter() - t0
+        gpu = b.results(ns)
+        rep = H.parity_report(gpu, np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), stats[:, :ns].T, ref["stats"], w["rtol"], w["atol"])
+        cpu = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {ns} sets of this step's batch, {cores} threads, vendored CVODE 2.3.0 + emitted C rhs/Jacobian, gcc -O2 -ffp-contract=off",
+               "parity_on_sample": {"frac_within_10rtol": rep["frac_within"], "frac_same_step_sequence": rep["frac_same_path"], "max_ratio": rep["max_ratio"]},
+               "oracle_mean_stats": dict(zip("nst nfe nsetups nje nni ncfn netf".split(), [float(x) for x in ref["stats"].mean(axis=0)]))}
+
+    if rank == 0:
+        Ff, FJ = count_ops(b.source())
+        F = algorithmic_flops(m.neq, Ff, FJ, mean_stats)
+        achieved = F * n / (kernel_ms * 1e-3) / 1e12
+        out_bytes = 8 * b.nrows * b.nstore + 8 * nv
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")
+        if os.path.exists(prof):
+            pj = json.load(open(prof))
+            if pj.get("sets") and pj.get("dram_bytes") is not None:
+                traffic = pj["dram_bytes"] / pj["sets"] * n        # per launch of this size, scaled from the capture
+        info = b.kernel_info()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "MAPK.xml parameter scan (BASELINE configs[1]): 21 kinetic constants x 2^U(-1,1), rtol 1e-6 atol 1e-9, t=0..1000, 100 output points, 8 species stored",
+                           "sets_per_gpu": n, "nvary": nv, "seed": SEED, "sharding": f"range x{world}, no collective",
+                           "l2": "per step 6.6 GB of outputs + inputs, far larger than the 126 MB L2; no explicit flush"},
+                "failed_sets": failed, "mean_stats": mean_stats, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                             "traffic": traffic, "peak_source": "measured live: ODES_measureFP64Peak (FMA chain micro-benchmark); MEASURED_PEAKS.json holds no FP64 figure",
+                             "flop_per_trajectory": F, "flop_model": {"F_f": Ff, "F_J": FJ, "qbar": 4.0, "formula": "SURVEY 8(d)"},
+                             "kernel": "odes_bdf_kernel", "kernel_ms": kernel_ms, "kernel_info": info,
+                             "hbm_view": {"algorithmic_bytes_per_trajectory": out_bytes, "achieved_gbs": out_bytes * n / (kernel_ms * 1e-3) / 1e9,
+                                          "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    b.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

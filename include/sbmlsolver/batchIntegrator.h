@@ -64,6 +64,8 @@ int ODESBatch_setValues(odesBatch_t *, int nsets, const double *values);
    Philox4x32-10 keyed by seed, counter = (firstSet + set, j)   */
 int ODESBatch_generateValues(odesBatch_t *, int nsets, unsigned long long seed, long long firstSet,
                              const double *base, const double *lo, const double *hi, int log10Scale);
+/* the batch's inputs back on the host as rows [nsets][nvary] */
+int ODESBatch_getValues(odesBatch_t *, int nsets, double *values);
 double *ODESBatch_deviceValues(odesBatch_t *);     /* [nvary][capacity] */
 double *ODESBatch_deviceResults(odesBatch_t *);    /* [nout+1][nstore][capacity] */
 
@@ -72,6 +74,10 @@ int ODESBatch_integrate(odesBatch_t *, int nsets);
 int ODESBatch_synchronize(odesBatch_t *);
 float ODESBatch_getLastKernelMs(const odesBatch_t *);   /* CUDA events on the launching stream */
 int ODESBatch_getNumLaunches(const odesBatch_t *);
+/* stopwatch on the launching stream: Start records an event, Stop records + synchronises a second one
+   and returns the milliseconds in between (-1 on failure) */
+int ODESBatch_timerStart(odesBatch_t *);
+float ODESBatch_timerStop(odesBatch_t *);
 
 /* outputs: device SoA -> host.  results: [nout+1][nstore][nsets] (batch fastest). */
 int ODESBatch_getResults(odesBatch_t *, int nsets, double *results);

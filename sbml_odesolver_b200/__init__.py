@@ -69,10 +69,11 @@ _SIGS = {
     "ODESBatch_reserve": (c_i, [c_p, c_i]), "ODESBatch_getCapacity": (c_i, [c_p]), "ODESBatch_getNout": (c_i, [c_p]),
     "ODESBatch_getNstore": (c_i, [c_p]), "ODESBatch_getSource": (c_s, [c_p]), "ODESBatch_getCompileLog": (c_s, [c_p]),
     "ODESBatch_getKernelInfo": (c_i, [c_p] + [c_p] * 5), "ODESBatch_getBaseValues": (None, [c_p, c_p, c_p]),
-    "ODESBatch_setValues": (c_i, [c_p, c_i, c_p]),
+    "ODESBatch_setValues": (c_i, [c_p, c_i, c_p]), "ODESBatch_getValues": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_generateValues": (c_i, [c_p, c_i, C.c_ulonglong, C.c_longlong, c_p, c_p, c_p, c_i]),
     "ODESBatch_deviceValues": (c_p, [c_p]), "ODESBatch_deviceResults": (c_p, [c_p]),
     "ODESBatch_integrate": (c_i, [c_p, c_i]), "ODESBatch_synchronize": (c_i, [c_p]),
+    "ODESBatch_timerStart": (c_i, [c_p]), "ODESBatch_timerStop": (C.c_float, [c_p]),
     "ODESBatch_getLastKernelMs": (C.c_float, [c_p]), "ODESBatch_getNumLaunches": (c_i, [c_p]),
     "ODESBatch_getResults": (c_i, [c_p, c_i, c_p]), "ODESBatch_getTrajectory": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_getStatus": (c_i, [c_p, c_i, c_p]), "ODESBatch_getStats": (c_i, [c_p, c_i, c_p]),
@@ -223,6 +224,11 @@ class Batch:
         v = np.ascontiguousarray(values, dtype=np.float64)
         _check(lib().ODESBatch_setValues(self.h, v.shape[0], v.ctypes.data), "ODESBatch_setValues")
         return v.shape[0]
+
+    def get_values(self, nsets):
+        v = np.empty((nsets, len(self.vary)))
+        _check(lib().ODESBatch_getValues(self.h, nsets, v.ctypes.data), "ODESBatch_getValues")
+        return v
 
     def generate_values(self, nsets, seed, first_set, base, lo, hi, log10=False):
         base, lo, hi = (np.ascontiguousarray(x, dtype=np.float64) for x in (base, lo, hi))

@@ -295,7 +295,7 @@ struct odesBatch {
   int capacity;
   double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired;
   size_t rowsCap;
-  cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, evIn[2], evK[2], evOut[2];
+  cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
   std::vector<double> base; std::vector<int> trigger0;
 };
@@ -327,6 +327,8 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
     if (b->e0) cudaEventDestroy(b->e0);
     if (b->e1) cudaEventDestroy(b->e1);
+    if (b->t0) cudaEventDestroy(b->t0);
+    if (b->t1) cudaEventDestroy(b->t1);
     for (int i = 0; i < 2; i++) { if (b->evIn[i]) cudaEventDestroy(b->evIn[i]); if (b->evK[i]) cudaEventDestroy(b->evK[i]); if (b->evOut[i]) cudaEventDestroy(b->evOut[i]); }
   }
   CompiledCode_free(b->code);
@@ -488,6 +490,20 @@ extern "C" int ODESBatch_setValues(odesBatch_t *b, int nsets, const double *valu
   return 1;
 }
 
+/* device SoA [nvary][capacity] -> host rows [nsets][nvary] (what setValues was given, or what generateValues made) */
+extern "C" int ODESBatch_getValues(odesBatch_t *b, int nsets, double *values)
+{
+  if (!ensure_loaded(b)) return 0;
+  if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  if (b->nvary == 0 || nsets == 0) return 1;
+  std::vector<double> soa((size_t)b->nvary * (size_t)nsets);
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  CUDA_OK(cudaMemcpy2D(soa.data(), sizeof(double) * (size_t)nsets, b->d_vary, sizeof(double) * (size_t)b->capacity,
+                       sizeof(double) * (size_t)nsets, (size_t)b->nvary, cudaMemcpyDeviceToHost));
+  for (int j = 0; j < b->nvary; j++) for (int s = 0; s < nsets; s++) values[(size_t)s * (size_t)b->nvary + (size_t)j] = soa[(size_t)j * (size_t)nsets + (size_t)s];
+  return 1;
+}
+
 extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long long seed, long long firstSet,
                                         const double *base, const double *lo, const double *hi, int log10Scale)
 {
@@ -535,6 +551,23 @@ extern "C" int ODESBatch_synchronize(odesBatch_t *b)
   CUDA_OK(cudaStreamSynchronize(b->stream));
   if (b->launches) { float ms = 0; if (cudaEventElapsedTime(&ms, b->e0, b->e1) == cudaSuccess) b->lastMs = ms; else cudaGetLastError(); }
   return 1;
+}
+
+/* CUDA-event stopwatch on the launching stream (bench.py times K launches with it) */
+extern "C" int ODESBatch_timerStart(odesBatch_t *b)
+{
+  if (!ensure_loaded(b)) return 0;
+  if (!b->t0) { CUDA_OK(cudaEventCreate(&b->t0)); CUDA_OK(cudaEventCreate(&b->t1)); }
+  CUDA_OK(cudaEventRecord(b->t0, b->stream));
+  return 1;
+}
+extern "C" float ODESBatch_timerStop(odesBatch_t *b)
+{
+  float ms = -1.0f;
+  if (!b->t0) return ms;
+  if (cudaEventRecord(b->t1, b->stream) != cudaSuccess || cudaEventSynchronize(b->t1) != cudaSuccess ||
+      cudaEventElapsedTime(&ms, b->t0, b->t1) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+  return ms;
 }
 
 extern "C" int ODESBatch_getResults(odesBatch_t *b, int nsets, double *results)

