@@ -30,7 +30,7 @@ extern "C" const char odes_bdf_kernel_source[];     /* bdf_kernel.cuh embedded a
 /* argument block of the kernel; must match struct OdesArgs in bdf_kernel.cuh */
 struct OdesArgs {
   const double *vary; double *out; int *status; int *stats; unsigned int *fired; const double *tpoints;
-  unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
+  unsigned long long *counter; unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
 };
 
 /* --------------------------------------------------------------- driver API */
@@ -293,7 +293,7 @@ struct odesBatch {
   compiled_code_t *code; CUfunction kernel;
   int block, minblocks, matLocal; size_t smemBytes;
   int capacity;
-  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired;
+  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot;
   size_t rowsCap;
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
@@ -321,7 +321,7 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
   if (ODES_deviceCount() > b->device) {
     cudaSetDevice(b->device);
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
-    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired);
+    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copyIn) cudaStreamDestroy(b->copyIn);
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
@@ -351,9 +351,9 @@ static std::string build_source(odesBatch_t *b)
   int want = env_int("ODES_THREADS_PER_SM", 128) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   char head[512];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3),
+           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 2), env_int("ODES_REFILL_WAIT", 6),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   src += model;
@@ -410,6 +410,9 @@ static int ensure_loaded(odesBatch_t *b)
     CUDA_OK(cudaEventCreateWithFlags(&b->evK[i], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&b->evOut[i], cudaEventDisableTiming));
   }
+  CUDA_OK(cudaMalloc(&b->d_counter, sizeof(unsigned long long) * 64));
+  { cudaDeviceProp p; CUDA_OK(cudaGetDeviceProperties(&p, b->device)); b->numSMs = p.multiProcessorCount; }
+  { int v = 1; DRV_OK(drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, b->kernel, b->block, b->smemBytes)); b->blocksPerSM = v < 1 ? 1 : v; }
   CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * (size_t)(b->opt->PrintStep + 1)));
   CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
   return 1;
@@ -522,15 +525,21 @@ extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long
   return 1;
 }
 
+/* One launch = one persistent grid (resident blocks only); lanes pull set indices from a device counter.
+   Each launch in flight uses its own counter slot (the pipelined host path has several in flight). */
 static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed)
 {
   OdesArgs a;
   a.vary = b->d_vary + offset; a.out = b->d_out + offset; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
+  a.counter = b->d_counter + (b->counterSlot++ & 63);
   a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;
   a.reltol = b->opt->RError; a.abstol = b->opt->Error;
   void *params[] = { &a };
-  const unsigned grid = (unsigned)((nsets + b->block - 1) / b->block);
+  unsigned grid = (unsigned)((nsets + b->block - 1) / b->block);
+  const unsigned resident = (unsigned)(b->numSMs * b->blocksPerSM);
+  if (grid > resident) grid = resident;
+  CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
   if (timed) CUDA_OK(cudaEventRecord(b->e0, stream));
   DRV_OK(drv.LaunchKernel(b->kernel, grid, 1, 1, (unsigned)b->block, 1, 1, (unsigned)b->smemBytes, (CUstream)stream, params, NULL));
   if (timed) CUDA_OK(cudaEventRecord(b->e1, stream));

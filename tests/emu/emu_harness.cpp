@@ -28,6 +28,8 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   a.vary = vary; a.out = out; a.status = status; a.stats = stats; a.fired = fired; a.tpoints = tpoints;
   a.stride = stride; a.nsets = nsets; a.nout = nout; a.mxstep = mxstep; a.pad = 0; a.reltol = reltol; a.abstol = abstol;
   static double sm[ODES_SMEM_WORDS + 1];
-  for (int s = 0; s < nsets; s++) integrate_set(a, (size_t)s, true, sm);
+  unsigned long long counter = 0;
+  a.counter = &counter;
+  integrate_lanes(a, sm);               /* one emulated lane pulls every set index in turn */
   return 0;
 }
