@@ -342,18 +342,20 @@ static std::string build_source(odesBatch_t *b)
   const int usejac = b->opt->UseJacobian && b->om->jacobian;
   int npv = 0;
   { const char *q = strstr(model, "#define NPV "); if (q) npv = atoi(q + 12); }
-  /* per-thread shared-memory words: M, saved Jacobian, LU rhs, zn[2..5], per-trajectory constants (bdf_kernel.cuh) */
-  const int words = neq * neq + (usejac ? b->om->sparsesize : neq * neq) + neq + 4 * neq + npv + neq + 19;
+  /* per-lane shared-memory words: zn[6], ewt, acor, y, ftemp, M, saved Jacobian, per-trajectory constants,
+     tau/tq/l (ODES_SMEM_WORDS of bdf_kernel.cuh) */
+  const int words = 10 * neq + neq * neq + (usejac ? b->om->sparsesize : neq * neq) + npv + 19;
   b->block = env_int("ODES_BLOCK", 64);
-  b->matLocal = env_int("ODES_MAT_LOCAL", (size_t)words * 8 * (size_t)b->block > 110 * 1024 ? 1 : 0);
+  /* two resident blocks per SM must fit (228 KB per SM, 1 KB reserved per block); otherwise local memory */
+  b->matLocal = env_int("ODES_MAT_LOCAL", (size_t)words * 8 * (size_t)b->block > 112 * 1024 ? 1 : 0);
   b->smemBytes = b->matLocal ? 0 : (size_t)words * 8 * (size_t)b->block;
-  int fit = b->smemBytes ? (int)((227 * 1024) / (b->smemBytes + 1024)) : 8;
-  int want = env_int("ODES_THREADS_PER_SM", 128) / b->block;
+  int fit = b->smemBytes ? (int)((228 * 1024) / (b->smemBytes + 1024)) : 8;
+  int want = env_int("ODES_THREADS_PER_SM", 256) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   char head[512];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 2), env_int("ODES_REFILL_WAIT", 6),
+           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 2), env_int("ODES_REFILL_WAIT", 6), env_int("ODES_COL_UNROLL", 2),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   src += model;
