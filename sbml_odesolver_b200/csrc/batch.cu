@@ -30,7 +30,7 @@ extern "C" const char odes_bdf_kernel_source[];     /* bdf_kernel.cuh embedded a
 /* argument block of the kernel; must match struct OdesArgs in bdf_kernel.cuh */
 struct OdesArgs {
   const double *vary; double *out; int *status; int *stats; unsigned int *fired; const double *tpoints;
-  unsigned long long *counter; unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
+  unsigned long long *counter; double *scratch; unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
 };
 
 /* --------------------------------------------------------------- driver API */
@@ -293,7 +293,7 @@ struct odesBatch {
   compiled_code_t *code; CUfunction kernel;
   int block, minblocks, matLocal; size_t smemBytes;
   int capacity;
-  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot;
+  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot; double *d_scratch; int globalLA, laWords;
   size_t rowsCap;
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
@@ -321,7 +321,7 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
   if (ODES_deviceCount() > b->device) {
     cudaSetDevice(b->device);
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
-    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter);
+    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copyIn) cudaStreamDestroy(b->copyIn);
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
@@ -342,10 +342,13 @@ static std::string build_source(odesBatch_t *b)
   const int usejac = b->opt->UseJacobian && b->om->jacobian;
   int npv = 0;
   { const char *q = strstr(model, "#define NPV "); if (q) npv = atoi(q + 12); }
-  /* per-lane shared-memory words: zn[6], ewt, acor, y, ftemp, M, saved Jacobian, per-trajectory constants,
-     tau/tq/l (ODES_SMEM_WORDS of bdf_kernel.cuh) */
-  const int words = 10 * neq + neq * neq + (usejac ? b->om->sparsesize : neq * neq) + npv + 19;
+  /* per-lane words (bdf_kernel.cuh): on chip zn[6], ewt, acor, y, ftemp, tau/tq/l; the linear-algebra words
+     (M, saved Jacobian, per-trajectory constants) on chip too, or in the L2-resident global scratch */
+  const int chipWords = 10 * neq + 19;
+  b->laWords = neq * neq + (usejac ? b->om->sparsesize : neq * neq) + npv;
   b->block = env_int("ODES_BLOCK", 64);
+  b->globalLA = env_int("ODES_GLOBAL_LA", 0);
+  const int words = chipWords + (b->globalLA ? 0 : b->laWords);
   /* two resident blocks per SM must fit (228 KB per SM, 1 KB reserved per block); otherwise local memory */
   b->matLocal = env_int("ODES_MAT_LOCAL", (size_t)words * 8 * (size_t)b->block > 112 * 1024 ? 1 : 0);
   b->smemBytes = b->matLocal ? 0 : (size_t)words * 8 * (size_t)b->block;
@@ -353,9 +356,9 @@ static std::string build_source(odesBatch_t *b)
   int want = env_int("ODES_THREADS_PER_SM", 256) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   char head[512];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_GLOBAL_LA=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 2), env_int("ODES_REFILL_WAIT", 6), env_int("ODES_COL_UNROLL", 2),
+           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 2), env_int("ODES_REFILL_WAIT", 6), env_int("ODES_COL_UNROLL", 1), b->globalLA,
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   src += model;
@@ -415,6 +418,7 @@ static int ensure_loaded(odesBatch_t *b)
   CUDA_OK(cudaMalloc(&b->d_counter, sizeof(unsigned long long) * 64));
   { cudaDeviceProp p; CUDA_OK(cudaGetDeviceProperties(&p, b->device)); b->numSMs = p.multiProcessorCount; }
   { int v = 1; DRV_OK(drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, b->kernel, b->block, b->smemBytes)); b->blocksPerSM = v < 1 ? 1 : v; }
+  if (b->globalLA) CUDA_OK(cudaMalloc(&b->d_scratch, sizeof(double) * (size_t)b->laWords * (size_t)b->numSMs * (size_t)b->blocksPerSM * (size_t)b->block));
   CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * (size_t)(b->opt->PrintStep + 1)));
   CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
   return 1;
@@ -535,6 +539,7 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   a.vary = b->d_vary + offset; a.out = b->d_out + offset; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
   a.counter = b->d_counter + (b->counterSlot++ & 63);
+  a.scratch = b->d_scratch;
   a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;
   a.reltol = b->opt->RError; a.abstol = b->opt->Error;
   void *params[] = { &a };

@@ -370,7 +370,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   /* per-trajectory constants live in strided shared memory (word k of this thread at p[k*s]) */
   CharBuffer_append(b, "#ifndef ODES_BLOCK\n#define ODES_BLOCK 64\n#endif\n#ifndef ODES_MAT_LOCAL\n#define ODES_MAT_LOCAL 0\n#endif\n"
                        "#if defined(ODES_HOST_EMULATION) || ODES_MAT_LOCAL\n#define ODES_SSTRIDE 1\n#else\n#define ODES_SSTRIDE ODES_BLOCK\n#endif\n"
-                       "struct PvRef { double *p; DEV double &operator[](int k) const { return p[k * ODES_SSTRIDE]; } };\n");
+                       "struct PvRef { double *p; unsigned int s; DEV double &operator[](int k) const { return p[(size_t)k * s]; } };\n");
   CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
   generateMacros(b);
   /* scatter of the saved sparse Jacobian into M = -gamma*J (diagonal +1 is added by the kernel) */

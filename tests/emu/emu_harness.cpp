@@ -30,6 +30,8 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   static double sm[ODES_SMEM_WORDS + 1];
   unsigned long long counter = 0;
   a.counter = &counter;
-  integrate_lanes(a, sm);               /* one emulated lane pulls every set index in turn */
+  static double gscr[ODES_GLOBAL_WORDS + 1];
+  a.scratch = gscr;
+  integrate_lanes(a, sm, gscr, 1u);     /* one emulated lane pulls every set index in turn */
   return 0;
 }
