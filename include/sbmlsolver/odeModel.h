@@ -128,7 +128,7 @@ void generateMacros(charBuffer_t *buffer);
    rules / event_f plus the kernel specialisation macros.  vary[] are value[] indices that
    are per-trajectory inputs (everything else is uniform).  Caller frees. */
 char *ODEModel_generateCUDASource(odeModel_t *, const cvodeSettings_t *, int nvary, const int *vary,
-                                  int nstore, const int *store);
+                                  int nstore, const int *store, const double *base /* values after reset, or NULL */);
 /* Host-C flavour of the same generated functions (the reference's compiled mode), used by
    tests and by the CPU baseline harness.  Caller frees. */
 char *ODEModel_generateCSource(odeModel_t *);

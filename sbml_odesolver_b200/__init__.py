@@ -43,7 +43,7 @@ _SIGS = {
     "ODEModel_constructJacobian": (c_i, [c_p]), "ODEModel_getJacobiElement": (c_p, [c_p, c_i]),
     "ODEModel_getJacobianIJEntry": (c_p, [c_p, c_i, c_i]),
     "ODEModel_generateCSource": (c_p, [c_p]),
-    "ODEModel_generateCUDASource": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p]),
+    "ODEModel_generateCUDASource": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p, c_p]),
     "CvodeSettings_create": (c_p, []), "CvodeSettings_createWithTime": (c_p, [c_d, c_i]),
     "CvodeSettings_createWith": (c_p, [c_d, c_i, c_d, c_d] + [c_i] * 10), "CvodeSettings_free": (None, [c_p]),
     "CvodeSettings_setTime": (c_i, [c_p, c_d, c_i]), "CvodeSettings_setTimeSeries": (c_i, [c_p, c_p, c_i]),

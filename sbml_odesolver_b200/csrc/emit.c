@@ -298,6 +298,7 @@ typedef struct {
   int *kind;          /* [nvalues] storage class                                   */
   int *slot;          /* [nvalues] K_THREAD: index into pv[]; K_ASSIGNED static: pv slot or -1 */
   int *local;         /* [nvalues] 1 if an assigned value is a fresh local a[] in this function */
+  const double *base; /* [nvalues] values after reset, or NULL: uniform constants are then read from c_base[] */
 } kinfo_t;
 
 static void name_cuda(charBuffer_t *s, int idx, const emit_ctx_t *c)
@@ -311,7 +312,11 @@ static void name_cuda(charBuffer_t *s, int idx, const emit_ctx_t *c)
     else cbprintf(s, "pv[%d]", k->slot[idx]);
     break;
   case K_THREAD: cbprintf(s, "pv[%d]", k->slot[idx]); break;
-  default: cbprintf(s, "c_base[%d]", idx);
+  default:
+    /* a constant that no trajectory changes: its value is known now, so x / 1.0, x * 1.0 ... fold at compile time
+       (exactly: these identities hold in IEEE arithmetic) */
+    if (k->base) { CharBuffer_append(s, "("); CharBuffer_appendDouble(s, k->base[idx]); CharBuffer_append(s, ")"); }
+    else cbprintf(s, "c_base[%d]", idx);
   }
 }
 
@@ -332,7 +337,7 @@ static void emit_refresh_all(charBuffer_t *b, const odeModel_t *om, const emit_c
 }
 
 char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
-                                  int nstore, const int *store)
+                                  int nstore, const int *store, const double *base)
 {
   int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac;
   charBuffer_t *b = CharBuffer_create();
@@ -344,6 +349,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   usejac = opt->UseJacobian && om->jacobian;
 
   k.om = om;
+  k.base = base;
   k.kind = (int *)calloc((size_t)nvalues + 1, sizeof(int));
   k.slot = (int *)calloc((size_t)nvalues + 1, sizeof(int));
   k.local = all_local;
@@ -373,10 +379,18 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
                        "struct PvRef { double *p; unsigned int s; DEV double &operator[](int k) const { return p[(size_t)k * s]; } };\n");
   CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
   generateMacros(b);
-  /* scatter of the saved sparse Jacobian into M = -gamma*J (diagonal +1 is added by the kernel) */
-  CharBuffer_append(b, "#define ODES_SCATTER_J(mg)");
-  if (usejac) for (i = 0; i < om->sparsesize; i++) cbprintf(b, " MAT(%d, %d) = SJ(%d) * (mg);", om->jacobSparse[i]->i, om->jacobSparse[i]->j, i);
-  CharBuffer_append(b, "\n");
+  /* scatter of the saved sparse Jacobian into column j of M = -gamma*J (the kernel adds the +1 on the diagonal);
+     j is warp-uniform at the call site, rows and non-zero indices are compile-time constants */
+  CharBuffer_append(b, "#define NP (8 * ((NEQ + 7) / 8))\n#define NSJW (HAS_JAC ? NNZ : NEQ * NP)\n#define NSJP (8 * ((NSJW + 7) / 8))\n#define NPVP (8 * ((NPV + 7) / 8))\n");
+  CharBuffer_append(b, "DEV void scatter_col(int j, double (&c)[A1(NP)], const double (&jnz)[A1(NSJP)], double mg)\n{\n  (void)c; (void)jnz; (void)mg;\n  switch (j) {\n");
+  if (usejac) {
+    for (j = 0; j < om->neq; j++) {
+      cbprintf(b, "  case %d:", j);
+      for (i = 0; i < om->sparsesize; i++) if (om->jacobSparse[i]->j == j) cbprintf(b, " c[%d] = jnz[%d] * mg;", om->jacobSparse[i]->i, i);
+      CharBuffer_append(b, " break;\n");
+    }
+  }
+  CharBuffer_append(b, "  default: break;\n  }\n}\n");
 
   /* model_init: uniform base values, then the varied inputs of this trajectory (SoA, batch fastest) */
   CharBuffer_append(b, "DEV void model_init(double (&y)[A1(NEQ)], const PvRef pv, const double *__restrict__ vary, size_t stride, size_t set)\n{\n");

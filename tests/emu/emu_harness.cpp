@@ -32,6 +32,7 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   a.counter = &counter;
   static double gscr[ODES_GLOBAL_WORDS + 1];
   a.scratch = gscr;
-  integrate_lanes(a, sm, gscr, 1u);     /* one emulated lane pulls every set index in turn */
+  La la; la.sm = sm; la.gm = gscr; la.gs = 1u; la.taddr = 0u;
+  integrate_lanes(a, sm, la);           /* one emulated lane pulls every set index in turn */
   return 0;
 }
