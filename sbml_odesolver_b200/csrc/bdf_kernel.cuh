@@ -67,10 +67,10 @@
 #define ODES_SETUP_WAIT 3
 #endif
 #ifndef ODES_REFILL_MIN
-#define ODES_REFILL_MIN 2
+#define ODES_REFILL_MIN 3
 #endif
 #ifndef ODES_REFILL_WAIT
-#define ODES_REFILL_WAIT 6
+#define ODES_REFILL_WAIT 20
 #endif
 #ifndef ODES_LOCKSTEP
 #define ODES_LOCKSTEP 0
@@ -1225,10 +1225,18 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     ODES_WARP_SYNC();
     {
       const bool want = (s.st == ST_DONE) && !exhausted;
+#if ODES_LOCKSTEP && !defined(ODES_HOST_EMULATION)
+      const int nwant_blk = __syncthreads_count(want);
+      const int nwant = ODES_WARP_COUNT(want);
+      if (nwant_blk > 0) {
+        const bool run = (nwant_blk >= ODES_REFILL_MIN * (ODES_BLOCK / 32)) || (__syncthreads_count(want && idle >= ODES_REFILL_WAIT) > 0);
+        if (run && nwant > 0) {
+#else
       const int nwant = ODES_WARP_COUNT(want);
       if (nwant > 0) {
         const bool run = (nwant >= ODES_REFILL_MIN) || ODES_WARP_ANY(want && idle >= ODES_REFILL_WAIT) || ODES_WARP_ALL(s.st == ST_DONE);
         if (run) {
+#endif
           const unsigned long long next = odes_take_sets(a.counter, want, nwant);
           const bool take = want && next < (unsigned long long)a.nsets;
           if (want && !take) exhausted = true;
@@ -1295,13 +1303,20 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       ODES_WARP_SYNC();
     }
     /* ---- SETUP: run when enough lanes want it, one of them has waited long enough, or nobody
-       else can make progress; waiting lanes simply re-enter here in the next pass ---- */
+       else can make progress; waiting lanes simply re-enter here in the next pass.  In lock step the vote is taken
+       over the whole block, so its warps factor together and stay aligned ---- */
     {
       const bool want = (s.st == ST_SETUP);
+#if ODES_LOCKSTEP && !defined(ODES_HOST_EMULATION)
+      const int nwant = __syncthreads_count(want);
+      if (nwant > 0) {
+        const bool run = (nwant >= ODES_SETUP_MIN * (ODES_BLOCK / 32)) || (__syncthreads_count(want && s.waited >= ODES_SETUP_WAIT) > 0);
+#else
       const int nwant = ODES_WARP_COUNT(want);
       if (nwant > 0) {
         const bool run = (nwant >= ODES_SETUP_MIN) || ODES_WARP_ANY(want && s.waited >= ODES_SETUP_WAIT) ||
                          ODES_WARP_ALL(want || s.st == ST_DONE);
+#endif
         if (run) { const int rc = s.blk_setup(want); if (want && rc < 0) { status = rc; s.st = ST_FINISH; } }
         else if (want) s.waited++;
         ODES_WARP_SYNC();
