@@ -151,7 +151,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
       if (e == 1.0) { gen_nested(s, n->children[0], c); break; }          /* pow(x,1) == x exactly  */
       if (e == 2.0) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
     }
-    gen_call(s, n, "pow", c); break;
+    gen_call(s, n, c->cuda ? "odes_pow" : "pow", c); break;
   case AST_INTEGER: CharBuffer_appendDouble(s, (double)n->ival); break;
   case AST_REAL: case AST_REAL_E: case AST_RATIONAL: CharBuffer_appendDouble(s, ASTNode_getReal(n)); break;
   case AST_NAME:
@@ -259,7 +259,7 @@ void generateMacros(charBuffer_t *b)
     "DEV double odes_sech(double x) { return 1. / cosh(x); }\n"
     "DEV double odes_logbase(double base, double x) { return log10(x) / log10(base); }\n"
     "DEV double odes_root(double degree, double x)\n"
-    "{ if (degree == floor(degree) && x < 0 && ((int)degree % 2 != 0)) return -pow(fabs(x), 1. / degree); return pow(x, 1. / degree); }\n"
+    "{ if (degree == floor(degree) && x < 0 && ((int)degree % 2 != 0)) return -ODES_POW(fabs(x), 1. / degree); return ODES_POW(x, 1. / degree); }\n"
     "DEV double odes_factorial(double x) { double r; int j = (int)floor(x); for (r = 1; j > 1; --j) r *= j; return r; }\n");
 }
 
@@ -270,7 +270,7 @@ char *ODEModel_generateCSource(odeModel_t *om)
   emit_ctx_t c; int i; char *out;
   c.cuda = 0; c.name = name_value; c.time = "t"; c.info = NULL;
   if (!om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
-  CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n");
+  CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n#define ODES_POW pow\n");
   generateMacros(b);
   CharBuffer_append(b, "void ode_f(double t, const double *y, double *ydot, double *value)\n{\n  (void)t;\n");
   for (i = 0; i < om->neq; i++) cbprintf(b, "  value[%d] = y[%d];\n", i, i);
@@ -378,6 +378,8 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
                        "#if defined(ODES_HOST_EMULATION) || ODES_MAT_LOCAL\n#define ODES_SSTRIDE 1\n#else\n#define ODES_SSTRIDE ODES_BLOCK\n#endif\n"
                        "struct PvRef { double *p; unsigned int s; DEV double &operator[](int k) const { return p[(size_t)k * s]; } };\n");
   CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
+  /* pow as the host libm computes it (glibc_pow.inc, defined after this section) */
+  CharBuffer_append(b, "DEV double odes_pow(double x, double y);\n#define ODES_POW odes_pow\n");
   generateMacros(b);
   /* scatter of the saved sparse Jacobian into column j of M = -gamma*J (the kernel adds the +1 on the diagonal);
      j is warp-uniform at the call site, rows and non-zero indices are compile-time constants */

@@ -2,9 +2,10 @@
 against the oracle on the same seeded inputs.
 
 Gate (north star): every output point within max(10 rtol |x|, 10 atol) of the reference's own CVODE integration,
-identical event firing order, identical failure flags.  The kernel replays CVODE's decisions exactly, so beyond
-that gate the tests also require the same per-trajectory work counters (nst, nfe, nsetups, nje, nni, ncfn, netf)
-for (nearly) all sets: a trajectory whose counters equal the oracle's took the same steps at the same orders."""
+identical event firing order, identical failure flags.  The kernel replays CVODE's arithmetic exactly (IEEE
+operations in the reference's order, no FMA contraction, glibc's pow restated), so the tests demand more than the
+gate: the same per-trajectory work counters (nst, nfe, nsetups, nje, nni, ncfn, netf) and BIT-IDENTICAL stored
+values against the oracle driven with the same emitted right-hand side (the reference's compiled mode)."""
 import numpy as np
 import pytest
 
@@ -28,9 +29,8 @@ def _oracle(w, vals):
     return H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, w["name"]), threads=8)
 
 
-@pytest.mark.parametrize("name,nsets,nout,min_same", [("mapk", 512, None, 0.97), ("repressilator", 96, 200, 0.95),
-                                                     ("goodwin", 256, None, 0.95), ("huang", 64, 20, 0.9)])
-def test_parity_with_oracle(name, nsets, nout, min_same):
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 1024, None), ("repressilator", 96, 200), ("goodwin", 256, None), ("huang", 128, None)])
+def test_parity_with_oracle(name, nsets, nout):
     w = H.workload(name, nout=nout)
     vals = H.workload_values(w, nsets, seed=2026)
     got = _gpu_run(w, vals)
@@ -38,12 +38,12 @@ def test_parity_with_oracle(name, nsets, nout, min_same):
     want = np.transpose(ref["out"], (1, 2, 0))
     assert np.array_equal(got["status"], ref["status"])
     rep = H.parity_report(got["out"], want, got["stats"], ref["stats"], w["rtol"], w["atol"])
-    print(name, {k: v for k, v in rep.items() if k not in ("ratio", "same_path")}, got["info"])
-    assert rep["frac_same_path"] >= min_same, rep
-    assert rep["max_ratio_same_path"] <= 1.0, rep
-    # tolerance gate: max(10 rtol |x|, 10 atol) at every output point
-    assert rep["frac_within"] >= 0.995, rep
-    assert rep["max_ratio"] <= 20.0, rep
+    bitident = float(np.mean([np.array_equal(got["out"][:, :, k], want[:, :, k], equal_nan=True) for k in range(nsets)]))
+    print(name, {k: v for k, v in rep.items() if k not in ("ratio", "same_path")}, "bit-identical sets", bitident, got["info"])
+    # tolerance gate: max(10 rtol |x|, 10 atol) at every output point -- and in fact bit for bit
+    assert rep["frac_within"] == 1.0 and rep["max_ratio"] <= 1.0, rep
+    assert rep["frac_same_path"] == 1.0, rep
+    assert bitident == 1.0, (bitident, rep)
 
 
 def test_event_order_identical():
