@@ -67,7 +67,7 @@ int ODESBatch_generateValues(odesBatch_t *, int nsets, unsigned long long seed, 
 /* the batch's inputs back on the host as rows [nsets][nvary] */
 int ODESBatch_getValues(odesBatch_t *, int nsets, double *values);
 double *ODESBatch_deviceValues(odesBatch_t *);     /* [nvary][capacity] */
-double *ODESBatch_deviceResults(odesBatch_t *);    /* [nout+1][nstore][capacity] */
+double *ODESBatch_deviceResults(odesBatch_t *);    /* [capacity][nout+1][nstore] */
 
 /* run: asynchronous launch on the plan's stream, then explicit synchronisation */
 int ODESBatch_integrate(odesBatch_t *, int nsets);
@@ -79,7 +79,8 @@ int ODESBatch_getNumLaunches(const odesBatch_t *);
 int ODESBatch_timerStart(odesBatch_t *);
 float ODESBatch_timerStop(odesBatch_t *);
 
-/* outputs: device SoA -> host.  results: [nout+1][nstore][nsets] (batch fastest). */
+/* outputs: device -> host.  results: [nsets][nout+1][nstore] (one contiguous time-major block per trajectory,
+   the layout of the reference's cvodeResults_t per design point). */
 int ODESBatch_getResults(odesBatch_t *, int nsets, double *results);
 int ODESBatch_getTrajectory(odesBatch_t *, int set, double *traj /* [nout+1][nstore] */);
 int ODESBatch_getStatus(odesBatch_t *, int nsets, int *status);

@@ -23,7 +23,7 @@ typedef struct batchResults {
   int nsets, nout, nvalues;      /* nout = number of time points (PrintStep+1) */
   char **names;                  /* [nvalues] */
   double *time;                  /* [nout] */
-  double *value;                 /* [nout][nvalues][nsets] */
+  double *value;                 /* [nsets][nout][nvalues] */
   int *status;                   /* [nsets] */
 } batchResults_t;
 

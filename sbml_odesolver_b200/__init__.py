@@ -247,9 +247,10 @@ class Batch:
         return lib().ODESBatch_getLastKernelMs(self.h)
 
     def results(self, nsets):
-        out = np.empty((self.nrows, self.nstore, nsets))
+        """Stored trajectories as a [row][value][set] VIEW of the library's [set][row][value] block."""
+        out = np.empty((nsets, self.nrows, self.nstore))
         _check(lib().ODESBatch_getResults(self.h, nsets, out.ctypes.data), "ODESBatch_getResults")
-        return out
+        return np.transpose(out, (1, 2, 0))
 
     def status(self, nsets):
         st = np.empty(nsets, dtype=np.int32)

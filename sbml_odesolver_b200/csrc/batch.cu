@@ -561,7 +561,7 @@ extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long
 static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed)
 {
   OdesArgs a;
-  a.vary = b->d_vary + offset; a.out = b->d_out + offset; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
+  a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
   a.counter = b->d_counter + (b->counterSlot++ & 63);
   a.scratch = b->d_scratch;
@@ -614,17 +614,20 @@ extern "C" float ODESBatch_timerStop(odesBatch_t *b)
 extern "C" int ODESBatch_getResults(odesBatch_t *b, int nsets, double *results)
 {
   CUDA_OK(cudaSetDevice(b->device));
-  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
-  CUDA_OK(cudaMemcpy2DAsync(results, sizeof(double) * (size_t)nsets, b->d_out, sizeof(double) * (size_t)b->capacity,
-                            sizeof(double) * (size_t)nsets, rows, cudaMemcpyDeviceToHost, b->stream));
+  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore;
+  if (b->nout == b->opt->PrintStep)
+    CUDA_OK(cudaMemcpyAsync(results, b->d_out, sizeof(double) * per * (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
+  else       /* shortened grid (single-instance restarts): rows [0, nout] of every trajectory */
+    CUDA_OK(cudaMemcpy2DAsync(results, sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, b->d_out, sizeof(double) * per,
+                              sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return 1;
 }
 extern "C" int ODESBatch_getTrajectory(odesBatch_t *b, int set, double *traj)
 {
   CUDA_OK(cudaSetDevice(b->device));
-  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
-  CUDA_OK(cudaMemcpy2D(traj, sizeof(double), b->d_out + set, sizeof(double) * (size_t)b->capacity, sizeof(double), rows, cudaMemcpyDeviceToHost));
+  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore;
+  CUDA_OK(cudaMemcpy(traj, b->d_out + (size_t)set * per, sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, cudaMemcpyDeviceToHost));
   return 1;
 }
 extern "C" int ODESBatch_getStatus(odesBatch_t *b, int nsets, int *status)
@@ -649,11 +652,11 @@ extern "C" int ODESBatch_getEventLog(odesBatch_t *b, int nsets, unsigned int *fi
 
 /* End-to-end helper with HOST buffers: the batch is cut into chunks; H2D of chunk k+1, the kernel of
    chunk k and D2H of chunk k-1 overlap on three streams.  values: [nsets][nvary] rows,
-   results: [nout+1][nstore][nsets]. */
+   results: [nsets][nout+1][nstore]. */
 extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
 {
   if (!ODESBatch_reserve(b, nsets)) return 0;
-  if (chunk <= 0) chunk = 1 << 16;
+  if (chunk <= 0) chunk = 1 << 18;
   chunk = (chunk + 31) & ~31;
   const int nchunks = (nsets + chunk - 1) / chunk;
   const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
@@ -673,8 +676,7 @@ extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values
     CUDA_OK(cudaEventRecord(b->evK[slot], b->stream));
     CUDA_OK(cudaStreamWaitEvent(b->copyOut, b->evK[slot], 0));
     if (results)
-      CUDA_OK(cudaMemcpy2DAsync(results + off, sizeof(double) * (size_t)nsets, b->d_out + off, sizeof(double) * (size_t)b->capacity,
-                                sizeof(double) * (size_t)n, rows, cudaMemcpyDeviceToHost, b->copyOut));
+      CUDA_OK(cudaMemcpyAsync(results + off * rows, b->d_out + off * rows, sizeof(double) * (size_t)n * rows, cudaMemcpyDeviceToHost, b->copyOut));
     if (status) CUDA_OK(cudaMemcpyAsync(status + off, b->d_status + off, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, b->copyOut));
   }
   CUDA_OK(cudaStreamSynchronize(b->copyOut));
@@ -697,14 +699,9 @@ extern "C" int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int n
   if (!b) return -1;
   int failed = -1;
   std::vector<int> st((size_t)nsets);
-  std::vector<double> soa;
-  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
-  if (out) soa.resize(rows * (size_t)nsets);
-  if (ODESBatch_runHost(b, nsets, values, out ? soa.data() : NULL, st.data(), 0)) {
+  if (ODESBatch_runHost(b, nsets, values, out, st.data(), 0)) {       /* out is already [nsets][nout+1][nvalues] */
     failed = 0;
     for (int s = 0; s < nsets; s++) { if (st[(size_t)s] < 0) failed++; if (status) status[s] = st[(size_t)s]; }
-    if (out)                                     /* [rows][nsets] -> [nsets][nout+1][nvalues] */
-      for (size_t r = 0; r < rows; r++) for (int s = 0; s < nsets; s++) out[(size_t)s * rows + r] = soa[r * (size_t)nsets + (size_t)s];
   }
   ODESBatch_free(b);
   return failed;

@@ -117,7 +117,7 @@ double BatchResults_getValue(const batchResults_t *r, int set, const char *name,
 {
   int i;
   for (i = 0; i < r->nvalues; i++)
-    if (strcmp(r->names[i], name) == 0) return r->value[((size_t)timestep * (size_t)r->nvalues + (size_t)i) * (size_t)r->nsets + (size_t)set];
+    if (strcmp(r->names[i], name) == 0) return r->value[((size_t)set * (size_t)r->nout + (size_t)timestep) * (size_t)r->nvalues + (size_t)i];
   SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_SYMBOL_IS_NOT_IN_MODEL, "Symbol %s is not in the model", name);
   return 0.0;
 }

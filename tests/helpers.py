@@ -95,14 +95,15 @@ class Emu:
         nsets = values.shape[0]
         nout = len(tpoints) - 1
         vary = np.ascontiguousarray(values.T)                      # SoA [nvary][nsets]
-        out = np.zeros((nout + 1, b.nstore, nsets))
+        raw = np.zeros((nsets, nout + 1, b.nstore))                # the library's [set][row][value] layout
+        out = np.transpose(raw, (1, 2, 0))                         # viewed as [row][value][set]
         status = np.zeros(nsets, dtype=np.int32)
         stats = np.zeros((7, nsets), dtype=np.int32)
         fired = np.zeros((nout + 1, nsets), dtype=np.uint32)
         base = np.ascontiguousarray(base, dtype=np.float64)
         trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
         tp = np.ascontiguousarray(tpoints, dtype=np.float64)
-        self.lib.emu_run(C.c_void_p(base.ctypes.data), C.c_void_p(trig0.ctypes.data), C.c_void_p(vary.ctypes.data), C.c_void_p(out.ctypes.data),
+        self.lib.emu_run(C.c_void_p(base.ctypes.data), C.c_void_p(trig0.ctypes.data), C.c_void_p(vary.ctypes.data), C.c_void_p(raw.ctypes.data),
                          C.c_void_p(status.ctypes.data), C.c_void_p(stats.ctypes.data), C.c_void_p(fired.ctypes.data), C.c_void_p(tp.ctypes.data),
                          C.c_ulonglong(nsets), C.c_int(nsets), C.c_int(nout), C.c_int(mxstep), C.c_double(rtol), C.c_double(atol))
         return dict(out=out, status=status, stats=stats, fired=fired)

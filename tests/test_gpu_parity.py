@@ -123,10 +123,10 @@ def test_run_host_pipeline_and_one_shot_entry():
     b.set_values(vals)
     b.integrate(1000)
     direct = b.results(1000)
-    res = np.zeros_like(direct)
+    res = np.zeros((1000, direct.shape[0], direct.shape[1]))          # [set][row][value], the library's layout
     st = np.zeros(1000, dtype=np.int32)
     b.run_host(vals, res, st, chunk=256)
-    assert np.array_equal(res, direct) and (st == 0).all()
+    assert np.array_equal(np.transpose(res, (1, 2, 0)), direct) and (st == 0).all()
     b.close()
     ii = L.IntegratorInstance_create(m.om, w["opt"])
     assert ii
