@@ -1,0 +1,62 @@
+"""The C example callers (examples/*.c) are drop-in users of the kept API: they compile against include/ with a C99
+compiler, and on a GPU box reproduce the reference's golden output (examples/testrun.out:27-129 is the reference's
+`integrate MAPK.xml 1000 100`)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+EX = os.path.join(H.ROOT, "examples")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", EX])
+    return os.path.join(EX, "_build")
+
+
+def test_examples_compile_as_c99():
+    d = _build()
+    assert os.path.exists(os.path.join(d, "integrate_timecourse")) and os.path.exists(os.path.join(d, "parameter_scan"))
+
+
+@pytest.mark.skipif(so.lib().ODES_deviceCount() > 0, reason="needs a box without a GPU")
+def test_example_fails_loudly_without_gpu():
+    d = _build()
+    r = subprocess.run([os.path.join(d, "integrate_timecourse"), H.model_path("mapk_cascade.xml"), "1000", "100"], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "CUDA" in r.stderr and "Integration not sucessful" in r.stderr
+
+
+@pytest.mark.gpu
+def test_integrate_timecourse_reproduces_testrun_golden():
+    d = _build()
+    r = subprocess.run([os.path.join(d, "integrate_timecourse"), H.model_path("mapk_cascade.xml"), "1000", "100"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert lines[0] == "#time MKKK MKKK_P MKK MKK_P MKK_PP MAPK MAPK_P MAPK_PP"
+    gold = [l.strip() for l in open(os.path.join(H.ROOT, "tests", "golden", "mapk_testrun.txt")) if not l.startswith("#")]
+    assert lines[1:] == gold                                    # every printed character of the 101 rows
+
+
+@pytest.mark.gpu
+def test_parameter_scan_matches_oracle():
+    d = _build()
+    r = subprocess.run([os.path.join(d, "parameter_scan"), H.model_path("mapk_cascade.xml"), "1000", "50", "KK2", "J1", "4", "16", "7"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split() for l in r.stdout.strip().split("\n")]
+    names = rows[0][1:-1]
+    got = np.array([[float(x) for x in row[1:-1]] for row in rows[1:]])
+    m = so.Model(H.model_path("mapk_cascade.xml"), globalize=[("J1", "KK2")])
+    assert names == m.names
+    opt = so.settings(1000.0, 50, 1e-9, 1e-6)
+    vals = np.linspace(4.0, 16.0, 7)[:, None]
+    ref = H.oracle_run(m, opt, [m.index("r_J1_KK2")], vals, 50)
+    want = ref["out"][:, 50, :]
+    tol = np.maximum(10 * 1e-6 * np.abs(want), 10 * 1e-9)
+    assert (np.abs(got - want) <= tol + 1e-9 * np.abs(want)).all()      # printed with 10 digits
+    assert all(row[-1] == "0" for row in rows[1:])
