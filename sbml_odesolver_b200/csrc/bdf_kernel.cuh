@@ -83,10 +83,13 @@
 #define ODES_GESL_UNROLL 8
 #endif
 /* ODES_LOCKSTEP 2 re-aligns the warps of a block before every block of the pass as well */
+#ifndef ODES_ALIGN_MASK
+#define ODES_ALIGN_MASK 7          /* which block boundaries re-align: 1 PRE, 2 F, 4 NEWTON, 8 COMPLETE */
+#endif
 #if ODES_LOCKSTEP >= 2 && !defined(ODES_HOST_EMULATION)
-#define ODES_BLOCK_ALIGN() __syncthreads()
+#define ODES_BLOCK_ALIGN(bit) do { if (ODES_ALIGN_MASK & (bit)) __syncthreads(); } while (0)
 #else
-#define ODES_BLOCK_ALIGN() ((void)0)
+#define ODES_BLOCK_ALIGN(bit) ((void)0)
 #endif
 
 /* warp-level primitives; the host emulation of the per-trajectory program has no warp */
@@ -1306,14 +1309,14 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       ODES_WARP_SYNC();
     }
     /* ---- PRE ---- */
-    ODES_BLOCK_ALIGN();
+    ODES_BLOCK_ALIGN(1);
     if (s.st == ST_PRE) {
       const int rc = s.blk_pre(a.mxstep);
       if (rc < 0) { status = rc; s.st = ST_FINISH; }
     }
     ODES_WARP_SYNC();
     /* ---- F: the model's right-hand side ---- */
-    ODES_BLOCK_ALIGN();
+    ODES_BLOCK_ALIGN(2);
     if (ODES_WARP_ANY(s.st == ST_F)) {
       const bool act = (s.st == ST_F);
       s.f(s.tn, act);
@@ -1341,7 +1344,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       }
     }
     /* ---- NEWTON ---- */
-    ODES_BLOCK_ALIGN();
+    ODES_BLOCK_ALIGN(4);
     if (ODES_WARP_ANY(s.st == ST_NEWTON)) {
       const bool act = (s.st == ST_NEWTON);
       const int rc = s.blk_newton(act);
@@ -1349,7 +1352,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       ODES_WARP_SYNC();
     }
     /* ---- COMPLETE ---- */
-    ODES_BLOCK_ALIGN();
+    ODES_BLOCK_ALIGN(8);
     if (s.st == ST_COMPLETE) {
       s.blk_complete(tout);
       if (s.after_step(tout, t)) s.st = ST_OUTPUT;
