@@ -1,0 +1,106 @@
+"""Front-end breadth: synthetic SBML Level 2 models with function definitions, initial
+assignments, rate and assignment rules, piecewise terms, stoichiometryMath, relational/logical operators and
+events go through the whole host chain -- reader, ODE construction, symbolic Jacobian, emitter -- and the emulated
+kernel must reproduce the oracle (same emitted right-hand side: bit for bit; interpreter: within tolerance)."""
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+M = 'xmlns="http://www.w3.org/1998/Math/MathML"'
+
+FEATURES = f'''<?xml version="1.0" encoding="UTF-8"?>
+<sbml xmlns="http://www.sbml.org/sbml/level2" level="2" version="1">
+ <model id="features">
+  <listOfFunctionDefinitions>
+   <functionDefinition id="mm">
+    <math {M}><lambda><bvar><ci>v</ci></bvar><bvar><ci>s</ci></bvar><bvar><ci>k</ci></bvar>
+     <apply><divide/><apply><times/><ci>v</ci><ci>s</ci></apply><apply><plus/><ci>k</ci><ci>s</ci></apply></apply></lambda></math>
+   </functionDefinition>
+  </listOfFunctionDefinitions>
+  <listOfCompartments><compartment id="c" size="2"/></listOfCompartments>
+  <listOfSpecies>
+   <species id="A" compartment="c" initialConcentration="4"/>
+   <species id="B" compartment="c" initialConcentration="0.5"/>
+   <species id="C" compartment="c" initialConcentration="0"/>
+   <species id="E" compartment="c" initialConcentration="1" boundaryCondition="true"/>
+  </listOfSpecies>
+  <listOfParameters>
+   <parameter id="vmax" value="1.5"/><parameter id="km" value="0.8"/><parameter id="kd" value="0.3"/>
+   <parameter id="gain" value="0" constant="false"/><parameter id="x" value="0.1" constant="false"/>
+   <parameter id="thr" value="2.5"/><parameter id="x0" value="0"/>
+  </listOfParameters>
+  <listOfInitialAssignments>
+   <initialAssignment symbol="x0"><math {M}><apply><times/><cn>2</cn><ci>km</ci></apply></math></initialAssignment>
+  </listOfInitialAssignments>
+  <listOfRules>
+   <assignmentRule variable="gain"><math {M}><piecewise><piece><cn>2</cn><apply><gt/><ci>A</ci><ci>thr</ci></apply></piece><otherwise><cn>0.5</cn></otherwise></piecewise></math></assignmentRule>
+   <rateRule variable="x"><math {M}><apply><minus/><apply><times/><ci>gain</ci><ci>B</ci></apply><apply><times/><ci>kd</ci><ci>x</ci></apply></apply></math></rateRule>
+  </listOfRules>
+  <listOfReactions>
+   <reaction id="r1" reversible="false">
+    <listOfReactants><speciesReference species="A"/></listOfReactants>
+    <listOfProducts><speciesReference species="B"><stoichiometryMath><math {M}><apply><plus/><cn>1</cn><cn>1</cn></apply></math></stoichiometryMath></speciesReference></listOfProducts>
+    <listOfModifiers><modifierSpeciesReference species="E"/></listOfModifiers>
+    <kineticLaw><math {M}><apply><times/><ci>c</ci><ci>E</ci><apply><ci>mm</ci><ci>vmax</ci><ci>A</ci><ci>km</ci></apply></apply></math></kineticLaw>
+   </reaction>
+   <reaction id="r2" reversible="false">
+    <listOfReactants><speciesReference species="B"/></listOfReactants>
+    <listOfProducts><speciesReference species="C"/></listOfProducts>
+    <kineticLaw><math {M}><apply><times/><ci>c</ci><ci>k2</ci><ci>B</ci><apply><power/><apply><plus/><cn>1</cn><ci>x</ci></apply><cn>1.5</cn></apply></apply></math>
+     <listOfParameters><parameter id="k2" value="0.4"/></listOfParameters></kineticLaw>
+   </reaction>
+  </listOfReactions>
+  <listOfEvents>
+   <event id="refill"><trigger><math {M}><apply><and/><apply><lt/><ci>A</ci><cn>0.5</cn></apply><apply><geq/><ci>C</ci><cn>1</cn></apply></apply></math></trigger>
+    <listOfEventAssignments><eventAssignment variable="A"><math {M}><apply><plus/><ci>A</ci><cn>3</cn></apply></math></eventAssignment></listOfEventAssignments>
+   </event>
+  </listOfEvents>
+ </model>
+</sbml>
+'''
+
+
+@pytest.fixture(scope="module")
+def features_model(tmp_path_factory):
+    p = tmp_path_factory.mktemp("m") / "features.xml"
+    p.write_text(FEATURES)
+    return so.Model(str(p))
+
+
+def test_structure_of_the_feature_model(features_model):
+    m = features_model
+    assert m.neq == 4 and m.names[:4] == ["x", "A", "B", "C"]            # predefined rate rule first, then species
+    assert m.nass == 3                                                   # gain + one per reaction
+    eq = {m.names[i]: m.equation(i) for i in range(m.neq + m.nass)}
+    assert eq["x"] == "gain * B - kd * x"
+    assert eq["A"] == "-(r1 / c)" and eq["C"] == "r2 / c"          # unary minus like unittest/test_odeModel.c:247
+    assert eq["B"] == "((1 + 1) * r1 - r2) / c"                            # stoichiometryMath multiplies the rate
+    assert eq["r1"] == "c * E * (vmax * A / (km + A))"                   # function definition inlined
+    assert eq["r2"] == "c * 0.4 * B * (1 + x)^1.5"                        # local parameter replaced by its value
+    assert "piecewise" in eq["gain"]
+    assert m.base_values()[m.index("x0")] == 0.0                         # initial assignment applies at reset, not in the file values
+
+
+@pytest.mark.parametrize("halt", [0, 1])
+def test_feature_model_emulated_kernel_vs_oracle(features_model, halt):
+    m = features_model
+    vary = [m.index(n) for n in ("vmax", "km", "kd", "A")]
+    rng = np.random.default_rng(3)
+    vals = np.stack([rng.uniform(0.5, 3, 24), rng.uniform(0.2, 2, 24), rng.uniform(0.05, 1, 24), rng.uniform(1, 6, 24)], axis=1)
+    opt = so.settings(40.0, 80, 1e-9, 1e-6, halt_on_event=halt)
+    b = so.Batch(m, opt, vary)
+    base, trig = b.base_values()
+    assert base[m.index("x0")] == pytest.approx(1.6)                     # 2*km with the model's own km
+    got = H.Emu(b, f"features{halt}").run(base, trig, vals, H.tpoints(opt, 80), 10000, 1e-6, 1e-9)
+    ref = H.oracle_run(m, opt, vary, vals, 80, compiled_so=H.compile_c_model(m, "features"))
+    assert np.array_equal(got["fired"].T, ref["fired"]) and ref["fired"].any()
+    assert np.array_equal(got["status"], ref["status"]) and np.array_equal(got["stats"].T, ref["stats"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    refi = H.oracle_run(m, opt, vary, vals, 80, want_margin=True)
+    safe = (refi["margin"] > 1e-4).all(axis=1)
+    assert safe.mean() > 0.8
+    assert np.array_equal(got["fired"].T[safe], refi["fired"][safe])
+    assert H.parity(got["out"][:, :, safe], np.transpose(refi["out"], (1, 2, 0))[:, :, safe], 1e-6, 1e-9) <= 1.0
+    b.close()

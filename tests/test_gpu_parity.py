@@ -167,3 +167,26 @@ def test_full_size_properties():
     b.integrate(n)
     assert np.array_equal(b.results(n), out)
     b.close(); b2.close()
+
+
+def test_feature_model_on_gpu(tmp_path):
+    """Function definitions, initial assignment, rate + piecewise assignment rules, stoichiometryMath, a Hill-type
+    power, a logical trigger and an event that restarts the solver: GPU vs oracle, bit for bit."""
+    from test_frontend_models import FEATURES
+    p = tmp_path / "features.xml"
+    p.write_text(FEATURES)
+    m = so.Model(str(p))
+    vary = [m.index(n) for n in ("vmax", "km", "kd", "A")]
+    rng = np.random.default_rng(3)
+    n = 4096
+    vals = np.stack([rng.uniform(0.5, 3, n), rng.uniform(0.2, 2, n), rng.uniform(0.05, 1, n), rng.uniform(1, 6, n)], axis=1)
+    opt = so.settings(40.0, 80, 1e-9, 1e-6)
+    b = so.Batch(m, opt, vary)
+    b.set_values(vals)
+    b.integrate(n)
+    out, st, stats, fired = b.results(n), b.status(n), b.stats(n).T, b.event_log(n).T
+    ref = H.oracle_run(m, opt, vary, vals, 80, compiled_so=H.compile_c_model(m, "features"), threads=8)
+    assert np.array_equal(st, ref["status"]) and np.array_equal(stats, ref["stats"])
+    assert np.array_equal(fired, ref["fired"]) and ref["fired"].any()
+    assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    b.close()
