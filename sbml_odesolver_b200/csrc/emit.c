@@ -59,6 +59,10 @@ static void cbprintf(charBuffer_t *c, const char *fmt, ...)
 /* --------------------------------------------------------- expressions */
 typedef struct emit_ctx {
   int cuda;                       /* 1: device flavour with exact-case strength reduction */
+  int interp;                     /* 1: output-time code (rules, events, stored rows): the reference evaluates these with
+                                     evaluateAST even in compiled mode (src/integratorInstance.c:1039-1072, :1139-1161), so
+                                     pow(x, 2) stays libm's pow; in ode_f / jacobi_f the reference's g++ -O build turns the
+                                     literal-2 call into x * x */
   /* resolves value[idx] to source text */
   void (*name)(charBuffer_t *, int idx, const struct emit_ctx *);
   const char *time;               /* text of the current time */
@@ -149,7 +153,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
       double e = evaluateAST(n->children[1], NULL);
       if (e == 0.0) { CharBuffer_append(s, "1.0"); break; }               /* pow(x,0) == 1 exactly  */
       if (e == 1.0) { gen_nested(s, n->children[0], c); break; }          /* pow(x,1) == x exactly  */
-      if (e == 2.0) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
+      if (e == 2.0 && !c->interp) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
     }
     gen_call(s, n, c->cuda ? "odes_pow" : "pow", c); break;
   case AST_INTEGER: CharBuffer_appendDouble(s, (double)n->ival); break;
@@ -233,7 +237,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
 static void name_value(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "value[%d]", idx); }
 void generateAST(charBuffer_t *s, const ASTNode_t *node)
 {
-  emit_ctx_t c; c.cuda = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL;
   gen(s, node, &c);
 }
 
@@ -268,7 +272,7 @@ char *ODEModel_generateCSource(odeModel_t *om)
 {
   charBuffer_t *b = CharBuffer_create();
   emit_ctx_t c; int i; char *out;
-  c.cuda = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL;
   if (!om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n#define ODES_POW pow\n");
   generateMacros(b);
@@ -365,7 +369,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   for (i = 0; i < om->nassbeforeodes; i++) { ode_local[om->assignmentsBeforeODEs[i]->i] = 1; mark_refs(om->assignmentsBeforeODEs[i]->ij, used_in_ode); }
   for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) k.slot[i] = npv++; }
 
-  c.cuda = 1; c.name = name_cuda; c.time = "t"; c.info = &k;
+  c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = "t"; c.info = &k;
 
   cbprintf(b, "/* generated by ODEModel_generateCUDASource for model '%s' (sm_100a device functions) */\n",
            om->simple && om->simple->id ? om->simple->id : "odes");
@@ -407,14 +411,14 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
 
   /* refresh of all assignment rules; static ones are written back to their slots */
   CharBuffer_append(b, "DEV void rules_all(double t, const double (&y)[A1(NEQ)], const PvRef pv, double (&a)[A1(NASS)])\n{\n  (void)t; (void)y; (void)pv; (void)a;\n");
-  k.local = all_local;
+  k.local = all_local; c.interp = 1;
   emit_refresh_all(b, om, &c, "  ");
   for (i = om->neq; i < om->neq + om->nass; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = a[%d];\n", k.slot[i], i - om->neq);
   CharBuffer_append(b, "}\n");
 
   /* ode_f: rules needed by the ODEs in topological order, then the right-hand sides */
   CharBuffer_append(b, "DEV void ode_f(double t, const double (&y)[A1(NEQ)], const PvRef pv, double (&ydot)[A1(NEQ)])\n{\n  double a[A1(NASS)]; (void)t; (void)pv; (void)a;\n");
-  k.local = ode_local;
+  k.local = ode_local; c.interp = 0;
   for (i = 0; i < om->nassbeforeodes; i++) {
     nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
     cbprintf(b, "  a[%d] = ", o->i - om->neq); gen(b, o->ij, &c); CharBuffer_append(b, ";\n");
@@ -431,7 +435,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
   CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], const PvRef pv, int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
                        "  unsigned int fired = 0; double a[A1(NASS)]; (void)t; (void)a; (void)y; (void)pv; (void)trigger; (void)reinit;\n");
-  k.local = all_local;
+  k.local = all_local; c.interp = 1;
   if (om->nevents > 0) {
     emit_refresh_all(b, om, &c, "  ");
     for (e = 0; e < om->nevents; e++) {

@@ -104,3 +104,47 @@ def test_feature_model_emulated_kernel_vs_oracle(features_model, halt):
     assert np.array_equal(got["fired"].T[safe], refi["fired"][safe])
     assert H.parity(got["out"][:, :, safe], np.transpose(refi["out"], (1, 2, 0))[:, :, safe], 1e-6, 1e-9) <= 1.0
     b.close()
+
+
+def chain_model_xml(n):
+    """A cascade S1 -> S2 -> ... -> Sn with saturable steps and feedback of the last species on the first step."""
+    sp = "".join(f'<species id="S{i}" compartment="c" initialConcentration="{1.0 if i == 1 else 0.1}"/>' for i in range(1, n + 1))
+    rx = []
+    for i in range(1, n):
+        law = (f"<apply><divide/><apply><times/><ci>v{i}</ci><ci>S{i}</ci></apply><apply><plus/><ci>K</ci><ci>S{i}</ci></apply></apply>")
+        if i == 1:
+            law = f"<apply><divide/>{law}<apply><plus/><cn>1</cn><apply><power/><ci>S{n}</ci><cn>2</cn></apply></apply></apply>"
+        rx.append(f'<reaction id="r{i}" reversible="false"><listOfReactants><speciesReference species="S{i}"/></listOfReactants>'
+                  f'<listOfProducts><speciesReference species="S{i + 1}"/></listOfProducts><kineticLaw><math {M}>{law}</math></kineticLaw></reaction>')
+    rx.append(f'<reaction id="r{n}" reversible="false"><listOfReactants><speciesReference species="S{n}"/></listOfReactants>'
+              f'<listOfProducts><speciesReference species="S1"/></listOfProducts><kineticLaw><math {M}><apply><times/><ci>kback</ci><ci>S{n}</ci></apply></math></kineticLaw></reaction>')
+    pars = "".join(f'<parameter id="v{i}" value="{0.5 + 0.1 * i}"/>' for i in range(1, n)) + '<parameter id="K" value="0.3"/><parameter id="kback" value="0.2"/>'
+    return (f'<?xml version="1.0" encoding="UTF-8"?><sbml xmlns="http://www.sbml.org/sbml/level2" level="2" version="1"><model id="chain{n}">'
+            f'<listOfCompartments><compartment id="c" size="1"/></listOfCompartments><listOfSpecies>{sp}</listOfSpecies>'
+            f'<listOfParameters>{pars}</listOfParameters><listOfReactions>{"".join(rx)}</listOfReactions></model></sbml>')
+
+
+@pytest.mark.parametrize("n", [3, 12, 17])
+def test_chain_models_emulated_kernel_vs_oracle(tmp_path, n):
+    """State dimensions around the storage thresholds: one and two 8-row chunks per matrix column, packed and
+    array pivots (n > 16).  n = 3 runs enough sets to meet arguments where libm's pow(x, 2) is not x * x rounded
+    (about 3e-4 of the calls): stored assignment-rule values follow the interpreter (pow), the ODEs the compiled x * x."""
+    p = tmp_path / f"chain{n}.xml"
+    p.write_text(chain_model_xml(n))
+    m = so.Model(str(p))
+    assert m.neq == n and m.nass == n
+    vary = [m.index(f"v{i}") for i in range(1, n)] + [m.index("K")]
+    rng = np.random.default_rng(n)
+    vals = m.base_values()[vary][None, :] * np.exp2(rng.uniform(-1, 1, size=(400 if n == 3 else 6, len(vary))))
+    opt = so.settings(30.0, 30, 1e-9, 1e-6)
+    b = so.Batch(m, opt, vary)
+    base, trig = b.base_values()
+    got = H.Emu(b, f"chain{n}").run(base, trig, vals, H.tpoints(opt, 30), 10000, 1e-6, 1e-9)
+    ref = H.oracle_run(m, opt, vary, vals, 30, compiled_so=H.compile_c_model(m, f"chain{n}"))
+    assert np.array_equal(got["stats"].T, ref["stats"]) and (got["status"] == 0).all()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)))
+    if n == 3:
+        import math
+        y3 = got["out"][1:, 2, :].ravel()
+        assert (np.array([math.pow(v, 2.0) for v in y3]) != y3 * y3).any()
+    b.close()

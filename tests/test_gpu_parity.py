@@ -190,3 +190,27 @@ def test_feature_model_on_gpu(tmp_path):
     assert np.array_equal(fired, ref["fired"]) and ref["fired"].any()
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
     b.close()
+
+
+@pytest.mark.parametrize("n", [3, 12, 17])
+def test_chain_models_on_gpu(tmp_path, n):
+    """n = 3 and 12 use tensor memory with one and two chunks per matrix column (12: all 512 columns of one block per
+    SM), n = 17 falls back to the global scratch: all bit-identical to the oracle."""
+    from test_frontend_models import chain_model_xml
+    p = tmp_path / f"chain{n}.xml"
+    p.write_text(chain_model_xml(n))
+    m = so.Model(str(p))
+    vary = [m.index(f"v{i}") for i in range(1, n)] + [m.index("K")]
+    rng = np.random.default_rng(n)
+    ns = 600
+    vals = m.base_values()[vary][None, :] * np.exp2(rng.uniform(-1, 1, size=(ns, len(vary))))
+    opt = so.settings(30.0, 30, 1e-9, 1e-6)
+    b = so.Batch(m, opt, vary)
+    b.set_values(vals)
+    b.integrate(ns)
+    out, st, stats = b.results(ns), b.status(ns), b.stats(ns).T
+    ref = H.oracle_run(m, opt, vary, vals, 30, compiled_so=H.compile_c_model(m, f"chain{n}"), threads=8)
+    print(n, b.kernel_info())
+    assert (st == 0).all() and np.array_equal(stats, ref["stats"])
+    assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))
+    b.close()
