@@ -4,7 +4,7 @@
  * scans one (global, or kinetic-law local) parameter over `points` values and prints, per design point, the value
  * of every ODE variable (or of one species) at the end time.  Where the reference loops
  *     for each value: IntegratorInstance_setVariableValue; while (!timeCourseCompleted) integrateOneStep; reset
- * (examples/ParameterScanner.c:136-163, src/odeSolver.c:313-330) this is ONE call of Model_odeSolverBatch:
+ * (examples/ParameterScanner.c:136-163, src/odeSolver.c:313-330) this is ONE call of Model_odeSolverBatchFlat (or Model_odeSolverBatch for per-point SBMLResults_t):
  * all design points are integrated by one kernel launch.
  */
 #include <stdio.h>
@@ -25,7 +25,7 @@ int main(int argc, char *argv[])
   vs = VarySettings_allocate(1, points);
   VarySettings_addParameter(vs, par, rid);
   for (i = 0; i < points; i++) { double v = points > 1 ? lo + (hi - lo) * i / (points - 1) : lo; VarySettings_addDesignPoint(vs, &v); }
-  res = SBML_odeSolverBatch(d, set, vs);
+  res = SBML_odeSolverBatchFlat(d, set, vs);
   if (!res) { SolverError_dumpAndClearErrors(); return EXIT_FAILURE; }
   printf("#%s", par);
   for (k = 0; k < res->nvalues; k++) if (only ? !strcmp(only, res->names[k]) : 1) printf(" %s", res->names[k]);

@@ -66,6 +66,13 @@ int IntegratorInstance_handleError(integratorInstance_t *);
 void IntegratorInstance_printStatistics(const integratorInstance_t *, FILE *);
 void IntegratorInstance_printCVODEStatistics(const integratorInstance_t *, FILE *);
 double IntegratorInstance_getIntegrationTime(const integratorInstance_t *);
+int IntegratorInstance_setInitialTime(integratorInstance_t *, double);
+const char *IntegratorInstance_getVariableName(integratorInstance_t *, variableIndex_t *);
+double *IntegratorInstance_getValues(integratorInstance_t *);
+void IntegratorInstance_dumpNames(integratorInstance_t *);
+void IntegratorInstance_dumpSolver(integratorInstance_t *);
+int IntegratorInstance_checkTrigger(integratorInstance_t *);
+int IntegratorInstance_updateModel(integratorInstance_t *);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,14 @@ const nonzeroElem_t *ODEModel_getAssignmentBeforeEvents(odeModel_t *, int);
 const nonzeroElem_t *ODEModel_getJacobiElement(const odeModel_t *, int);
 const ASTNode_t *NonzeroElement_getEquation(nonzeroElem_t *);
 const char *NonzeroElement_getVariableName(nonzeroElem_t *, odeModel_t *);
+variableIndex_t *NonzeroElement_getVariableIndex(nonzeroElem_t *, odeModel_t *);
+variableIndex_t *NonzeroElement_getVariable2Index(nonzeroElem_t *, odeModel_t *);
+const Model_t *ODEModel_getInputSBML(odeModel_t *);
+int ODEModel_getNumPiecewise(odeModel_t *);
+int ODEModel_getNumEvents(odeModel_t *);
+const ASTNode_t *ODEModel_getEventTrigger(odeModel_t *, int);
+const ASTNode_t *ODEModel_getEventAssignment(odeModel_t *, int, int);
+ASTNode_t *ASTNode_indexAST(const ASTNode_t *f, odeModel_t *om);
 const char *NonzeroElement_getVariable2Name(nonzeroElem_t *, odeModel_t *);
 List_t *topoSort(int **matrix, int n, int *changed, int *required);
 

@@ -2,12 +2,15 @@
  * odeSolver.h -- high-level batch interface: varySettings_t and
  * Model_odeSolverBatch.  Reference: src/sbmlsolver/odeSolver.h:53-92,
  * src/odeSolver.c:235-352 (batch loop), :354-440 (globalize/localize).
- * Model_odeSolverBatch keeps its meaning but runs all design points in one
- * batched device launch and returns the results as a batchResults_t.
+ * Model_odeSolverBatch keeps its signature and meaning (one SBMLResults_t per
+ * design point) but runs all design points in one batched device launch;
+ * Model_odeSolverBatchFlat returns the same run as one flat batchResults_t
+ * without the per-point containers (the form to use for 10^5..10^6 points).
  */
 #ifndef ODES_B200_ODESOLVER_H
 #define ODES_B200_ODESOLVER_H
 #include "sbmlsolver/batchIntegrator.h"
+#include "sbmlsolver/sbmlResults.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -40,8 +43,14 @@ const char *VarySettings_getReactionName(const varySettings_t *, int);
 void VarySettings_dump(varySettings_t *);
 void VarySettings_free(varySettings_t *);
 
-batchResults_t *Model_odeSolverBatch(Model_t *, cvodeSettings_t *, varySettings_t *);
-batchResults_t *SBML_odeSolverBatch(SBMLDocument_t *, cvodeSettings_t *, varySettings_t *);
+SBMLResults_t *SBML_odeSolver(SBMLDocument_t *, cvodeSettings_t *);
+SBMLResults_t *Model_odeSolver(Model_t *, cvodeSettings_t *);
+SBMLResultsArray_t *SBML_odeSolverBatch(SBMLDocument_t *, cvodeSettings_t *, varySettings_t *);
+SBMLResultsArray_t *Model_odeSolverBatch(Model_t *, cvodeSettings_t *, varySettings_t *);
+SBMLResults_t *SBMLResults_fromIntegrator(Model_t *, integratorInstance_t *);
+batchResults_t *Model_odeSolverBatchFlat(Model_t *, cvodeSettings_t *, varySettings_t *);
+batchResults_t *SBML_odeSolverBatchFlat(SBMLDocument_t *, cvodeSettings_t *, varySettings_t *);
+SBMLResultsArray_t *SBMLResultsArray_fromBatch(Model_t *, odeModel_t *, const batchResults_t *);
 double BatchResults_getValue(const batchResults_t *, int set, const char *name, int timestep);
 void BatchResults_free(batchResults_t *);
 int Model_globalizeParameter(Model_t *m, const char *id, const char *rid);

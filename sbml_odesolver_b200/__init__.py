@@ -64,7 +64,14 @@ _SIGS = {
     "CvodeResults_getNout": (c_i, [c_p]), "CvodeResults_getTime": (c_d, [c_p, c_i]), "CvodeResults_getValue": (c_d, [c_p, c_p, c_i]),
     "VarySettings_allocate": (c_p, [c_i, c_i]), "VarySettings_addParameter": (c_i, [c_p, c_s, c_s]),
     "VarySettings_addDesignPoint": (c_i, [c_p, c_p]), "VarySettings_free": (None, [c_p]),
-    "Model_odeSolverBatch": (c_p, [c_p, c_p, c_p]), "BatchResults_getValue": (c_d, [c_p, c_i, c_s, c_i]), "BatchResults_free": (None, [c_p]),
+    "Model_odeSolverBatch": (c_p, [c_p, c_p, c_p]), "Model_odeSolverBatchFlat": (c_p, [c_p, c_p, c_p]),
+    "Model_odeSolver": (c_p, [c_p, c_p]), "SBML_odeSolver": (c_p, [c_p, c_p]), "SBMLResults_fromIntegrator": (c_p, [c_p, c_p]),
+    "SBMLResultsArray_fromBatch": (c_p, [c_p, c_p, c_p]), "SBMLResultsArray_free": (None, [c_p]),
+    "SBMLResultsArray_getNumResults": (c_i, [c_p]), "SBMLResultsArray_getResults": (c_p, [c_p, c_i]),
+    "SBMLResults_free": (None, [c_p]), "SBMLResults_getNout": (c_i, [c_p]), "SBMLResults_getTime": (c_p, [c_p]),
+    "SBMLResults_getTimeCourse": (c_p, [c_p, c_s]), "SBMLResults_dump": (None, [c_p]),
+    "TimeCourse_getName": (c_s, [c_p]), "TimeCourse_getNumValues": (c_i, [c_p]), "TimeCourse_getValue": (c_d, [c_p, c_i]),
+    "BatchResults_getValue": (c_d, [c_p, c_i, c_s, c_i]), "BatchResults_free": (None, [c_p]),
     "ODESBatch_create": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p, c_i]), "ODESBatch_free": (None, [c_p]),
     "ODESBatch_reserve": (c_i, [c_p, c_i]), "ODESBatch_getCapacity": (c_i, [c_p]), "ODESBatch_getNout": (c_i, [c_p]),
     "ODESBatch_getNstore": (c_i, [c_p]), "ODESBatch_getSource": (c_s, [c_p]), "ODESBatch_getCompileLog": (c_s, [c_p]),

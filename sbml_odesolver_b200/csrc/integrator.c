@@ -339,3 +339,73 @@ void IntegratorInstance_printStatistics(const integratorInstance_t *engine, FILE
 }
 double IntegratorInstance_getIntegrationTime(const integratorInstance_t *engine)
 { return engine->clockStarted ? ((double)(clock() - engine->startTime)) / CLOCKS_PER_SEC : 0.0; }
+
+/* ---- smaller entries of the reference's integratorInstance.h ---- */
+/* src/integratorInstance.c:508-527 */
+int IntegratorInstance_setInitialTime(integratorInstance_t *engine, double initialtime)
+{
+  if ((engine->isValid == 0 && engine->solver->t == engine->solver->t0) && engine->solver->tout > initialtime) {
+    engine->solver->t0 = initialtime; engine->solver->t = initialtime; engine->data->currenttime = (float)initialtime;
+    return 1;
+  }
+  SolverError_error(WARNING_ERROR_TYPE, SOLVER_ERROR_ATTEMPTING_TO_SET_IMPOSSIBLE_INITIAL_TIME,
+                    "Requested intial time (%f) is not possible! Reset integrator first, and make sure that the first output time (%f) "
+                    "is smaller than the requested initial time! New setting ignored!", initialtime, engine->solver->tout);
+  return 0;
+}
+const char *IntegratorInstance_getVariableName(integratorInstance_t *engine, variableIndex_t *vi) { return VariableIndex_getName(vi, engine->om); }
+double *IntegratorInstance_getValues(integratorInstance_t *engine) { return engine->data->value; }
+void IntegratorInstance_dumpNames(integratorInstance_t *engine) { ODEModel_dumpNames(engine->om); }
+/* src/integratorInstance.c:1658-1690 (the CVODE statistics come from the device counters) */
+void IntegratorInstance_dumpSolver(integratorInstance_t *engine)
+{
+  cvodeSolver_t *solver = engine->solver;
+  printf("\nINTEGRATOR STATE:\n\nCurrent Time Settings:\n");
+  printf("start time:          %g\ncurrent time:        %g\nnext time:           %g\n", solver->t0, solver->t, solver->tout);
+  printf("current step number: %d\ntotal step number:   %d\n\n", solver->iout, solver->nout);
+  if (engine->om->neq) {
+    printf("CVODE Error Settings:\nabsolute error tolerance: %g\nrelative error tolerance: %g\nmax. internal step nr.:   %d\n\n",
+           engine->opt->Error, engine->opt->RError, engine->opt->Mxstep);
+    IntegratorInstance_printCVODEStatistics(engine, stdout);
+  }
+}
+/* edge-triggered event check on the current values (src/integratorInstance.c:1371-1428) */
+int IntegratorInstance_checkTrigger(integratorInstance_t *engine)
+{
+  int i, j, fired = 0; cvodeSettings_t *opt = engine->opt; cvodeData_t *data = engine->data; odeModel_t *om = engine->om;
+  for (i = 0; i < om->nassbeforeevents; i++) { nonzeroElem_t *o = om->assignmentsBeforeEvents[i]; data->value[o->i] = evaluateAST(o->ij, data); }
+  for (i = 0; i < data->nevents; i++) {
+    if (data->trigger[i] == 0) {
+      if (evaluateAST(om->event[i], data)) {
+        if (opt->HaltOnEvent) {
+          char *eq = SBML_formulaToString(om->event[i]);
+          SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_EVENT_TRIGGER_FIRED, "Event Trigger %d (%s) fired at time %g. Aborting simulation.", i, eq, data->currenttime);
+          free(eq);
+        }
+        fired++;
+        data->trigger[i] = 1;
+        for (j = 0; j < om->neventAss[i]; j++) set_value_by_index(engine, om->eventIndex[i][j], evaluateAST(om->eventAssignment[i][j], data));
+      }
+    } else if (!evaluateAST(om->event[i], data)) data->trigger[i] = 0;
+  }
+  return fired;
+}
+/* writes the last stored values back into the SBML model (src/integratorInstance.c:966-1003) */
+int IntegratorInstance_updateModel(integratorInstance_t *engine)
+{
+  int i; odeModel_t *om = engine->om; cvodeResults_t *results = engine->results; Model_t *m = om->m;
+  Species_t *s; Compartment_t *c; Parameter_t *p;
+  if (!m || !results) return 0;
+  for (i = 0; i < engine->data->nvalues; i++) {
+    const double v = results->value[i][results->nout];
+    if ((s = Model_getSpeciesById(m, om->names[i])) != NULL) {
+      c = Model_getCompartmentById(m, s->compartment);
+      if (!s->hasOnlySubstanceUnits && c && c->spatialDimensions != 0) { s->initialConcentration = v; s->isSetInitialConcentration = 1; s->isSetInitialAmount = 0; }
+      else { s->initialAmount = v; s->isSetInitialAmount = 1; s->isSetInitialConcentration = 0; }
+    }
+    else if ((c = Model_getCompartmentById(m, om->names[i])) != NULL) { c->size = v; c->isSetSize = 1; }
+    else if ((p = Model_getParameterById(m, om->names[i])) != NULL) { p->value = v; p->isSetValue = 1; }
+    else return 0;
+  }
+  return 1;
+}

@@ -706,3 +706,14 @@ void VariableIndex_free(variableIndex_t *vi) { free(vi); }
 const ASTNode_t *ODEModel_getOde(const odeModel_t *om, const variableIndex_t *vi) { return (0 <= vi->index && vi->index < om->neq) ? om->ode[vi->index] : NULL; }
 const ASTNode_t *ODEModel_getAssignment(const odeModel_t *om, const variableIndex_t *vi)
 { return (om->neq <= vi->index && vi->index < om->neq + om->nass) ? om->assignment[vi->type_index] : NULL; }
+
+/* ---- smaller accessors of the reference's odeModel.h (src/odeModel.c:1241-1300, :1609-1720) ---- */
+const Model_t *ODEModel_getInputSBML(odeModel_t *om) { return om->m; }
+int ODEModel_getNumPiecewise(odeModel_t *om) { return om->npiecewise; }
+int ODEModel_getNumEvents(odeModel_t *om) { return om->nevents; }
+const ASTNode_t *ODEModel_getEventTrigger(odeModel_t *om, int i) { return (i >= 0 && i < om->nevents) ? om->event[i] : NULL; }
+const ASTNode_t *ODEModel_getEventAssignment(odeModel_t *om, int i, int j)
+{ return (i >= 0 && i < om->nevents && j >= 0 && j < om->neventAss[i]) ? om->eventAssignment[i][j] : NULL; }
+variableIndex_t *NonzeroElement_getVariableIndex(nonzeroElem_t *nz, odeModel_t *om) { return ODEModel_getVariableIndexByNum(om, nz->i != -1 ? nz->i : nz->j); }
+variableIndex_t *NonzeroElement_getVariable2Index(nonzeroElem_t *nz, odeModel_t *om) { return (nz->i == -1 || nz->j == -1) ? NULL : ODEModel_getVariableIndexByNum(om, nz->j); }
+ASTNode_t *ASTNode_indexAST(const ASTNode_t *f, odeModel_t *om) { return indexAST(f, om->neq + om->nass + om->nconst, om->names); }

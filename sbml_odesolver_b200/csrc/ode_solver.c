@@ -122,7 +122,9 @@ double BatchResults_getValue(const batchResults_t *r, int set, const char *name,
   return 0.0;
 }
 
-batchResults_t *Model_odeSolverBatch(Model_t *m, cvodeSettings_t *set, varySettings_t *vs)
+/* one batched device run over all design points; when mapped is given, the per-point SBMLResults_t are built while
+   the scanned kinetic-law parameters are still globalised (their names appear in the kinetic laws) */
+static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varySettings_t *vs, SBMLResultsArray_t **mapped)
 {
   int i, j, nvalues, *idx; odeModel_t *om; batchResults_t *res = NULL; odesBatch_t *plan = NULL; double *rows;
   for (i = 0; i < vs->nrparams; i++) if (vs->rid[i] && strlen(vs->rid[i]) > 0) Model_globalizeParameter(m, vs->id[i], vs->rid[i]);
@@ -154,6 +156,7 @@ batchResults_t *Model_odeSolverBatch(Model_t *m, cvodeSettings_t *set, varySetti
       if (!ODESBatch_runHost(plan, res->nsets, rows, res->value, res->status, 0)) { BatchResults_free(res); res = NULL; }
       free(rows);
       ODESBatch_free(plan);
+      if (res && mapped) *mapped = SBMLResultsArray_fromBatch(m, om, res);
     }
     free(idx);
     om->m = NULL;                    /* the SBML model stays with the caller */
@@ -162,5 +165,16 @@ batchResults_t *Model_odeSolverBatch(Model_t *m, cvodeSettings_t *set, varySetti
   for (i = 0; i < vs->nrparams; i++) if (vs->rid[i] && strlen(vs->rid[i]) > 0) Model_localizeParameter(m, vs->id[i], vs->rid[i]);
   return res;
 }
-batchResults_t *SBML_odeSolverBatch(SBMLDocument_t *d, cvodeSettings_t *set, varySettings_t *vs)
+batchResults_t *Model_odeSolverBatchFlat(Model_t *m, cvodeSettings_t *set, varySettings_t *vs) { return run_design_points(m, set, vs, NULL); }
+batchResults_t *SBML_odeSolverBatchFlat(SBMLDocument_t *d, cvodeSettings_t *set, varySettings_t *vs)
+{ return (d && d->model) ? Model_odeSolverBatchFlat(d->model, set, vs) : NULL; }
+/* the reference's call (src/odeSolver.c:235-352): one SBMLResults_t per design point */
+SBMLResultsArray_t *Model_odeSolverBatch(Model_t *m, cvodeSettings_t *set, varySettings_t *vs)
+{
+  SBMLResultsArray_t *a = NULL;
+  batchResults_t *flat = run_design_points(m, set, vs, &a);
+  BatchResults_free(flat);
+  return a;
+}
+SBMLResultsArray_t *SBML_odeSolverBatch(SBMLDocument_t *d, cvodeSettings_t *set, varySettings_t *vs)
 { return (d && d->model) ? Model_odeSolverBatch(d->model, set, vs) : NULL; }

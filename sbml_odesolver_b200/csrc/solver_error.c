@@ -60,3 +60,13 @@ void SolverError_freeDumpString(char *s) { free(s); }
 int SolverError_dumpHelper(char *s) { int n = (int)strlen(s); fputs(s, stderr); return n; }
 void SolverError_dump(void) { char *s = SolverError_dumpToString(); fputs(s, stderr); free(s); }
 void SolverError_dumpAndClearErrors(void) { SolverError_dump(); SolverError_clear(); }
+/* src/solverError.c:196-270 */
+static int memoryExhaustion = 0;
+void SolverError_haltOnErrors(void) { if (SolverError_getNum(ERROR_ERROR_TYPE) || SolverError_getNum(FATAL_ERROR_TYPE)) exit(EXIT_FAILURE); }
+int SolverError_isMemoryExhausted(void) { return memoryExhaustion; }
+void *SolverError_calloc(size_t num, size_t size)
+{
+  void *r = calloc(num, size);
+  memoryExhaustion = memoryExhaustion || !r;
+  return r;
+}

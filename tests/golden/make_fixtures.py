@@ -48,6 +48,23 @@ for l in lines[start + 1:]:
     rows.append(l.strip())
 assert len(rows) == 101
 open(os.path.join(OUT, "mapk_testrun.txt"), "w").write("# t MKKK MKKK_P MKK MKK_P MKK_PP MAPK MAPK_P MAPK_PP  (examples/testrun.out:28-129)\n" + "\n".join(rows) + "\n")
+# reaction fluxes of the same run (examples/testrun.out:132-234) and the custom-grid rows (:235-243)
+start = next(i for i, l in enumerate(lines) if l.startswith("#time J0 "))
+rows = []
+for l in lines[start + 1:]:
+    if not re.match(r"^[0-9]", l):
+        break
+    rows.append(l.strip())
+assert len(rows) == 101
+open(os.path.join(OUT, "mapk_testrun_fluxes.txt"), "w").write("# t J0 .. J9  (examples/testrun.out:132-234)\n" + "\n".join(rows) + "\n")
+start = [i for i, l in enumerate(lines) if l.startswith("#time MKKK ")][1]
+rows = []
+for l in lines[start + 1:]:
+    if not re.match(r"^[0-9]", l):
+        break
+    rows.append(l.strip())
+assert len(rows) == 7
+open(os.path.join(OUT, "mapk_testrun_customgrid.txt"), "w").write("# t + 8 species on the grid 0,0.5,1,4,9,16,25  (examples/testrun.out:235-243)\n" + "\n".join(rows) + "\n")
 for name in ("MAPK_10pt.dat", "MAPK_100pt.dat"):
     rows = [l.strip() for l in open(os.path.join(REF, "examples", name)) if re.match(r"^[0-9]", l)]
     open(os.path.join(OUT, name.lower() + ".txt"), "w").write(f"# rows of examples/{name}: t + 8 species\n" + "\n".join(rows) + "\n")

@@ -20,7 +20,7 @@ def _build():
 
 def test_examples_compile_as_c99():
     d = _build()
-    assert os.path.exists(os.path.join(d, "integrate_timecourse")) and os.path.exists(os.path.join(d, "parameter_scan"))
+    assert all(os.path.exists(os.path.join(d, x)) for x in ("integrate_timecourse", "parameter_scan", "batch_scan_results"))
 
 
 @pytest.mark.skipif(so.lib().ODES_deviceCount() > 0, reason="needs a box without a GPU")
@@ -60,3 +60,25 @@ def test_parameter_scan_matches_oracle():
     tol = np.maximum(10 * 1e-6 * np.abs(want), 10 * 1e-9)
     assert (np.abs(got - want) <= tol + 1e-9 * np.abs(want)).all()      # printed with 10 digits
     assert all(row[-1] == "0" for row in rows[1:])
+
+
+@pytest.mark.gpu
+def test_batch_scan_results_prints_species_per_design_point():
+    """2 x 3 grid over a global and a kinetic-law parameter; the printed %g columns equal the oracle's values."""
+    d = _build()
+    r = subprocess.run([os.path.join(d, "batch_scan_results"), H.model_path("mapk_cascade.xml"), "500", "5", "V1", "2", "4", "2", "KK2", "J1", "4", "16", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    blocks = r.stdout.strip().split("### Parameters: ")[1:]
+    assert len(blocks) == 6
+    m = so.Model(H.model_path("mapk_cascade.xml"), globalize=[("J1", "KK2")])
+    opt = so.settings(500.0, 5, 1e-9, 1e-6)
+    pts = np.array([[2 + i * 1.0, 4 + j * 4.0] for i in range(2) for j in range(3)])
+    ref = H.oracle_run(m, opt, [m.index("V1"), m.index("r_J1_KK2")], pts, 5)
+    for s, blk in enumerate(blocks):
+        lines = blk.strip().split("\n")
+        assert lines[0] == "V1=%f, KK2=%f, " % (pts[s, 0], pts[s, 1])
+        assert lines[1] == "## Printing Species time courses" and lines[2].split() == ["#time"] + m.names[:8]
+        for n, l in enumerate(lines[3:9]):
+            want = ["%g" % (100.0 * n)] + ["%g" % v for v in ref["out"][s, n, :8]]
+            assert l.split() == want, (s, n)
