@@ -293,7 +293,7 @@ struct odesBatch {
   compiled_code_t *code; CUfunction kernel;
   int block, minblocks, matLocal; size_t smemBytes;
   int capacity;
-  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot; double *d_scratch; int laMode, laWords, tmemCols, maxBlocksPerSM;
+  double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot; double *d_scratch; int warpMode, laMode, laWords, tmemCols, maxBlocksPerSM;
   size_t rowsCap;
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
@@ -354,6 +354,26 @@ static std::string build_source(odesBatch_t *b)
   int la = env_int("ODES_LA", -1);
   if (la < 0) la = (tmemCols <= 512 && neq > 0) ? 2 : ((size_t)(chipWords + b->laWords) * 8 * 64 <= 112 * 1024 ? 0 : 1);
   if (la == 2 && tmemCols > 512) la = 1;
+  /* larger networks: one trajectory per WARP (bdf_warp_kernel.cuh) -- state in registers, row of the Newton matrix
+     per lane; chosen when a lane's linear-algebra words no longer fit tensor memory */
+  int warp = env_int("ODES_WARP", -1);
+  if (warp < 0) warp = (la != 2 && neq > 8 && neq <= 32 && usejac) ? 1 : 0;
+  if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
+  b->warpMode = warp;
+  if (warp) {
+    const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);
+    b->laMode = 0; b->tmemCols = 0; b->block = 32 * wpb; b->matLocal = 0; b->smemBytes = 0;
+    b->minblocks = env_int("ODES_MINBLOCKS", 1); b->maxBlocksPerSM = 32;
+    char headw[512];
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks,
+             env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
+    std::string srcw = headw;
+    srcw += model;
+    srcw += odes_bdf_kernel_source;
+    free(model);
+    return srcw;
+  }
   b->laMode = la; b->tmemCols = la == 2 ? tmemCols : 0;
   b->block = env_int("ODES_BLOCK", la == 2 ? 128 : 64);
   /* blocks of more than 4 warps: warps w and w+4 share TMEM lanes and take separate column ranges */
@@ -568,7 +588,8 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;
   a.reltol = b->opt->RError; a.abstol = b->opt->Error;
   void *params[] = { &a };
-  unsigned grid = (unsigned)((nsets + b->block - 1) / b->block);
+  const int perBlock = b->warpMode ? b->block / 32 : b->block;       /* trajectories in flight per block */
+  unsigned grid = (unsigned)((nsets + perBlock - 1) / perBlock);
   const unsigned resident = (unsigned)(b->numSMs * b->blocksPerSM);
   if (grid > resident) grid = resident;
   CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));

@@ -275,6 +275,10 @@ struct OdesArgs {
 #define TQ(j) V(TAUOFF + (LMAX + 1), j)
 #define LL(j) V(TAUOFF + (LMAX + 1) + 6, j)
 
+#ifndef ODES_WARP
+#define ODES_WARP 0
+#endif
+#if !ODES_WARP
 /* where this lane's linear-algebra words are */
 struct La {
   double *sm;                  /* ODES_LA 0: this lane's shared-memory words                     */
@@ -331,6 +335,8 @@ template <int N8> DEV void la_commit(const La &la, int w, const double (&v)[N8 *
   la_fence(la);
 }
 
+#endif /* !ODES_WARP */
+
 /* 1.0/j for the small integers of the BDF coefficient formulas (j <= 7): compile-time constants are the
    correctly rounded quotients, i.e. what the reference's run-time division ONE/j yields */
 #ifdef ODES_HOST_EMULATION
@@ -353,6 +359,7 @@ ODES_NOINLINE double root_pow(double x, int n)
   return odes_glibc_pow(x, inv_int(n));
 }
 ODES_NOINLINE double rsqrt_(double x) { return x <= 0.0 ? 0.0 : sqrt(x); }
+#if !ODES_WARP
 /* N_VWrmsNorm(x, ewt) with x the vector at word offset off (nvector_serial.c:591) */
 ODES_NOINLINE double wrms_vec(const double *sm, int off)
 {
@@ -1442,3 +1449,4 @@ extern "C" __global__ void __launch_bounds__(ODES_BLOCK, ODES_MINBLOCKS) odes_bd
 #endif
 }
 #endif
+#endif /* !ODES_WARP */

@@ -432,6 +432,63 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   if (usejac) for (i = 0; i < om->sparsesize; i++) { cbprintf(b, "  jnz[%d] = ", i); gen(b, om->jacobSparse[i]->ij, &c); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "}\n");
 
+  /* warp-per-trajectory flavour (bdf_warp_kernel.cuh): the same expressions, one element per lane.
+     w_rules_level: the rules the ODEs need, grouped by dependency depth (rules of one level are independent);
+     w_ode_case: right-hand side of element i; w_jac_row: the structurally non-zero entries of row i.
+     y and a are the warp's staging arrays in shared memory. */
+  {
+    int nb = om->nassbeforeodes, nlev = 0, lev, cnt;
+    int *depth = (int *)calloc((size_t)nb + 1, sizeof(int));
+    int *refs = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+    k.local = ode_local; c.interp = 0;
+    for (i = 0; i < nb; i++) {
+      int d = 0, r;
+      memset(refs, 0, sizeof(int) * (size_t)(nvalues + 1));
+      mark_refs(om->assignmentsBeforeODEs[i]->ij, refs);
+      for (r = 0; r < i; r++) if (refs[om->assignmentsBeforeODEs[r]->i] && depth[r] + 1 > d) d = depth[r] + 1;
+      depth[i] = d;
+      if (d + 1 > nlev) nlev = d + 1;
+    }
+    cbprintf(b, "#define W_NLEVELS %d\n", nlev);
+    CharBuffer_append(b, "DEV void w_rules_level(int level, int lane, double t, const double *y, double *a, const PvRef pv)\n{\n  (void)level; (void)lane; (void)t; (void)y; (void)a; (void)pv;\n  switch (level) {\n");
+    for (lev = 0; lev < nlev; lev++) {
+      int slot;
+      cbprintf(b, "  case %d:\n    switch (lane) {\n", lev);
+      for (slot = 0; slot < 32; slot++) {
+        int open = 0;
+        for (cnt = 0, i = 0; i < nb; i++) {
+          if (depth[i] != lev) continue;
+          if (cnt % 32 == slot) {
+            nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
+            if (!open) { cbprintf(b, "    case %d:", slot); open = 1; }
+            cbprintf(b, " a[%d] = ", o->i - om->neq); gen(b, o->ij, &c); CharBuffer_append(b, ";");
+          }
+          cnt++;
+        }
+        if (open) CharBuffer_append(b, " break;\n");
+      }
+      CharBuffer_append(b, "    default: break;\n    }\n    break;\n");
+    }
+    CharBuffer_append(b, "  default: break;\n  }\n}\n");
+    CharBuffer_append(b, "DEV double w_ode_case(int i, double t, const double *y, const double *a, const PvRef pv)\n{\n  (void)t; (void)y; (void)a; (void)pv;\n  switch (i) {\n");
+    for (i = 0; i < om->neq; i++) { cbprintf(b, "  case %d: return ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
+    CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
+    CharBuffer_append(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#ifdef ODES_HOST_EMULATION\n#define JR(j) jr[j].v[lane]\n#else\n#define JR(j) jr[j]\n#endif\ntemplate <class JRow> DEV void w_jac_row(int lane, double t, const double *y, const PvRef pv, JRow &jr)\n{\n  (void)t; (void)y; (void)pv; (void)jr;\n  switch (lane) {\n");
+    if (usejac) {
+      for (i = 0; i < om->neq; i++) {
+        int open = 0;
+        for (j = 0; j < om->sparsesize; j++) {
+          if (om->jacobSparse[j]->i != i) continue;
+          if (!open) { cbprintf(b, "  case %d:\n", i); open = 1; }
+          cbprintf(b, "    JR(%d) = ", om->jacobSparse[j]->j); gen(b, om->jacobSparse[j]->ij, &c); CharBuffer_append(b, ";\n");
+        }
+        if (open) CharBuffer_append(b, "    break;\n");
+      }
+    }
+    CharBuffer_append(b, "  default: break;\n  }\n}\n#endif\n");
+    free(depth); free(refs);
+  }
+
   /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
   CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], const PvRef pv, int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
                        "  unsigned int fired = 0; double a[A1(NASS)]; (void)t; (void)a; (void)y; (void)pv; (void)trigger; (void)reinit;\n");

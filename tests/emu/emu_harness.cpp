@@ -27,12 +27,18 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   OdesArgs a;
   a.vary = vary; a.out = out; a.status = status; a.stats = stats; a.fired = fired; a.tpoints = tpoints;
   a.stride = stride; a.nsets = nsets; a.nout = nout; a.mxstep = mxstep; a.pad = 0; a.reltol = reltol; a.abstol = abstol;
-  static double sm[ODES_SMEM_WORDS + 1];
   unsigned long long counter = 0;
   a.counter = &counter;
+#if ODES_WARP
+  a.scratch = 0;
+  static WarpMem wm;
+  integrate_warp(a, wm);                /* one emulated warp (32-wide lane values) pulls every set index in turn */
+#else
+  static double sm[ODES_SMEM_WORDS + 1];
   static double gscr[ODES_GLOBAL_WORDS + 1];
   a.scratch = gscr;
   La la; la.sm = sm; la.gm = gscr; la.gs = 1u; la.taddr = 0u;
   integrate_lanes(a, sm, la);           /* one emulated lane pulls every set index in turn */
+#endif
   return 0;
 }
