@@ -44,6 +44,7 @@ static struct {
   CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
   CUresult (*MemcpyHtoD)(CUdeviceptr, const void *, size_t);
+  CUresult (*MemcpyDtoH)(void *, CUdeviceptr, size_t);
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t);
 } drv;
 
@@ -67,6 +68,7 @@ static int load_driver(void)
   GET(FuncGetAttribute, "cuFuncGetAttribute");
   GET(LaunchKernel, "cuLaunchKernel");
   GET(MemcpyHtoD, "cuMemcpyHtoD");
+  GET(MemcpyDtoH, "cuMemcpyDtoH");
   GET(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
 #undef GET
   drv.ready = 1;
@@ -438,6 +440,12 @@ static int ensure_loaded(odesBatch_t *b)
   if (b->nvalues > 0) DRV_OK(drv.MemcpyHtoD(sym, b->base.data(), sizeof(double) * (size_t)b->nvalues));
   DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
   if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
+  if (b->warpMode) {
+    unsigned int wmBytes = 0;
+    DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_warpmem_bytes"));
+    DRV_OK(drv.MemcpyDtoH(&wmBytes, sym, sizeof wmBytes));
+    b->smemBytes = (size_t)wmBytes * (size_t)(b->block / 32);
+  }
   if (b->smemBytes > 48 * 1024) DRV_OK(drv.FuncSetAttribute(b->kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)b->smemBytes));
   CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&b->copyIn, cudaStreamNonBlocking));

@@ -473,7 +473,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
     CharBuffer_append(b, "DEV double w_ode_case(int i, double t, const double *y, const double *a, const PvRef pv)\n{\n  (void)t; (void)y; (void)a; (void)pv;\n  switch (i) {\n");
     for (i = 0; i < om->neq; i++) { cbprintf(b, "  case %d: return ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
     CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
-    CharBuffer_append(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#ifdef ODES_HOST_EMULATION\n#define JR(j) jr[j].v[lane]\n#else\n#define JR(j) jr[j]\n#endif\ntemplate <class JRow> DEV void w_jac_row(int lane, double t, const double *y, const PvRef pv, JRow &jr)\n{\n  (void)t; (void)y; (void)pv; (void)jr;\n  switch (lane) {\n");
+    CharBuffer_append(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#define JR(j) jr[32 * (j) + lane]\nDEV void w_jac_row(int lane, double t, const double *y, const PvRef pv, double *jr)\n{\n  (void)t; (void)y; (void)pv; (void)jr;\n  switch (lane) {\n");
     if (usejac) {
       for (i = 0; i < om->neq; i++) {
         int open = 0;
