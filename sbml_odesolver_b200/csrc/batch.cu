@@ -365,7 +365,8 @@ static std::string build_source(odesBatch_t *b)
   if (warp) {
     const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);
     b->laMode = 0; b->tmemCols = 0; b->block = 32 * wpb; b->matLocal = 0; b->smemBytes = 0;
-    b->minblocks = env_int("ODES_MINBLOCKS", 1); b->maxBlocksPerSM = 32;
+    /* measured on huang96 (B200): 8 warps per SM 113 k, 12 warps 145 k, 16 warps (128 registers, spills) 136 k trajectories/s */
+    b->minblocks = env_int("ODES_MINBLOCKS", wpb == 4 ? 3 : 1); b->maxBlocksPerSM = 32;
     char headw[512];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d%s\n",
              env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks,

@@ -97,3 +97,20 @@ def test_generated_source_has_single_hot_instances():
     assert src.count("DEV void ode_f(") == 1 and src.count("DEV void jacobi_f(") == 1
     assert "#define NEQ 8" in src and "#define NNZ 26" in src and "#define NVARY 21" in src
     b.close()
+
+
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 12, None), ("repressilator", 4, 100), ("goodwin", 8, None), ("events", 16, None)])
+def test_emulated_warp_kernel_is_bit_identical_on_the_small_models(monkeypatch, name, nsets, nout):
+    """The warp-per-trajectory layout (bdf_warp_kernel.cuh, chosen automatically for n > 12) forced onto the small
+    models: events with solver restarts, pow in rate laws, long output grids -- same bits as the oracle."""
+    monkeypatch.setenv("ODES_WARP", "1")
+    w = H.workload(name, nout=nout)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=43)
+    got = _emulate(w, vals, tag=name + "_warp")
+    assert "-DODES_WARP=1" in so.Batch(m, w["opt"], w["vary"]).source().split("\n")[0]
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, name))
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"].T, ref["stats"])
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)

@@ -214,3 +214,36 @@ def test_chain_models_on_gpu(tmp_path, n):
     assert (st == 0).all() and np.array_equal(stats, ref["stats"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))
     b.close()
+
+
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 300, None), ("goodwin", 200, None), ("events", 400, None), ("repressilator", 64, 200)])
+def test_warp_layout_forced_on_small_models(monkeypatch, name, nsets, nout):
+    """bdf_warp_kernel.cuh (one trajectory per warp; automatic for n > 12) on the small models: solver restarts after
+    events, pow in rate laws, failure flags -- bit-identical to the oracle like the lane layout."""
+    monkeypatch.setenv("ODES_WARP", "1")
+    w = H.workload(name, nout=nout)
+    vals = H.workload_values(w, nsets, seed=515)
+    got = _gpu_run(w, vals)
+    assert got["info"]["threads_per_block"] == 128 and got["info"]["smem_bytes_per_block"] > 0
+    ref = _oracle(w, vals)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"], ref["stats"])
+    if name == "events":
+        assert np.array_equal(got["fired"], ref["fired"]) and ref["fired"].any()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+
+
+def test_warp_layout_failure_flags(monkeypatch):
+    monkeypatch.setenv("ODES_WARP", "1")
+    w = H.workload("mapk", nout=4)
+    m = w["model"]
+    opt = so.settings(1000.0, 4, 1e-9, 1e-6, mxstep=15)
+    vals = H.workload_values(w, 40, seed=3)
+    b = so.Batch(m, opt, w["vary"])
+    b.set_values(vals)
+    b.integrate(40)
+    out, st = b.results(40), b.status(40)
+    ref = H.oracle_run(m, opt, w["vary"], vals, 4, compiled_so=H.compile_c_model(m, "mapk"))
+    assert (st == -4).all() and np.array_equal(st, ref["status"])
+    assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    b.close()
