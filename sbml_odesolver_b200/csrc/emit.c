@@ -67,7 +67,28 @@ typedef struct emit_ctx {
   void (*name)(charBuffer_t *, int idx, const struct emit_ctx *);
   const char *time;               /* text of the current time */
   const void *info;
+  struct leafrec *leaf;           /* non-NULL: leaf mode -- numbers and names are printed as operand placeholders x<k> and
+                                     recorded, so that expressions of identical shape print identical text */
 } emit_ctx_t;
+
+/* leaf mode (warp flavour): operands of one expression.  An operand is a word of the warp's value space V (state,
+   rule values, per-trajectory constants) or a number that goes to the literal pool behind it. */
+#define LEAF_MAX 16
+struct leafrec { int n, failed; int isnum[LEAF_MAX]; int off[LEAF_MAX]; double num[LEAF_MAX]; };
+static void leaf_number(charBuffer_t *s, const emit_ctx_t *c, double v)
+{
+  struct leafrec *lr = c->leaf; char t[24];
+  if (lr->n >= LEAF_MAX) { lr->failed = 1; CharBuffer_append(s, "0.0"); return; }
+  lr->isnum[lr->n] = 1; lr->num[lr->n] = v; lr->off[lr->n] = -1;
+  snprintf(t, sizeof t, "x%d", lr->n++); CharBuffer_append(s, t);
+}
+static void leaf_word(charBuffer_t *s, const emit_ctx_t *c, int off)
+{
+  struct leafrec *lr = c->leaf; char t[24];
+  if (lr->n >= LEAF_MAX) { lr->failed = 1; CharBuffer_append(s, "0.0"); return; }
+  lr->isnum[lr->n] = 0; lr->num[lr->n] = 0.0; lr->off[lr->n] = off;
+  snprintf(t, sizeof t, "x%d", lr->n++); CharBuffer_append(s, t);
+}
 
 static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c);
 
@@ -137,7 +158,8 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
   /* constant sub-expressions of numbers are folded at emit time with the host evaluator
      (same IEEE operations the interpreter would perform at run time) */
   if (c->cuda && n->nchildren > 0 && is_const_tree(n) && !ASTNode_isLogical(n) && !ASTNode_isRelational(n) && n->type != AST_FUNCTION_PIECEWISE) {
-    CharBuffer_appendDouble(s, evaluateAST((ASTNode_t *)n, NULL));
+    if (c->leaf) leaf_number(s, c, evaluateAST((ASTNode_t *)n, NULL));
+    else CharBuffer_appendDouble(s, evaluateAST((ASTNode_t *)n, NULL));
     return;
   }
   switch (n->type) {
@@ -156,8 +178,8 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
       if (e == 2.0 && !c->interp) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
     }
     gen_call(s, n, c->cuda ? "odes_pow" : "pow", c); break;
-  case AST_INTEGER: CharBuffer_appendDouble(s, (double)n->ival); break;
-  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: CharBuffer_appendDouble(s, ASTNode_getReal(n)); break;
+  case AST_INTEGER: if (c->leaf) leaf_number(s, c, (double)n->ival); else CharBuffer_appendDouble(s, (double)n->ival); break;
+  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: if (c->leaf) leaf_number(s, c, ASTNode_getReal(n)); else CharBuffer_appendDouble(s, ASTNode_getReal(n)); break;
   case AST_NAME:
     if (ASTNode_isSetIndex(n)) c->name(s, (int)ASTNode_getIndex(n), c);
     else {
@@ -237,7 +259,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
 static void name_value(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "value[%d]", idx); }
 void generateAST(charBuffer_t *s, const ASTNode_t *node)
 {
-  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL; c.leaf = NULL;
   gen(s, node, &c);
 }
 
@@ -272,7 +294,7 @@ char *ODEModel_generateCSource(odeModel_t *om)
 {
   charBuffer_t *b = CharBuffer_create();
   emit_ctx_t c; int i; char *out;
-  c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL;
+  c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL; c.leaf = NULL;
   if (!om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n#define ODES_POW pow\n");
   generateMacros(b);
@@ -340,6 +362,239 @@ static void emit_refresh_all(charBuffer_t *b, const odeModel_t *om, const emit_c
   }
 }
 
+
+/* ------------------------------------------------ warp-per-trajectory flavour (bdf_warp_kernel.cuh)
+   The same expressions, one element per lane.  The warp keeps a value space V in shared memory:
+     V[0..32) y, V[W_AS_OFF + r] rule value r, V[W_PV_OFF + k] per-trajectory constant k, V[W_LIT_OFF + n] literal n.
+   Expressions of identical shape (identical text once numbers and names are replaced by operand placeholders) are
+   evaluated by all their lanes together, each lane reading ITS operands through a packed offset word it keeps in a
+   register (w_group_task); right-hand sides that are signed sums of rule values -- the form odeConstruct builds from
+   the stoichiometry -- are evaluated from a packed term list (w_ode_task) in the emitted left-to-right order; whatever
+   fits neither is evaluated per lane in a switch (w_rules_level, w_ode_case).  Every lane performs exactly the IEEE
+   operations of its element's emitted expression, in the emitted order. */
+#define W_MAXGROUPS 8
+#define W_GROUP_LEAVES 5
+#define W_ODE_TERMS_MAX 10
+typedef struct { int npv, nass, neq, nlit; double *lit; int naspad, npvpad; const kinfo_t *k; } wspace_t;
+static int w_as_off(const wspace_t *w) { (void)w; return 32; }
+static int w_pv_off(const wspace_t *w) { return 32 + w->naspad; }
+static int w_lit_off(const wspace_t *w) { return 32 + w->naspad + w->npvpad; }
+static int w_literal(wspace_t *w, double v)
+{
+  int i;
+  for (i = 0; i < w->nlit; i++) if (memcmp(&w->lit[i], &v, sizeof v) == 0) return i;
+  w->lit = (double *)realloc(w->lit, sizeof(double) * (size_t)(w->nlit + 1));
+  w->lit[w->nlit] = v;
+  return w->nlit++;
+}
+static const wspace_t *g_wspace;      /* the resolver below has no other way to reach it */
+static void name_leaf(charBuffer_t *s, int idx, const emit_ctx_t *c)
+{
+  const kinfo_t *k = (const kinfo_t *)c->info; const odeModel_t *om = k->om;
+  switch (k->kind[idx]) {
+  case K_ODE: leaf_word(s, c, idx); break;
+  case K_ASSIGNED:
+    if (k->local[idx]) leaf_word(s, c, w_as_off(g_wspace) + idx - om->neq);
+    else leaf_word(s, c, w_pv_off(g_wspace) + k->slot[idx]);
+    break;
+  case K_THREAD: leaf_word(s, c, w_pv_off(g_wspace) + k->slot[idx]); break;
+  default:
+    if (k->base) leaf_number(s, c, k->base[idx]);
+    else c->leaf->failed = 1, CharBuffer_append(s, "0.0");
+  }
+}
+/* a name that is one word of V, or -1 */
+static int w_plain_word(const ASTNode_t *n, const wspace_t *w)
+{
+  const kinfo_t *k = w->k; int idx;
+  if (n->type != AST_NAME || !ASTNode_isSetIndex(n)) return -1;
+  idx = (int)ASTNode_getIndex(n);
+  switch (k->kind[idx]) {
+  case K_ODE: return idx;
+  case K_ASSIGNED: return k->local[idx] ? w_as_off(w) + idx - w->neq : w_pv_off(w) + k->slot[idx];
+  case K_THREAD: return w_pv_off(w) + k->slot[idx];
+  default: return -1;
+  }
+}
+/* left-to-right signed sum of plain words: off[], neg[]; returns the number of terms or -1 */
+static int w_flatten_sum(const ASTNode_t *n, int neg, const wspace_t *w, int *off, int *negs, int cap)
+{
+  unsigned int i; int cnt, o;
+  if ((o = w_plain_word(n, w)) >= 0) { if (cap < 1) return -1; off[0] = o; negs[0] = neg; return 1; }
+  if (n->type == AST_MINUS && n->nchildren == 1) {
+    if ((o = w_plain_word(n->children[0], w)) < 0 || cap < 1) return -1;
+    off[0] = o; negs[0] = !neg; return 1;
+  }
+  if ((n->type != AST_PLUS && n->type != AST_MINUS) || n->nchildren < 2 || neg) return -1;
+  cnt = w_flatten_sum(n->children[0], 0, w, off, negs, cap);
+  if (cnt < 0) return -1;
+  for (i = 1; i < n->nchildren; i++) {
+    if ((o = w_plain_word(n->children[i], w)) < 0 || cnt >= cap) return -1;
+    off[cnt] = o; negs[cnt] = (n->type == AST_MINUS); cnt++;
+  }
+  return cnt;
+}
+static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k, emit_ctx_t *c, int *ode_local, int usejac, int npv)
+{
+  int nb = om->nassbeforeodes, nlev = 0, lev, i, j, g, ngroups = 0, nvalues = om->neq + om->nass + om->nconst;
+  int *depth = (int *)calloc((size_t)nb + 1, sizeof(int)), *refs = (int *)calloc((size_t)nvalues + 1, sizeof(int));
+  int *group = (int *)calloc((size_t)nb + 1, sizeof(int));            /* table group of rule i, or -1 */
+  char **text = (char **)calloc((size_t)nb + 1, sizeof(char *));
+  struct leafrec *leaves = (struct leafrec *)calloc((size_t)nb + 1, sizeof(struct leafrec));
+  int glevel[W_MAXGROUPS], grep_[W_MAXGROUPS], gcount[W_MAXGROUPS];
+  int *odeoff = (int *)calloc((size_t)om->neq * W_ODE_TERMS_MAX + 1, sizeof(int)), *odeneg = (int *)calloc((size_t)om->neq * W_ODE_TERMS_MAX + 1, sizeof(int));
+  int *odecnt = (int *)calloc((size_t)om->neq + 1, sizeof(int)); double *odediv = (double *)calloc((size_t)om->neq + 1, sizeof(double));
+  int odeterms = 0, odefallback = 0, odedivide = 0, negzero;
+  wspace_t w;
+  w.npv = npv; w.nass = om->nass; w.neq = om->neq; w.nlit = 0; w.lit = NULL; w.k = k;
+  w.naspad = 8 * ((om->nass + 8) / 8); w.npvpad = 8 * ((npv + 7) / 8) + 8;
+  g_wspace = &w;
+  k->local = ode_local; c->interp = 0;
+  negzero = w_literal(&w, -0.0);
+
+  /* dependency depth of the rules the right-hand sides need */
+  for (i = 0; i < nb; i++) {
+    int d = 0, r;
+    memset(refs, 0, sizeof(int) * (size_t)(nvalues + 1));
+    mark_refs(om->assignmentsBeforeODEs[i]->ij, refs);
+    for (r = 0; r < i; r++) if (refs[om->assignmentsBeforeODEs[r]->i] && depth[r] + 1 > d) d = depth[r] + 1;
+    depth[i] = d;
+    if (d + 1 > nlev) nlev = d + 1;
+  }
+  /* shapes: the text of each rule with operand placeholders */
+  for (i = 0; i < nb; i++) {
+    charBuffer_t *tb = CharBuffer_create(); emit_ctx_t lc = *c;
+    lc.leaf = &leaves[i]; lc.name = name_leaf;
+    gen(tb, om->assignmentsBeforeODEs[i]->ij, &lc);
+    text[i] = tb->b; tb->b = NULL; CharBuffer_free(tb);
+    group[i] = -1;
+    if (leaves[i].failed || leaves[i].n > W_GROUP_LEAVES) { free(text[i]); text[i] = NULL; }
+  }
+  for (i = 0; i < nb; i++) {
+    int members = 1;
+    if (!text[i] || group[i] >= 0) continue;
+    for (j = i + 1; j < nb; j++) if (text[j] && group[j] < 0 && depth[j] == depth[i] && strcmp(text[i], text[j]) == 0) members++;
+    if (members < 2 || ngroups >= W_MAXGROUPS) continue;
+    glevel[ngroups] = depth[i]; grep_[ngroups] = i; gcount[ngroups] = 0;
+    for (j = i; j < nb && gcount[ngroups] < 32; j++)
+      if (text[j] && group[j] < 0 && depth[j] == depth[i] && strcmp(text[i], text[j]) == 0) { group[j] = ngroups; gcount[ngroups]++; }
+    ngroups++;
+  }
+  /* right-hand sides that are signed sums of words, optionally divided by a constant */
+  for (i = 0; i < om->neq; i++) {
+    const ASTNode_t *n = om->ode[i]; double div = 1.0; int cnt;
+    if (n->type == AST_DIVIDE && n->nchildren == 2) {
+      const ASTNode_t *d = n->children[1]; int ok = 0;
+      if (is_const_tree(d)) { div = evaluateAST((ASTNode_t *)d, NULL); ok = 1; }
+      else if (d->type == AST_NAME && ASTNode_isSetIndex(d) && k->kind[ASTNode_getIndex(d)] == K_UNIFORM && k->base) { div = k->base[ASTNode_getIndex(d)]; ok = 1; }
+      if (ok) n = n->children[0];
+    }
+    cnt = w_flatten_sum(n, 0, &w, odeoff + i * W_ODE_TERMS_MAX, odeneg + i * W_ODE_TERMS_MAX, W_ODE_TERMS_MAX);
+    if (cnt < 1 || i >= 32) { odecnt[i] = 0; odefallback = 1; continue; }
+    odecnt[i] = cnt; odediv[i] = div;
+    if (cnt > odeterms) odeterms = cnt;
+    if (div != 1.0) odedivide = 1;
+  }
+  /* pool the literals of the grouped rules */
+  for (i = 0; i < nb; i++) if (group[i] >= 0) for (j = 0; j < leaves[i].n; j++) if (leaves[i].isnum[j]) leaves[i].off[j] = w_lit_off(&w) + w_literal(&w, leaves[i].num[j]);
+
+  cbprintf(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#define W_NLEVELS %d\n#define W_AS_OFF %d\n#define W_PV_OFF %d\n#define W_LIT_OFF %d\n#define W_NLIT %d\n#define W_NGROUPS %d\n"
+              "#define W_ODE_NTERMS %d\n#define W_ODE_DIVIDE %d\n#define W_ODE_FALLBACK %d\n#define W_NEGZERO_OFF %d\n",
+           nlev, w_as_off(&w), w_pv_off(&w), w_lit_off(&w), w.nlit, ngroups, odeterms, odedivide, odefallback, w_lit_off(&w) + negzero);
+  CharBuffer_append(b, "DEV double w_literal(int n)\n{\n  switch (n) {\n");
+  for (i = 0; i < w.nlit; i++) { cbprintf(b, "  case %d: return ", i); if (i == negzero) CharBuffer_append(b, "-0.0"); else CharBuffer_appendDouble(b, w.lit[i]); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
+  /* packed operand words: bit 63 valid, bits 50..59 destination, 10 bits per operand from bit 0 */
+  CharBuffer_append(b, "DEV unsigned long long w_group_task(int g, int lane)\n{\n  (void)g; (void)lane;\n  switch (g * 32 + lane) {\n");
+  for (g = 0; g < ngroups; g++) {
+    int lane = 0;
+    for (i = 0; i < nb; i++) {
+      unsigned long long word = 1ull << 63;
+      if (group[i] != g) continue;
+      word |= (unsigned long long)(w_as_off(&w) + om->assignmentsBeforeODEs[i]->i - om->neq) << 50;
+      for (j = 0; j < leaves[i].n; j++) word |= (unsigned long long)leaves[i].off[j] << (10 * j);
+      cbprintf(b, "  case %d: return 0x%llxull;\n", g * 32 + lane, word);
+      lane++;
+    }
+  }
+  CharBuffer_append(b, "  default: return 0ull;\n  }\n}\n");
+  CharBuffer_append(b, "DEV void w_groups_level(int level, const unsigned long long (&task)[A1(W_NGROUPS)], double t, double *V)\n{\n  (void)level; (void)task; (void)t; (void)V;\n  switch (level) {\n");
+  for (lev = 0; lev < nlev; lev++) {
+    cbprintf(b, "  case %d:\n", lev);
+    for (g = 0; g < ngroups; g++) {
+      if (glevel[g] != lev) continue;
+      cbprintf(b, "    if (task[%d] >> 63) {\n      const unsigned long long w_ = task[%d];\n", g, g);
+      for (j = 0; j < leaves[grep_[g]].n; j++) cbprintf(b, "      const double x%d = V[(w_ >> %d) & 1023u];\n", j, 10 * j);
+      cbprintf(b, "      V[(w_ >> 50) & 1023u] = %s;\n    }\n", text[grep_[g]]);
+    }
+    CharBuffer_append(b, "    break;\n");
+  }
+  CharBuffer_append(b, "  default: break;\n  }\n}\n");
+  /* rules outside the groups: per lane */
+  CharBuffer_append(b, "DEV void w_rules_level(int level, int lane, double t, const double *y, double *a, const PvRef pv)\n{\n  (void)level; (void)lane; (void)t; (void)y; (void)a; (void)pv;\n  switch (level) {\n");
+  for (lev = 0; lev < nlev; lev++) {
+    int slot, any = 0;
+    for (i = 0; i < nb; i++) if (depth[i] == lev && group[i] < 0) any = 1;
+    cbprintf(b, "  case %d:\n", lev);
+    if (any) {
+      CharBuffer_append(b, "    switch (lane) {\n");
+      for (slot = 0; slot < 32; slot++) {
+        int open = 0, cnt = 0;
+        for (i = 0; i < nb; i++) {
+          if (depth[i] != lev || group[i] >= 0) continue;
+          if (cnt % 32 == slot) {
+            nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
+            if (!open) { cbprintf(b, "    case %d:", slot); open = 1; }
+            cbprintf(b, " a[%d] = ", o->i - om->neq); gen(b, o->ij, c); CharBuffer_append(b, ";");
+          }
+          cnt++;
+        }
+        if (open) CharBuffer_append(b, " break;\n");
+      }
+      CharBuffer_append(b, "    default: break;\n    }\n");
+    }
+    CharBuffer_append(b, "    break;\n");
+  }
+  CharBuffer_append(b, "  default: break;\n  }\n}\n");
+  { int any = 0; for (i = 0; i < nb; i++) if (group[i] < 0) any = 1; cbprintf(b, "#define W_RULES_FALLBACK %d\n", any); }
+  /* right-hand sides: term lists (bit 63 valid; 11 bits per term: offset, sign), divisors, and the per-lane rest */
+  cbprintf(b, "#define W_ODE_WORDS %d\n", odeterms > 5 ? 2 : 1);
+  CharBuffer_append(b, "DEV unsigned long long w_ode_task(int lane, int word)\n{\n  switch (2 * lane + word) {\n");
+  for (i = 0; i < om->neq; i++) {
+    int wd;
+    if (!odecnt[i]) continue;
+    for (wd = 0; wd < (odeterms > 5 ? 2 : 1); wd++) {
+      unsigned long long word = 1ull << 63;
+      for (j = 5 * wd; j < odeterms && j < 5 * wd + 5; j++) {
+        const int off = j < odecnt[i] ? odeoff[i * W_ODE_TERMS_MAX + j] : w_lit_off(&w) + negzero, neg = j < odecnt[i] ? odeneg[i * W_ODE_TERMS_MAX + j] : 0;
+        word |= (unsigned long long)(off | (neg << 10)) << (11 * (j - 5 * wd));
+      }
+      cbprintf(b, "  case %d: return 0x%llxull;\n", 2 * i + wd, word);
+    }
+  }
+  CharBuffer_append(b, "  default: return 0ull;\n  }\n}\nDEV double w_ode_divisor(int lane)\n{\n  switch (lane) {\n");
+  for (i = 0; i < om->neq; i++) if (odecnt[i] && odediv[i] != 1.0) { cbprintf(b, "  case %d: return ", i); CharBuffer_appendDouble(b, odediv[i]); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "  default: return 1.0;\n  }\n}\n");
+  CharBuffer_append(b, "DEV double w_ode_case(int i, double t, const double *y, const double *a, const PvRef pv)\n{\n  (void)t; (void)y; (void)a; (void)pv;\n  switch (i) {\n");
+  for (i = 0; i < om->neq; i++) { if (odecnt[i]) continue; cbprintf(b, "  case %d: return ", i); gen(b, om->ode[i], c); CharBuffer_append(b, ";\n"); }
+  CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
+  CharBuffer_append(b, "#define JR(j) jr[32 * (j) + lane]\nDEV void w_jac_row(int lane, double t, const double *y, const PvRef pv, double *jr)\n{\n  (void)t; (void)y; (void)pv; (void)jr;\n  switch (lane) {\n");
+  if (usejac) {
+    for (i = 0; i < om->neq; i++) {
+      int open = 0;
+      for (j = 0; j < om->sparsesize; j++) {
+        if (om->jacobSparse[j]->i != i) continue;
+        if (!open) { cbprintf(b, "  case %d:\n", i); open = 1; }
+        cbprintf(b, "    JR(%d) = ", om->jacobSparse[j]->j); gen(b, om->jacobSparse[j]->ij, c); CharBuffer_append(b, ";\n");
+      }
+      if (open) CharBuffer_append(b, "    break;\n");
+    }
+  }
+  CharBuffer_append(b, "  default: break;\n  }\n}\n#endif\n");
+  for (i = 0; i < nb; i++) free(text[i]);
+  free(text); free(leaves); free(group); free(depth); free(refs); free(odeoff); free(odeneg); free(odecnt); free(odediv); free(w.lit);
+}
+
 char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
                                   int nstore, const int *store, const double *base)
 {
@@ -369,7 +624,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   for (i = 0; i < om->nassbeforeodes; i++) { ode_local[om->assignmentsBeforeODEs[i]->i] = 1; mark_refs(om->assignmentsBeforeODEs[i]->ij, used_in_ode); }
   for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) k.slot[i] = npv++; }
 
-  c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = "t"; c.info = &k;
+  c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = "t"; c.info = &k; c.leaf = NULL;
 
   cbprintf(b, "/* generated by ODEModel_generateCUDASource for model '%s' (sm_100a device functions) */\n",
            om->simple && om->simple->id ? om->simple->id : "odes");
@@ -432,62 +687,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   if (usejac) for (i = 0; i < om->sparsesize; i++) { cbprintf(b, "  jnz[%d] = ", i); gen(b, om->jacobSparse[i]->ij, &c); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "}\n");
 
-  /* warp-per-trajectory flavour (bdf_warp_kernel.cuh): the same expressions, one element per lane.
-     w_rules_level: the rules the ODEs need, grouped by dependency depth (rules of one level are independent);
-     w_ode_case: right-hand side of element i; w_jac_row: the structurally non-zero entries of row i.
-     y and a are the warp's staging arrays in shared memory. */
-  {
-    int nb = om->nassbeforeodes, nlev = 0, lev, cnt;
-    int *depth = (int *)calloc((size_t)nb + 1, sizeof(int));
-    int *refs = (int *)calloc((size_t)nvalues + 1, sizeof(int));
-    k.local = ode_local; c.interp = 0;
-    for (i = 0; i < nb; i++) {
-      int d = 0, r;
-      memset(refs, 0, sizeof(int) * (size_t)(nvalues + 1));
-      mark_refs(om->assignmentsBeforeODEs[i]->ij, refs);
-      for (r = 0; r < i; r++) if (refs[om->assignmentsBeforeODEs[r]->i] && depth[r] + 1 > d) d = depth[r] + 1;
-      depth[i] = d;
-      if (d + 1 > nlev) nlev = d + 1;
-    }
-    cbprintf(b, "#define W_NLEVELS %d\n", nlev);
-    CharBuffer_append(b, "DEV void w_rules_level(int level, int lane, double t, const double *y, double *a, const PvRef pv)\n{\n  (void)level; (void)lane; (void)t; (void)y; (void)a; (void)pv;\n  switch (level) {\n");
-    for (lev = 0; lev < nlev; lev++) {
-      int slot;
-      cbprintf(b, "  case %d:\n    switch (lane) {\n", lev);
-      for (slot = 0; slot < 32; slot++) {
-        int open = 0;
-        for (cnt = 0, i = 0; i < nb; i++) {
-          if (depth[i] != lev) continue;
-          if (cnt % 32 == slot) {
-            nonzeroElem_t *o = om->assignmentsBeforeODEs[i];
-            if (!open) { cbprintf(b, "    case %d:", slot); open = 1; }
-            cbprintf(b, " a[%d] = ", o->i - om->neq); gen(b, o->ij, &c); CharBuffer_append(b, ";");
-          }
-          cnt++;
-        }
-        if (open) CharBuffer_append(b, " break;\n");
-      }
-      CharBuffer_append(b, "    default: break;\n    }\n    break;\n");
-    }
-    CharBuffer_append(b, "  default: break;\n  }\n}\n");
-    CharBuffer_append(b, "DEV double w_ode_case(int i, double t, const double *y, const double *a, const PvRef pv)\n{\n  (void)t; (void)y; (void)a; (void)pv;\n  switch (i) {\n");
-    for (i = 0; i < om->neq; i++) { cbprintf(b, "  case %d: return ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
-    CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
-    CharBuffer_append(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#define JR(j) jr[32 * (j) + lane]\nDEV void w_jac_row(int lane, double t, const double *y, const PvRef pv, double *jr)\n{\n  (void)t; (void)y; (void)pv; (void)jr;\n  switch (lane) {\n");
-    if (usejac) {
-      for (i = 0; i < om->neq; i++) {
-        int open = 0;
-        for (j = 0; j < om->sparsesize; j++) {
-          if (om->jacobSparse[j]->i != i) continue;
-          if (!open) { cbprintf(b, "  case %d:\n", i); open = 1; }
-          cbprintf(b, "    JR(%d) = ", om->jacobSparse[j]->j); gen(b, om->jacobSparse[j]->ij, &c); CharBuffer_append(b, ";\n");
-        }
-        if (open) CharBuffer_append(b, "    break;\n");
-      }
-    }
-    CharBuffer_append(b, "  default: break;\n  }\n}\n#endif\n");
-    free(depth); free(refs);
-  }
+  emit_warp_flavour(b, om, &k, &c, ode_local, usejac, npv);
 
   /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
   CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], const PvRef pv, int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"
