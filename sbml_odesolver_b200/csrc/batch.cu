@@ -369,7 +369,7 @@ static std::string build_source(odesBatch_t *b)
     b->minblocks = env_int("ODES_MINBLOCKS", wpb == 4 ? 3 : 1); b->maxBlocksPerSM = 32;
     char headw[512];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 1), env_int("ODES_WDIV", 1),
+             env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
