@@ -85,7 +85,7 @@ class Emu:
         if not os.path.exists(lib):
             open(cu, "w").write(src)
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
-                                  (["-DODES_WARP=1"] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
+                                  ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
                                    f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
         self.lib = C.CDLL(lib)
         self.batch = batch
