@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sets", type=int, default=1_000_000, help="trajectories per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mapk", choices=["mapk", "repressilator", "goodwin", "huang"],
+                    help="mapk = the headline configuration (BASELINE configs[1]); the others are the parity-test configurations, for profiles/")
     ap.add_argument("--ref-sets", type=int, default=0, help="sets per step of the CPU arm (default: scaled to the core count)")
     ap.add_argument("--cpu-sets", type=int, default=0, help="sample size of the cpu_baseline leg (default: scaled to the core count)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -188,14 +190,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    w = H.workload("mapk")
+    w = H.workload(args.workload)
     m, nv, n = w["model"], len(w["vary"]), args.sets
     store = list(range(m.neq))
     b = so.Batch(m, w["opt"], w["vary"], store=store, device=local)
     b.reserve(n)
-    lo, hi = -np.ones(nv), np.ones(nv)
+    lo, hi = w["span"][0] * np.ones(nv), w["span"][1] * np.ones(nv)
     first = rank * n
-    b.generate_values(n, SEED, first, w["nominal"], lo, hi)
+    b.generate_values(n, SEED, first, w["nominal"], lo, hi, log10=w["log10"])
     fp64_peak = L.ODES_measureFP64Peak(local, 5) if rank == 0 else 0.0
 
     # ---------------- device-resident timing ----------------
@@ -264,7 +266,7 @@ def main():
         kind = "reference" if H.have_ref() else "port"
         ns = args.cpu_sets or max(2048, min(4000 * cores, 400_000, n))
         vals = b.get_values(ns)
-        cso = H.compile_c_model(m, "mapk")
+        cso = H.compile_c_model(m, args.workload)
         t0 = time.perf_counter()
         ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
         dt = time.perf_counter() - t0
@@ -282,16 +284,19 @@ def main():
         out_bytes = 8 * b.nrows * b.nstore + 8 * nv
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")
-        if os.path.exists(prof):
+        if os.path.exists(prof) and args.workload == "mapk":
             pj = json.load(open(prof))
             if pj.get("sets") and pj.get("dram_bytes") is not None:
                 traffic = pj["dram_bytes"] / pj["sets"] * n        # per launch of this size, scaled from the capture
         info = b.kernel_info()
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        workload_text = ("MAPK.xml parameter scan (BASELINE configs[1]): 21 kinetic constants x 2^U(-1,1), rtol 1e-6 atol 1e-9, t=0..1000, 100 output points, 8 species stored"
+                         if args.workload == "mapk" else
+                         f"{args.workload} (BASELINE parity configuration, not the headline): {nv} varied values, rtol 1e-6 atol 1e-9, t=0..{w['end']:g}, {w['nout']} output points, {m.neq} variables stored")
+        line = {"metric": METRIC if args.workload == "mapk" else f"trajectories/sec ({args.workload}, rtol 1e-6)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "MAPK.xml parameter scan (BASELINE configs[1]): 21 kinetic constants x 2^U(-1,1), rtol 1e-6 atol 1e-9, t=0..1000, 100 output points, 8 species stored",
+                "config": {"workload": workload_text,
                            "sets_per_gpu": n, "nvary": nv, "seed": SEED, "sharding": f"range x{world}, no collective",
-                           "l2": "per step 6.6 GB of outputs + inputs, far larger than the 126 MB L2; no explicit flush"},
+                           "l2": f"per step {1e-9 * n * (8 * b.nrows * b.nstore + 8 * nv):.1f} GB of outputs + inputs, far larger than the 126 MB L2; no explicit flush"},
                 "failed_sets": failed, "mean_stats": mean_stats, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                              "traffic": traffic, "peak_source": "measured live: ODES_measureFP64Peak (FMA chain micro-benchmark); MEASURED_PEAKS.json holds no FP64 figure",
