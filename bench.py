@@ -79,6 +79,32 @@ def algorithmic_flops(neq, Ff, FJ, mean_stats, qbar=4.0):
     return nfe * Ff + nje * FJ + nsetups * (2 * n ** 3 / 3 + 2 * n * n) + nni * (2 * n * n + 6 * n) + nst * n * (qbar * (qbar + 1) / 2 + 2 * (qbar + 1) + 10)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs of its GPU's NUMA node before anything is allocated, so that the pinned host
+    buffers of the end-to-end leg are node-local (8 ranks x 6.5 GB of results per step otherwise cross the sockets).
+    Returns a short description for the JSON line, or None when the topology cannot be read."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return None
+        bus = bus[-12:]                                              # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md, clocks line)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -171,6 +197,7 @@ def main():
     if L.ODES_deviceCount() <= local:
         raise SystemExit("bench.py: no CUDA device for this rank -- the batched integrator has no CPU fallback")
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch
@@ -295,7 +322,7 @@ def main():
         line = {"metric": METRIC if args.workload == "mapk" else f"trajectories/sec ({args.workload}, rtol 1e-6)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_text,
-                           "sets_per_gpu": n, "nvary": nv, "seed": SEED, "sharding": f"range x{world}, no collective",
+                           "sets_per_gpu": n, "nvary": nv, "seed": SEED, "sharding": f"range x{world}, no collective", "host_affinity": numa,
                            "l2": f"per step {1e-9 * n * (8 * b.nrows * b.nstore + 8 * nv):.1f} GB of outputs + inputs, far larger than the 126 MB L2; no explicit flush"},
                 "failed_sets": failed, "mean_stats": mean_stats, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,

@@ -359,7 +359,9 @@ static std::string build_source(odesBatch_t *b)
   /* larger networks: one trajectory per WARP (bdf_warp_kernel.cuh) -- state in registers, row of the Newton matrix
      per lane; chosen when a lane's linear-algebra words no longer fit tensor memory */
   int warp = env_int("ODES_WARP", -1);
-  if (warp < 0) warp = (la != 2 && neq > 8 && neq <= 32 && usejac) ? 1 : 0;
+  /* crossover measured with tools/gpu_layout_crossover.py (chain models, 10^5 sets): n = 16 lane 1.09 M vs warp 0.69 M,
+     n = 20 0.51 M vs 0.56 M, n = 24 0.26 M vs 0.48 M, n = 32 0.11 M vs 0.38 M trajectories/s; huang96 (n = 22) 82 k vs 174 k */
+  if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
   if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
   b->warpMode = warp;
   if (warp) {
