@@ -20,7 +20,7 @@ def _build():
 
 def test_examples_compile_as_c99():
     d = _build()
-    assert all(os.path.exists(os.path.join(d, x)) for x in ("integrate_timecourse", "parameter_scan", "batch_scan_results"))
+    assert all(os.path.exists(os.path.join(d, x)) for x in ("integrate_timecourse", "parameter_scan", "batch_scan_results", "odesolver_cli"))
 
 
 @pytest.mark.skipif(so.lib().ODES_deviceCount() > 0, reason="needs a box without a GPU")
@@ -82,3 +82,45 @@ def test_batch_scan_results_prints_species_per_design_point():
         for n, l in enumerate(lines[3:9]):
             want = ["%g" % (100.0 * n)] + ["%g" % v for v in ref["out"][s, n, :8]]
             assert l.split() == want, (s, n)
+
+
+def _cli(*args):
+    d = _build()
+    r = subprocess.run([os.path.join(d, "odesolver_cli"), H.model_path("mapk_cascade.xml")] + list(args), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.split("\n")
+
+
+@pytest.mark.gpu
+def test_cli_concentration_block_reproduces_the_golden_dat_file():
+    """examples/MAPK_10pt.dat: `#t names / ##CONCENTRATIONS / rows / ##CONCENTRATIONS / #t names` (odeSolver/printModel.c:915-944)."""
+    names = "MKKK MKKK_P MKK MKK_P MKK_PP MAPK MAPK_P MAPK_PP"
+    out = _cli("--time", "100", "--printstep", "10", "--error", "1e-12", "--rerror", "1e-10")
+    assert out[0] == f"#t {names} " and out[1] == "##CONCENTRATIONS"
+    assert out[13] == "##CONCENTRATIONS" and out[14] == f"#t {names} " and out[15:] == ["", "", ""]
+    got = np.array([[float(x) for x in l.split()] for l in out[2:13]])
+    gold = np.loadtxt(os.path.join(H.ROOT, "tests", "golden", "mapk_10pt.dat.txt"), comments="#")
+    assert np.array_equal(got[:, 0], gold[:, 0])
+    np.testing.assert_allclose(got[:, 1:], gold[:, 1:], rtol=2e-6)      # printed from a converged run: one unit in the 6th digit
+    assert (got == gold).mean() > 0.95
+    assert all(l.endswith(" ") for l in out[2:13])                      # "%g " per value, as the reference prints
+
+
+@pytest.mark.gpu
+def test_cli_reaction_rates_block_matches_testrun_fluxes():
+    """-k with the CLI defaults (atol 1e-9, rtol 1e-4) prints the kinetic laws of examples/testrun.out:132-234."""
+    out = _cli("--time", "1000", "--printstep", "100", "-k")
+    assert out[0] == "#t J0 J1 J2 J3 J4 J5 J6 J7 J8 J9 " and out[1] == "##REACTION RATES" and out[103] == "##REACTION RATES"
+    gold = [l.strip() for l in open(os.path.join(H.ROOT, "tests", "golden", "mapk_testrun_fluxes.txt")) if not l.startswith("#")]
+    assert [l.strip() for l in out[2:103]] == gold                      # every printed character
+
+
+@pytest.mark.gpu
+def test_cli_all_values_and_ode_values():
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    out = _cli("--time", "50", "--printstep", "5", "-a")
+    assert out[0].split() == ["#t"] + m.names and len(out[2].split()) == 1 + m.nvalues
+    out = _cli("--time", "50", "--printstep", "5", "-y")
+    assert out[1] == "##ODE VALUES" and out[0].split() == ["#t"] + m.names[:8]
+    row = [float(x) for x in out[2].split()]
+    assert abs(row[1] + row[2]) < 1e-12                                  # d[MKKK]/dt = -d[MKKK_P]/dt
