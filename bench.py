@@ -265,7 +265,7 @@ def main():
         vals = np.ctypeslib.as_array(C.cast(hv, C.POINTER(C.c_double)), shape=(n, nv))
         res = np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_double)), shape=(n, b.nrows, b.nstore))     # [set][row][value]
         hst = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_int)), shape=(n,))
-        chunk = 1 << 18
+        chunk = 0                                                  # one launch; finished groups of sets stream back while it runs
         vals[:] = b.get_values(n)                                  # this step's device-generated sets, as host rows
         for _ in range(2):
             b.run_host(vals, res, hst, chunk=chunk)

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sched.h>
 #include <string>
 #include <vector>
 #include "sbmlsolver/batchIntegrator.h"
@@ -31,6 +32,7 @@ extern "C" const char odes_bdf_kernel_source[];     /* bdf_kernel.cuh embedded a
 struct OdesArgs {
   const double *vary; double *out; int *status; int *stats; unsigned int *fired; const double *tpoints;
   unsigned long long *counter; double *scratch; unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
+  unsigned int *groupDone; unsigned int *hostFlags; int groupShift, pad2;
 };
 
 /* --------------------------------------------------------------- driver API */
@@ -297,6 +299,7 @@ struct odesBatch {
   int capacity;
   double *d_vary, *d_out, *d_tpoints, *d_rows; int *d_status, *d_stats; unsigned int *d_fired; unsigned long long *d_counter; int numSMs, blocksPerSM, counterSlot; double *d_scratch; int warpMode, laMode, laWords, tmemCols, maxBlocksPerSM;
   size_t rowsCap;
+  unsigned int *d_groupDone, *h_flags, *d_flags; int groupCap;   /* completion signalling of the host pipeline */
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
   std::vector<double> base; std::vector<int> trigger0;
@@ -323,7 +326,7 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
   if (ODES_deviceCount() > b->device) {
     cudaSetDevice(b->device);
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
-    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch);
+    cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch); cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copyIn) cudaStreamDestroy(b->copyIn);
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
@@ -589,9 +592,11 @@ extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long
 
 /* One launch = one persistent grid (resident blocks only); lanes pull set indices from a device counter.
    Each launch in flight uses its own counter slot (the pipelined host path has several in flight). */
-static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed)
+static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed, int groupShift = -1)
 {
   OdesArgs a;
+  a.groupDone = NULL; a.hostFlags = NULL; a.groupShift = 0; a.pad2 = 0;
+  if (groupShift >= 0) { a.groupDone = b->d_groupDone; a.hostFlags = b->d_flags; a.groupShift = groupShift; }
   a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
   a.counter = b->d_counter + (b->counterSlot++ & 63);
@@ -682,18 +687,17 @@ extern "C" int ODESBatch_getEventLog(odesBatch_t *b, int nsets, unsigned int *fi
   return 1;
 }
 
-/* End-to-end helper with HOST buffers: the batch is cut into chunks; H2D of chunk k+1, the kernel of
-   chunk k and D2H of chunk k-1 overlap on three streams.  values: [nsets][nvary] rows,
-   results: [nsets][nout+1][nstore]. */
-extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
+/* End-to-end helper with HOST buffers.  values: [nsets][nvary] rows, results: [nsets][nout+1][nstore].
+   The batch is cut into chunks (default: one chunk up to 2^22 sets); per chunk, H2D + transpose, ONE launch, and the
+   results stream back while the kernel runs: sets are handed out in index order, the lane that completes a group of
+   2^ODES_GROUP_SHIFT consecutive sets raises a flag in mapped host memory, and this thread copies every finished
+   group (results are trajectory-major, so a group is one contiguous block) on the copy stream.  Only the last
+   groups' copies are left when the kernel ends.  chunk < 0: the older scheme (-chunk sets per launch, copies of
+   chunk k-1 overlap the kernel of chunk k). */
+static int run_host_chunked(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
 {
-  if (!ODESBatch_reserve(b, nsets)) return 0;
-  if (chunk <= 0) chunk = 1 << 18;
-  chunk = (chunk + 31) & ~31;
   const int nchunks = (nsets + chunk - 1) / chunk;
   const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
-  const size_t need = (size_t)nsets * (size_t)(b->nvary > 0 ? b->nvary : 1);
-  if (need > b->rowsCap) { cudaFree(b->d_rows); b->d_rows = NULL; CUDA_OK(cudaMalloc(&b->d_rows, need * sizeof(double))); b->rowsCap = need; }
   for (int k = 0; k < nchunks; k++) {
     const size_t off = (size_t)k * (size_t)chunk;
     const int n = (int)((size_t)nsets - off < (size_t)chunk ? (size_t)nsets - off : (size_t)chunk);
@@ -713,6 +717,59 @@ extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values
   }
   CUDA_OK(cudaStreamSynchronize(b->copyOut));
   CUDA_OK(cudaStreamSynchronize(b->stream));
+  return 1;
+}
+extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
+{
+  if (!ODESBatch_reserve(b, nsets)) return 0;
+  const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  const size_t need = (size_t)nsets * (size_t)(b->nvary > 0 ? b->nvary : 1);
+  if (need > b->rowsCap) { cudaFree(b->d_rows); b->d_rows = NULL; CUDA_OK(cudaMalloc(&b->d_rows, need * sizeof(double))); b->rowsCap = need; }
+  if (chunk < 0) return run_host_chunked(b, nsets, values, results, status, ((-chunk) + 31) & ~31);
+  if (chunk == 0) chunk = 1 << 22;
+  chunk = (chunk + 31) & ~31;
+  const int shift = env_int("ODES_GROUP_SHIFT", 14);
+  const int gsize = 1 << shift;
+  const int maxGroups = (chunk + gsize - 1) / gsize;
+  if (maxGroups > b->groupCap) {
+    cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
+    b->d_groupDone = NULL; b->h_flags = NULL; b->groupCap = 0;
+    CUDA_OK(cudaMalloc(&b->d_groupDone, sizeof(unsigned int) * (size_t)maxGroups));
+    CUDA_OK(cudaHostAlloc((void **)&b->h_flags, sizeof(unsigned int) * (size_t)maxGroups, cudaHostAllocMapped));
+    CUDA_OK(cudaHostGetDevicePointer((void **)&b->d_flags, b->h_flags, 0));
+    b->groupCap = maxGroups;
+  }
+  for (size_t off = 0; off < (size_t)nsets; off += (size_t)chunk) {
+    const int n = (int)((size_t)nsets - off < (size_t)chunk ? (size_t)nsets - off : (size_t)chunk);
+    const int ngroups = (n + gsize - 1) / gsize;
+    if (b->nvary > 0) {
+      CUDA_OK(cudaMemcpyAsync(b->d_rows + off * (size_t)b->nvary, values + off * (size_t)b->nvary, sizeof(double) * (size_t)n * (size_t)b->nvary, cudaMemcpyHostToDevice, b->stream));
+      odes_rows_to_soa_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_rows + off * (size_t)b->nvary, b->d_vary + off, (size_t)b->capacity, n, b->nvary);
+    }
+    CUDA_OK(cudaMemsetAsync(b->d_groupDone, 0, sizeof(unsigned int) * (size_t)ngroups, b->stream));
+    for (int g = 0; g < ngroups; g++) ((volatile unsigned int *)b->h_flags)[g] = 0u;
+    if (!launch(b, n, off, b->stream, off == 0, shift)) return 0;
+    CUDA_OK(cudaEventRecord(b->evK[0], b->stream));
+    /* copy finished groups while the kernel runs; consecutive finished groups go out as one copy */
+    int next = 0;
+    while (next < ngroups) {
+      const cudaError_t q = cudaEventQuery(b->evK[0]);
+      if (q != cudaSuccess && q != cudaErrorNotReady) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "kernel failed: %s", cudaGetErrorString(q)); return 0; }
+      if (q == cudaErrorNotReady) (void)cudaGetLastError();
+      const bool over = (q == cudaSuccess);
+      int upto = next;
+      while (upto < ngroups && (over || ((volatile unsigned int *)b->h_flags)[upto])) upto++;
+      if (upto > next) {
+        const size_t s0 = off + (size_t)next * (size_t)gsize;
+        const size_t cnt = (size_t)(upto == ngroups ? n : upto * gsize) - (size_t)next * (size_t)gsize;
+        if (results) CUDA_OK(cudaMemcpyAsync(results + s0 * rows, b->d_out + s0 * rows, sizeof(double) * cnt * rows, cudaMemcpyDeviceToHost, b->copyOut));
+        if (status) CUDA_OK(cudaMemcpyAsync(status + s0, b->d_status + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, b->copyOut));
+        next = upto;
+      } else sched_yield();
+    }
+    CUDA_OK(cudaStreamSynchronize(b->copyOut));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+  }
   return 1;
 }
 

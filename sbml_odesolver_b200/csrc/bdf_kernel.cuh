@@ -202,7 +202,29 @@ struct OdesArgs {
   unsigned long long stride;
   int nsets, nout, mxstep, pad;
   double reltol, abstol;
+  /* completion signalling for the host pipeline (ODESBatch_runHost): sets are handed out in index order, so groups of
+     2^groupShift consecutive sets finish roughly in order; the lane that completes a group publishes it to a flag array
+     in mapped host memory and the host copies that group's results while the kernel is still integrating the rest */
+  unsigned int *groupDone;     /* [groups] device counters, zeroed before the launch; NULL: no signalling */
+  unsigned int *hostFlags;     /* [groups] mapped pinned host memory */
+  int groupShift, pad2;
 };
+#ifndef ODES_HOST_EMULATION
+__device__ __forceinline__ void odes_signal_done(const OdesArgs &a, size_t set)
+{
+  if (!a.groupDone) return;
+  __threadfence();                                            /* this trajectory's rows, status and counters first */
+  const unsigned int g = (unsigned int)(set >> a.groupShift);
+  const unsigned int first = g << a.groupShift, left = (unsigned int)a.nsets - first, full = 1u << a.groupShift;
+  const unsigned int size = left < full ? left : full;
+  if (atomicAdd(&a.groupDone[g], 1u) + 1u == size) {
+    __threadfence_system();
+    *((volatile unsigned int *)a.hostFlags + g) = 1u;
+  }
+}
+#else
+static inline void odes_signal_done(const OdesArgs &, size_t) {}
+#endif
 
 #define ODES_STR_(x) #x
 #define ODES_STR(x) ODES_STR_(x)
@@ -1248,6 +1270,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
         a.stats[3 * stride + set] = s.c_nje; a.stats[4 * stride + set] = s.c_nni; a.stats[5 * stride + set] = s.c_ncfn;
         a.stats[6 * stride + set] = s.c_netf;
       }
+      odes_signal_done(a, set);
       s.st = ST_DONE; idle = 0;
     }
     ODES_WARP_SYNC();

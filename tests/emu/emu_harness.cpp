@@ -26,6 +26,7 @@ extern "C" int emu_run(const double *base, const int *trig0, const double *vary,
   for (int i = 0; i < NEVENTS; i++) c_trigger0[i] = trig0[i];
   OdesArgs a;
   a.vary = vary; a.out = out; a.status = status; a.stats = stats; a.fired = fired; a.tpoints = tpoints;
+  a.groupDone = 0; a.hostFlags = 0; a.groupShift = 0; a.pad2 = 0;
   a.stride = stride; a.nsets = nsets; a.nout = nout; a.mxstep = mxstep; a.pad = 0; a.reltol = reltol; a.abstol = abstol;
   unsigned long long counter = 0;
   a.counter = &counter;

@@ -6,6 +6,8 @@ identical event firing order, identical failure flags.  The kernel replays CVODE
 operations in the reference's order, no FMA contraction, glibc's pow restated), so the tests demand more than the
 gate: the same per-trajectory work counters (nst, nfe, nsetups, nje, nni, ncfn, netf) and BIT-IDENTICAL stored
 values against the oracle driven with the same emitted right-hand side (the reference's compiled mode)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -125,8 +127,16 @@ def test_run_host_pipeline_and_one_shot_entry():
     direct = b.results(1000)
     res = np.zeros((1000, direct.shape[0], direct.shape[1]))          # [set][row][value], the library's layout
     st = np.zeros(1000, dtype=np.int32)
-    b.run_host(vals, res, st, chunk=256)
-    assert np.array_equal(np.transpose(res, (1, 2, 0)), direct) and (st == 0).all()
+    # chunk > 0: launches of that many sets, finished groups of sets stream back while the kernel runs (group size
+    # 2^ODES_GROUP_SHIFT, ragged last group); chunk < 0: the double-buffered scheme with one copy per launch
+    for chunk, shift in ((256, "5"), (0, "4"), (0, "14"), (992, "6"), (-256, "14")):
+        monkey_env = dict(ODES_GROUP_SHIFT=shift)
+        os.environ.update(monkey_env)
+        res[:] = -1.0
+        st[:] = -1
+        b.run_host(vals, res, st, chunk=chunk)
+        assert np.array_equal(np.transpose(res, (1, 2, 0)), direct) and (st == 0).all(), (chunk, shift)
+    os.environ.pop("ODES_GROUP_SHIFT")
     b.close()
     ii = L.IntegratorInstance_create(m.om, w["opt"])
     assert ii
@@ -246,4 +256,23 @@ def test_warp_layout_failure_flags(monkeypatch):
     ref = H.oracle_run(m, opt, w["vary"], vals, 4, compiled_so=H.compile_c_model(m, "mapk"))
     assert (st == -4).all() and np.array_equal(st, ref["status"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    b.close()
+
+
+def test_run_host_streams_results_of_the_warp_layout():
+    """The warp-per-trajectory kernel raises the same completion flags (huang96, failures included: mxstep too small for some sets)."""
+    w = H.workload("huang", nout=10)
+    m = w["model"]
+    opt = so.settings(10.0, 10, 1e-9, 1e-6, mxstep=40)
+    vals = H.workload_values(w, 700, seed=8)
+    b = so.Batch(m, opt, w["vary"], store=list(range(m.neq)))
+    b.set_values(vals)
+    b.integrate(700)
+    direct, dst = b.results(700), b.status(700)
+    res = np.zeros((700, direct.shape[0], direct.shape[1]))
+    st = np.zeros(700, dtype=np.int32)
+    os.environ["ODES_GROUP_SHIFT"] = "5"
+    b.run_host(vals, res, st, chunk=0)
+    os.environ.pop("ODES_GROUP_SHIFT")
+    assert np.array_equal(np.transpose(res, (1, 2, 0)), direct, equal_nan=True) and np.array_equal(st, dst)
     b.close()
