@@ -86,7 +86,9 @@ int ODESBatch_getTrajectory(odesBatch_t *, int set, double *traj /* [nout+1][nst
 int ODESBatch_getStatus(odesBatch_t *, int nsets, int *status);
 int ODESBatch_getStats(odesBatch_t *, int nsets, int *stats /* [ODES_NUM_STATS][nsets] */);
 int ODESBatch_getEventLog(odesBatch_t *, int nsets, unsigned int *fired /* [nout+1][nsets] bitmasks */);
-/* pipelined end-to-end helper: chunks the batch, overlaps H2D / kernel / D2H on three streams */
+/* end-to-end helper with host buffers (values [nsets][nvary] in, results [nsets][nout+1][nstore] and status out).
+   chunk >= 0: launches of `chunk` sets (0: up to 2^22), the results of finished groups of sets are copied back while
+   the kernel runs; chunk < 0: launches of -chunk sets, the copy of launch k-1 overlaps launch k */
 int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *results, int *status,
                       int chunk);
 
