@@ -9,6 +9,9 @@ Sources (reference file:line):
   unittest/test_processAST.c:248-299  differentiateAST strings (d/dx)
   unittest/test_processAST.c:333-367  simplifyAST strings
   unittest/test_integratorSettings.c  defaults of CvodeSettings_create / createWithTime
+  unittest/test_odeConstruct.c:34-91   Model_getValueById / Model_setValue
+  unittest/test_odeConstruct.c:93-412  Model_reduceToOdes: object counts, parameter order, rule formulas
+  unittest/test_odeConstruct.c:414-520 Species_odeFromReactions: the ODE of every species as a formula string
 """
 import json
 import os
@@ -37,7 +40,7 @@ def cstr(s):
     return bytes(s, "utf-8").decode("unicode_escape")
 
 
-kats = {"structure": [], "jacobian": [], "evaluate": [], "differentiate": [], "simplify": []}
+kats = {"structure": [], "jacobian": [], "evaluate": [], "differentiate": [], "simplify": [], "reduce": [], "species_ode": [], "get_value": [], "set_value": []}
 
 for name, body in tests_of(os.path.join(REF, "unittest/test_odeModel.c")):
     fm = re.search(r'EXAMPLES_FILENAME\("([^"]+)"\)', body)
@@ -72,6 +75,25 @@ for name, body in tests_of(os.path.join(REF, "unittest/test_processAST.c")):
     elif name == "test_simplifyAST":
         for inp, exp in re.findall(r'CHECK_SIMPLIFY\("([^"]+)", "([^"]+)"\)', body):
             kats["simplify"].append([inp, exp])
+
+for name, body in tests_of(os.path.join(REF, "unittest/test_odeConstruct.c")):
+    fm = re.search(r'EXAMPLES_FILENAME\("([^"]+)"\)', body)
+    if not fm or fm.group(1) not in MODEL_ALIAS:
+        continue
+    model = MODEL_ALIAS[fm.group(1)]
+    if name.startswith("test_Model_reduceToOdes_"):
+        counts = {fn: int(v) for fn, v in re.findall(r"ck_assert\(Model_(getNum\w+)\(omodel\) == (\d+)\)", body)}
+        params = [[int(i), nm] for i, nm in re.findall(r'CHECK_PARAMETER\(omodel, (\d+), "([^"]+)"\)', body)]
+        rules = [[int(i), f] for i, f in re.findall(r'CHECK_RULE\(omodel, (\d+), "([^"]+)"\)', body)]
+        kats["reduce"].append({"test": name, "model": model, "counts": counts, "parameters": params, "rules": rules})
+    elif name.startswith("test_Species_odeFromReactions_"):
+        kats["species_ode"].append({"test": name, "model": model, "odes": [[int(i), f] for i, f in re.findall(r'check_species\((\d+), "([^"]+)"\)', body)]})
+    elif name == "test_Model_getValueById":
+        pairs = re.findall(r'Model_getValueById\(model, "([^"]+)"\);\s*ck_assert\(v == ([^)]+)\)', body)
+        kats["get_value"].append({"model": model, "values": [[k, float(v)] for k, v in pairs]})
+    elif name == "test_Model_setValue":
+        calls = re.findall(r'Model_setValue\(model, "([^"]+)", (NULL|"[^"]+"), ([0-9.]+)\);\s*ck_assert\(r == (\d)\)', body)
+        kats["set_value"].append({"model": model, "calls": [[i, None if r == "NULL" else r.strip('"'), float(v), int(ok)] for i, r, v, ok in calls]})
 
 json.dump(kats, open(OUT, "w"), indent=1)
 print({k: len(v) for k, v in kats.items()})

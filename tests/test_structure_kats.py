@@ -128,3 +128,86 @@ def test_mapk_globalised_parameters_are_appended():
     assert m.names[18:22] == ["uVol", "V1", "Ki", "K1"]
     assert m.names[22:] == [f"r_{r}_{p}" for r, p in so.MAPK_LOCALS]
     assert len(vary) == 21 and (nominal > 0).all()
+
+
+# ---- ODE assembly (src/odeConstruct.c:85-584) against unittest/test_odeConstruct.c ----
+class _Rule(C.Structure):
+    _fields_ = [("type", C.c_int), ("variable", C.c_char_p), ("math", C.c_void_p)]
+
+
+class _Param(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("value", C.c_double), ("isSetValue", C.c_int), ("constant", C.c_int)]
+
+
+def _model_api():
+    L = so.lib()
+    for fn in ("Model_getNumCompartments", "Model_getNumSpecies", "Model_getNumParameters", "Model_getNumReactions", "Model_getNumRules",
+               "Model_getNumEvents", "Model_getNumInitialAssignments", "Model_getNumFunctionDefinitions"):
+        getattr(L, fn).restype, getattr(L, fn).argtypes = C.c_uint, [C.c_void_p]
+    for fn in ("Model_getRule", "Model_getParameter", "Model_getSpecies"):
+        getattr(L, fn).restype, getattr(L, fn).argtypes = C.c_void_p, [C.c_void_p, C.c_uint]
+    L.Model_reduceToOdes.restype, L.Model_reduceToOdes.argtypes = C.c_void_p, [C.c_void_p]
+    L.Species_odeFromReactions.restype, L.Species_odeFromReactions.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p]
+    L.Model_getValueById.restype, L.Model_getValueById.argtypes = C.c_double, [C.c_void_p, C.c_char_p]
+    L.Model_setValue.restype, L.Model_setValue.argtypes = C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]
+    L.Model_free.restype, L.Model_free.argtypes = None, [C.c_void_p]
+    return L
+
+
+def _doc(name):
+    L = so.lib()
+    d = L.readSBML(H.model_path(name).encode())
+    assert d
+    return d, L.SBMLDocument_getModel(d)
+
+
+@pytest.mark.parametrize("kat", KATS["reduce"], ids=lambda k: k["model"])
+def test_model_reduce_to_odes(kat):
+    """unittest/test_odeConstruct.c:93-412: the reduced model (reactions replaced by rate rules + one assignment rule
+    per reaction): object counts, parameter order, and the formula of every rule, in order."""
+    L = _model_api()
+    d, m = _doc(kat["model"])
+    om = L.Model_reduceToOdes(m)
+    assert om and om != m
+    have = {"getNumCompartments", "getNumSpecies", "getNumParameters", "getNumReactions", "getNumRules", "getNumEvents",
+            "getNumInitialAssignments", "getNumFunctionDefinitions"}
+    for fn, want in kat["counts"].items():
+        if fn in have:
+            assert getattr(L, "Model_" + fn)(om) == want, fn
+        else:
+            assert want == 0, fn            # unit definitions, compartment / species types, constraints: not modelled, reference expects none
+    for i, name in kat["parameters"]:
+        assert C.cast(L.Model_getParameter(om, i), C.POINTER(_Param)).contents.id.decode() == name
+    for i, formula in kat["rules"]:
+        r = C.cast(L.Model_getRule(om, i), C.POINTER(_Rule)).contents
+        assert _str(r.math) == formula, (i, r.variable)
+    L.Model_free(om)
+    L.SBMLDocument_free(d)
+
+
+@pytest.mark.parametrize("kat", KATS["species_ode"], ids=lambda k: k["model"])
+def test_species_ode_from_reactions(kat):
+    """unittest/test_odeConstruct.c:414-520: the ODE of every species, built from the stoichiometry, as a formula string."""
+    L = _model_api()
+    d, m = _doc(kat["model"])
+    for i, formula in kat["odes"]:
+        n = L.Species_odeFromReactions(L.Model_getSpecies(m, i), m)
+        assert n, i
+        assert _str(n) == formula, i
+        L.ASTNode_free(n)
+    L.SBMLDocument_free(d)
+
+
+def test_model_get_value_and_set_value():
+    """unittest/test_odeConstruct.c:34-91"""
+    L = _model_api()
+    for kat in KATS["get_value"]:
+        d, m = _doc(kat["model"])
+        for ident, want in kat["values"]:
+            assert L.Model_getValueById(m, ident.encode()) == want, ident
+        L.SBMLDocument_free(d)
+    for kat in KATS["set_value"]:
+        d, m = _doc(kat["model"])
+        for ident, rid, value, ok in kat["calls"]:
+            assert L.Model_setValue(m, ident.encode(), rid.encode() if rid else None, value) == ok, (ident, rid)
+        L.SBMLDocument_free(d)
