@@ -14,7 +14,7 @@
  *
  * All pointers are plain host pointers unless named "device".  No torch types.
  * Every function returns 1 on success and 0 on failure (a SolverError is
- * pushed, codes 14XXXX) unless stated otherwise.  There is no CPU fallback:
+ * pushed, codes 15XXXX) unless stated otherwise.  There is no CPU fallback:
  * without a CUDA device every launch entry fails with
  * SOLVER_ERROR_CUDA_UNAVAILABLE.
  */

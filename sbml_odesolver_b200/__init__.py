@@ -9,7 +9,7 @@ plus the new ODESBatch_* / IntegratorInstance_integrateBatch batched entry).
 
 There is no Python or CPU implementation of the integrator behind it: if the
 library is missing, importing raises; if no CUDA device is present, every
-launch entry fails with SOLVER_ERROR_CUDA_UNAVAILABLE (140000).
+launch entry fails with SOLVER_ERROR_CUDA_UNAVAILABLE (150000).
 """
 import ctypes as C
 import os

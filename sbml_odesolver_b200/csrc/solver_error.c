@@ -13,7 +13,8 @@
 typedef struct { errorCode_t code; char *msg; } entry_t;
 static struct { entry_t *e; int n, cap; } store[NUMBER_OF_ERROR_TYPES];
 static pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
-static const char *TYPE_NAME[NUMBER_OF_ERROR_TYPES] = { "Fatal Error", "Error", "Warning", "Message" };
+/* right-aligned type names and tab-separated fields: the dump format unittest/test_solverError.c:131-147 pins */
+static const char *TYPE_NAME[NUMBER_OF_ERROR_TYPES] = { "Fatal Error", "      Error", "    Warning", "    Message" };
 
 void SolverError_error(errorType_t type, errorCode_t code, const char *fmt, ...)
 {
@@ -50,7 +51,7 @@ char *SolverError_dumpToString(void)
   for (t = 0; t < NUMBER_OF_ERROR_TYPES; t++)
     for (i = 0; i < store[t].n; i++) {
       char line[2300];
-      int n = snprintf(line, sizeof line, "%s: %d %s\n", TYPE_NAME[t], (int)store[t].e[i].code, store[t].e[i].msg);
+      int n = snprintf(line, sizeof line, "%s\t%d\t%s\n", TYPE_NAME[t], (int)store[t].e[i].code, store[t].e[i].msg);
       if (len + (size_t)n + 1 > cap) { cap = 2 * (len + (size_t)n + 1); s = (char *)realloc(s, cap); }
       memcpy(s + len, line, (size_t)n + 1); len += (size_t)n;
     }

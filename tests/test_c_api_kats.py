@@ -1,0 +1,16 @@
+"""Builds and runs tests/c/test_api_kats.c: the reference's unit tests of VarySettings_*, SolverError_* and the
+SBMLResults accessors (unittest/test_odeSolver.c:111-290, test_solverError.c:18-148, test_sbmlResults.c) restated as a
+plain C99 program against libodes_b200.so -- a drop-in caller's view of the kept API."""
+import os
+import subprocess
+
+import helpers as H
+
+
+def test_reference_api_unit_tests_in_c(tmp_path):
+    exe = tmp_path / "test_api_kats"
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-I" + os.path.join(H.ROOT, "include"), os.path.join(H.ROOT, "tests", "c", "test_api_kats.c"),
+                           "-o", str(exe), "-L" + os.path.join(H.ROOT, "sbml_odesolver_b200"), "-lodes_b200",
+                           "-Wl,-rpath," + os.path.join(H.ROOT, "sbml_odesolver_b200"), "-lm"])
+    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
