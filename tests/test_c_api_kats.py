@@ -4,13 +4,32 @@ plain C99 program against libodes_b200.so -- a drop-in caller's view of the kept
 import os
 import subprocess
 
+import pytest
+
 import helpers as H
 
 
-def test_reference_api_unit_tests_in_c(tmp_path):
-    exe = tmp_path / "test_api_kats"
-    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-I" + os.path.join(H.ROOT, "include"), os.path.join(H.ROOT, "tests", "c", "test_api_kats.c"),
+def _build(tmp_path, name):
+    exe = tmp_path / name
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-I" + os.path.join(H.ROOT, "include"), os.path.join(H.ROOT, "tests", "c", name + ".c"),
                            "-o", str(exe), "-L" + os.path.join(H.ROOT, "sbml_odesolver_b200"), "-lodes_b200",
                            "-Wl,-rpath," + os.path.join(H.ROOT, "sbml_odesolver_b200"), "-lm"])
+    return exe
+
+
+def test_reference_api_unit_tests_in_c(tmp_path):
+    exe = _build(tmp_path, "test_api_kats")
+    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_integrator_instance_unit_tests_compile(tmp_path):
+    _build(tmp_path, "test_integrator_kats")
+
+
+@pytest.mark.gpu
+def test_integrator_instance_unit_tests_in_c(tmp_path):
+    """unittest/test_integratorInstance.c:15-150 with the default settings, through the kept single-instance API."""
+    exe = _build(tmp_path, "test_integrator_kats")
     r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
