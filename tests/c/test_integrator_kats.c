@@ -35,7 +35,7 @@ int main(int argc, char **argv)
   /* results */
   cr = IntegratorInstance_getResults(ii);
   CK(ii->results == cr);
-  CK(CvodeResults_getNout(cr) == 10);
+  CK(CvodeResults_getNout(cr) == 11);                       /* number of time points, src/cvodeData.c:208-211 */
   for (i = 0; i <= 10; i++) CK_TOL(CvodeResults_getTime(cr, i), i * 0.1);
   CK(cr->value[0][0] == 90.0 && cr->value[0][10] < 90.0 && cr->value[0][10] > 89.0);      /* MKKK decays slowly from 90 */
   CK(fabs(cr->value[0][10] + cr->value[1][10] - 100.0) < 1e-8);                          /* MKKK + MKKK_P is conserved */
