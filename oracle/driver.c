@@ -156,6 +156,16 @@ static void *run_range(void *arg)
       if (rows) memcpy(rows + (size_t)iout * (size_t)nvalues, value, (size_t)nvalues * sizeof(double));
       if (jb->fired) jb->fired[(size_t)s * (size_t)(nout + 1) + (size_t)iout] = firedmask;
       if (jb->margin) jb->margin[(size_t)s * (size_t)(nout + 1) + (size_t)iout] = mg;
+      /* steady-state detection after the row is stored (src/integratorInstance.c:1176-1182, :1442-1507): mean and
+         standard deviation of the right-hand sides on the refreshed values */
+      if (opt->SteadyState == 1 && neq > 0) {
+        double mean = 0.0, var = 0.0;
+        for (i = 0; i < neq; i++) mean += fabs(oracle_eval(om->ode[i], value, t));
+        mean = mean / neq;
+        for (i = 0; i < neq; i++) { double dd = oracle_eval(om->ode[i], value, t) - mean; var += dd * dd; }
+        var = var / (neq - 1);
+        if ((mean + sqrt(var)) < opt->ssThreshold) halted = 1;
+      }
       if (halted) { iout++; break; }
     }
     if (flag < 0 || halted) {

@@ -55,6 +55,7 @@ _SIGS = {
     "CvodeSettings_setHaltOnEvent": (None, [c_p, c_i]), "CvodeSettings_setResetCvodeOnEvent": (None, [c_p, c_i]),
     "CvodeSettings_setTStop": (None, [c_p, c_i]), "CvodeSettings_setJacobian": (None, [c_p, c_i]),
     "CvodeSettings_setErrors": (None, [c_p, c_d, c_d, c_i]),
+    "CvodeSettings_setHaltOnSteadyState": (None, [c_p, c_i]), "CvodeSettings_setSteadyStateThreshold": (None, [c_p, c_d]),
     "IntegratorInstance_create": (c_p, [c_p, c_p]), "IntegratorInstance_free": (None, [c_p]),
     "IntegratorInstance_integrate": (c_i, [c_p]), "IntegratorInstance_integrateOneStep": (c_i, [c_p]),
     "IntegratorInstance_timeCourseCompleted": (c_i, [c_p]), "IntegratorInstance_getTime": (c_d, [c_p]),
@@ -192,10 +193,12 @@ class Model:
         return out
 
 
-def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1):
+def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1, steady_state=0, ss_threshold=None):
     """CvodeSettings_createWith(Time, PrintStep, Error, RError, Mxstep, Method=BDF, Iter=Newton, ...)."""
-    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, 0, 0, use_jacobian, 0, halt_on_event, 0, store_results, 0, 0)
+    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, 0, 0, use_jacobian, 0, halt_on_event, steady_state, store_results, 0, 0)
     _check(opt, "CvodeSettings_createWith")
+    if ss_threshold is not None:
+        lib().CvodeSettings_setSteadyStateThreshold(opt, ss_threshold)
     return opt
 
 

@@ -1417,6 +1417,9 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
 #if HALT_ON_EVENT
         if (firedmask) { s.st = ST_FINISH; break; }
 #endif
+#if HALT_ON_STEADY
+        if (steady_f(t, yl, pv)) { s.st = ST_FINISH; break; }       /* approximate steady state: the run ends with this row */
+#endif
         if (iout > a.nout) { s.st = ST_FINISH; break; }
 #if NEQ > 0
         if (restart) { s.st = ST_START; break; }    /* event assignment: the solver restarts from y[] */

@@ -734,6 +734,21 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   }
   CharBuffer_append(b, "}\n");
 
+  /* steady_f: IntegratorInstance_checkSteadyState (src/integratorInstance.c:1442-1507) at an output time, after the row
+     has been stored: mean and standard deviation of the right-hand sides, evaluated the way the reference's
+     interpreter does on the refreshed values; non-zero when mean + std is below the threshold */
+  cbprintf(b, "#define HALT_ON_STEADY %d\n", (opt->SteadyState == 1 && om->neq > 0) ? 1 : 0);
+  if (opt->SteadyState == 1 && om->neq > 0) {
+    CharBuffer_append(b, "#define SS_THRESHOLD "); CharBuffer_appendDouble(b, opt->ssThreshold); CharBuffer_append(b, "\n");
+    CharBuffer_append(b, "DEV int steady_f(double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  double a[A1(NASS)], dy[A1(NEQ)], mean = 0.0, var = 0.0; (void)t; (void)a; (void)pv;\n");
+    k.local = all_local; c.interp = 1;
+    emit_refresh_all(b, om, &c, "  ");
+    for (i = 0; i < om->neq; i++) { cbprintf(b, "  dy[%d] = ", i); gen(b, om->ode[i], &c); CharBuffer_append(b, ";\n"); }
+    CharBuffer_append(b, "  _Pragma(\"unroll\") for (int i = 0; i < NEQ; i++) mean += fabs(dy[i]);\n  mean = mean / NEQ;\n"
+                         "  _Pragma(\"unroll\") for (int i = 0; i < NEQ; i++) { const double d = dy[i] - mean; var += d * d; }\n"
+                         "  var = var / (NEQ - 1);\n  return (mean + sqrt(var)) < SS_THRESHOLD;\n}\n");
+  }
+
   free(k.kind); free(k.slot); free(used_in_ode); free(all_local); free(ode_local);
   out = b->b; b->b = NULL; CharBuffer_free(b);
   return out;

@@ -247,8 +247,9 @@ SBMLResultsArray_t *SBMLResultsArray_fromBatch(Model_t *m, odeModel_t *om, const
   for (i = 0; i < b->nsets; i++) {
     const double *v = b->value + (size_t)i * (size_t)b->nout * (size_t)b->nvalues;
     int np = b->nout;
-    /* integration failures leave NaN rows: the reference's results end at the last stored index (integratorInstance.c:1141) */
-    while (np > 1 && b->nvalues > 0 && v[(size_t)(np - 1) * (size_t)b->nvalues] != v[(size_t)(np - 1) * (size_t)b->nvalues] && b->status[i] != 0) np--;
+    /* rows a run did not reach (solver failure, halt on event, halt on steady state) are not-a-number in the flat
+       results: the reference's results end at the last stored index (integratorInstance.c:1141) */
+    while (np > 1 && b->nvalues > 0 && v[(size_t)(np - 1) * (size_t)b->nvalues] != v[(size_t)(np - 1) * (size_t)b->nvalues]) np--;
     a->results[i] = SBMLResults_create(m, np);
     for (n = 0; n < np; n++) ResultMap_fill(map, a->results[i], n, b->time[n], v + (size_t)n * (size_t)b->nvalues, data);
   }

@@ -114,3 +114,27 @@ def test_emulated_warp_kernel_is_bit_identical_on_the_small_models(monkeypatch, 
     assert np.array_equal(got["stats"].T, ref["stats"])
     assert np.array_equal(got["fired"].T, ref["fired"])
     assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+
+
+@pytest.mark.parametrize("warp", [0, 1])
+def test_emulated_steady_state_halt(monkeypatch, warp):
+    """CvodeSettings_setHaltOnSteadyState per trajectory (src/integratorInstance.c:1176-1182, :1442-1507): a run ends
+    with the first output row at which mean + standard deviation of the rates falls below the threshold; later rows
+    are not-a-number, the status stays 0.  huang96 settles; every set stops at the row the oracle stops at."""
+    monkeypatch.setenv("ODES_WARP", str(warp))
+    w = H.workload("huang", nout=40)
+    m = w["model"]
+    opt = so.settings(400.0, 40, 1e-9, 1e-6, steady_state=1, ss_threshold=1e-5)
+    vals = H.workload_values(w, 6, seed=12)
+    b = so.Batch(m, opt, w["vary"])
+    emu = H.Emu(b, f"huang_steady{warp}")
+    base, trig = b.base_values()
+    got = emu.run(base, trig, vals, H.tpoints(opt, 40), 10000, 1e-6, 1e-9)
+    b.close()
+    ref = H.oracle_run(m, opt, w["vary"], vals, 40, compiled_so=H.compile_c_model(m, "huang"))
+    want = np.transpose(ref["out"], (1, 2, 0))
+    last = (~np.isnan(want[:, 0, :])).sum(axis=0)                      # rows stored per set
+    assert ((last > 3) & (last < 41)).all(), last                       # every set halts somewhere inside the grid
+    assert (got["status"] == 0).all() and np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(np.isnan(got["out"]), np.isnan(want))
+    assert np.array_equal(got["out"], want, equal_nan=True)

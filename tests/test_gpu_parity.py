@@ -276,3 +276,23 @@ def test_run_host_streams_results_of_the_warp_layout():
     os.environ.pop("ODES_GROUP_SHIFT")
     assert np.array_equal(np.transpose(res, (1, 2, 0)), direct, equal_nan=True) and np.array_equal(st, dst)
     b.close()
+
+
+@pytest.mark.parametrize("warp", [0, 1])
+def test_steady_state_halt_on_gpu(monkeypatch, warp):
+    """Per-trajectory steady-state halting (CvodeSettings_setHaltOnSteadyState): same last row as the oracle, rows after
+    it not-a-number, status 0 -- in both layouts."""
+    monkeypatch.setenv("ODES_WARP", str(warp))
+    w = H.workload("huang", nout=40)
+    m = w["model"]
+    opt = so.settings(400.0, 40, 1e-9, 1e-6, steady_state=1, ss_threshold=1e-5)
+    vals = H.workload_values(w, 300, seed=12)
+    b = so.Batch(m, opt, w["vary"])
+    b.set_values(vals)
+    b.integrate(300)
+    out, st = b.results(300), b.status(300)
+    b.close()
+    ref = H.oracle_run(m, opt, w["vary"], vals, 40, compiled_so=H.compile_c_model(m, "huang"), threads=8)
+    want = np.transpose(ref["out"], (1, 2, 0))
+    assert (st == 0).all() and np.isnan(want[-1, 0, :]).mean() > 0.5        # most sets settle inside the grid
+    assert np.array_equal(out, want, equal_nan=True)

@@ -107,10 +107,12 @@ def test_failed_design_point_ends_at_its_last_stored_row():
     m = so.Model(H.model_path("mapk_cascade.xml"))
     out = np.tile(m.base_values()[None, None, :], (2, 6, 1))
     out[1, 4:, :] = np.nan
-    flat = _flat(out, np.array([0, -4]), np.arange(6.0))
+    out = np.concatenate([out, out[1:2]])                              # a third point: halted (status 0), e.g. steady state
+    flat = _flat(out, np.array([0, -4, 0]), np.arange(6.0))
     arr = L.SBMLResultsArray_fromBatch(m.sbml, m.om, C.byref(flat))
     assert L.SBMLResults_getNout(L.SBMLResultsArray_getResults(arr, 0)) == 6
     assert L.SBMLResults_getNout(L.SBMLResultsArray_getResults(arr, 1)) == 4
+    assert L.SBMLResults_getNout(L.SBMLResultsArray_getResults(arr, 2)) == 4
     L.SBMLResultsArray_free(arr)
 
 
