@@ -9,6 +9,7 @@ Sources (reference file:line):
   unittest/test_processAST.c:248-299  differentiateAST strings (d/dx)
   unittest/test_processAST.c:333-367  simplifyAST strings
   unittest/test_integratorSettings.c  defaults of CvodeSettings_create / createWithTime
+  unittest/test_sbml.c:16-240          parseModel: object counts, parameter ids, reaction ids and kinetic-law formulas
   unittest/test_odeConstruct.c:34-91   Model_getValueById / Model_setValue
   unittest/test_odeConstruct.c:93-412  Model_reduceToOdes: object counts, parameter order, rule formulas
   unittest/test_odeConstruct.c:414-520 Species_odeFromReactions: the ODE of every species as a formula string
@@ -40,7 +41,7 @@ def cstr(s):
     return bytes(s, "utf-8").decode("unicode_escape")
 
 
-kats = {"structure": [], "jacobian": [], "evaluate": [], "differentiate": [], "simplify": [], "reduce": [], "species_ode": [], "get_value": [], "set_value": []}
+kats = {"structure": [], "jacobian": [], "evaluate": [], "differentiate": [], "simplify": [], "reduce": [], "species_ode": [], "get_value": [], "set_value": [], "parse": []}
 
 for name, body in tests_of(os.path.join(REF, "unittest/test_odeModel.c")):
     fm = re.search(r'EXAMPLES_FILENAME\("([^"]+)"\)', body)
@@ -94,6 +95,15 @@ for name, body in tests_of(os.path.join(REF, "unittest/test_odeConstruct.c")):
     elif name == "test_Model_setValue":
         calls = re.findall(r'Model_setValue\(model, "([^"]+)", (NULL|"[^"]+"), ([0-9.]+)\);\s*ck_assert\(r == (\d)\)', body)
         kats["set_value"].append({"model": model, "calls": [[i, None if r == "NULL" else r.strip('"'), float(v), int(ok)] for i, r, v, ok in calls]})
+
+for name, body in tests_of(os.path.join(REF, "unittest/test_sbml.c")):
+    fm = re.search(r'EXAMPLES_FILENAME\("([^"]+)"\)', body)
+    if not fm or fm.group(1) not in MODEL_ALIAS or not name.startswith("test_parseModel_"):
+        continue
+    counts = {fn: int(v) for fn, v in re.findall(r"ck_assert\(Model_(getNum\w+)\(model\) == (\d+)\)", body)}
+    params = [[int(i), nm] for i, nm in re.findall(r'CHECK_PARAMETER\(model, (\d+), "([^"]+)"\)', body)]
+    reactions = [[int(i), rid, f] for i, rid, f in re.findall(r'CHECK_REACTION\(model, (\d+), "([^"]+)", "([^"]+)"\)', body)]
+    kats["parse"].append({"test": name, "model": MODEL_ALIAS[fm.group(1)], "counts": counts, "parameters": params, "reactions": reactions})
 
 json.dump(kats, open(OUT, "w"), indent=1)
 print({k: len(v) for k, v in kats.items()})

@@ -211,3 +211,36 @@ def test_model_get_value_and_set_value():
         for ident, rid, value, ok in kat["calls"]:
             assert L.Model_setValue(m, ident.encode(), rid.encode() if rid else None, value) == ok, (ident, rid)
         L.SBMLDocument_free(d)
+
+
+class _KineticLaw(C.Structure):
+    _fields_ = [("math", C.c_void_p)]
+
+
+class _Reaction(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("reversible", C.c_int), ("fast", C.c_int), ("reactants", C.c_byte * 16), ("products", C.c_byte * 16),
+                ("modifiers", C.c_byte * 16), ("kineticLaw", C.POINTER(_KineticLaw))]
+
+
+@pytest.mark.parametrize("kat", KATS["parse"], ids=lambda k: k["model"])
+def test_parse_model(kat):
+    """unittest/test_sbml.c:16-240: what the SBML reader delivers -- object counts, parameter ids, reaction ids and
+    kinetic-law formulas (compared without white space: the Level 1 files keep their formula text in the reference,
+    here every formula is rendered from the tree)."""
+    L = _model_api()
+    L.Model_getReaction.restype, L.Model_getReaction.argtypes = C.c_void_p, [C.c_void_p, C.c_uint]
+    d, m = _doc(kat["model"])
+    have = {"getNumCompartments", "getNumSpecies", "getNumParameters", "getNumReactions", "getNumRules", "getNumEvents",
+            "getNumInitialAssignments", "getNumFunctionDefinitions"}
+    for fn, want in kat["counts"].items():
+        if fn in have:
+            assert getattr(L, "Model_" + fn)(m) == want, fn
+        else:
+            assert want == 0, fn
+    for i, name in kat["parameters"]:
+        assert C.cast(L.Model_getParameter(m, i), C.POINTER(_Param)).contents.id.decode() == name
+    for i, rid, formula in kat["reactions"]:
+        r = C.cast(L.Model_getReaction(m, i), C.POINTER(_Reaction)).contents
+        assert r.id.decode() == rid
+        assert _str(r.kineticLaw.contents.math).replace(" ", "") == formula.replace(" ", ""), rid
+    L.SBMLDocument_free(d)
