@@ -4,12 +4,15 @@
  *   unittest/test_odeSolver.c:111-290     VarySettings_*  (fixture: VarySettings_allocate(3, 4))
  *   unittest/test_solverError.c:18-148    SolverError_*   (codes, order, dump format)
  *   unittest/test_sbmlResults.c:27-260    SBMLResults_* / TimeCourse_* accessors on a results object
+ *   unittest/test_modelSimplify.c:40-240  AST_replaceNameBy{Formula,Name,Value,Parameters}, AST_replaceFunctionDefinition,
+ *                                         AST_replaceConstants
  * Built and run by tests/test_c_api_kats.py (CPU tier; no device needed).
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "sbmlsolver/odeSolver.h"
+#include "sbmlsolver/processAST.h"
 #include "sbmlsolver/solverError.h"
 
 static int failures = 0;
@@ -131,11 +134,91 @@ static void test_sbml_results(const char *mapk)
   SBMLDocument_free(d);
 }
 
+/* fixture of unittest/test_modelSimplify.c: 1 + (x * x) */
+static ASTNode_t *sum_of_one_and_square(void) { ASTNode_t *n = SBML_parseFormula("1 + (x * x)"); CK(n != NULL); return n; }
+static void check_one_plus_product(ASTNode_t *node, ASTNode_t **factor0, ASTNode_t **factor1)
+{
+  ASTNode_t *c;
+  CK(ASTNode_getType(node) == AST_PLUS); CK(ASTNode_getNumChildren(node) == 2);
+  c = ASTNode_getChild(node, 0);
+  CK(ASTNode_getType(c) == AST_INTEGER); CK(ASTNode_getInteger(c) == 1);
+  c = ASTNode_getChild(node, 1);
+  CK(ASTNode_getType(c) == AST_TIMES); CK(ASTNode_getNumChildren(c) == 2);
+  *factor0 = ASTNode_getChild(c, 0); *factor1 = ASTNode_getChild(c, 1);
+}
+static void check_constants(const char *dir, const char *file, const char *formula, const char *expected)
+{
+  char path[4096]; SBMLDocument_t *d; ASTNode_t *n; char *s;
+  snprintf(path, sizeof path, "%s/%s", dir, file);
+  d = readSBML(path);
+  CK(d != NULL); if (!d) return;
+  n = SBML_parseFormula(formula);
+  AST_replaceConstants(SBMLDocument_getModel(d), n);
+  s = SBML_formulaToString(n);
+  CK_STR(s, expected);
+  free(s); ASTNode_free(n); SBMLDocument_free(d);
+}
+static void test_model_simplify(const char *dir)
+{
+  ASTNode_t *node, *n, *f[2], *c; int i;
+  /* replaceNameByFormula: x -> y/z */
+  node = sum_of_one_and_square(); n = SBML_parseFormula("y/z");
+  AST_replaceNameByFormula(node, "x", n);
+  check_one_plus_product(node, &f[0], &f[1]);
+  for (i = 0; i < 2; i++) {
+    CK(ASTNode_getType(f[i]) == AST_DIVIDE); CK(ASTNode_getNumChildren(f[i]) == 2);
+    c = ASTNode_getChild(f[i], 0); CK(ASTNode_getType(c) == AST_NAME); CK_STR(ASTNode_getName(c), "y");
+    c = ASTNode_getChild(f[i], 1); CK(ASTNode_getType(c) == AST_NAME); CK_STR(ASTNode_getName(c), "z");
+  }
+  ASTNode_free(n); ASTNode_free(node);
+  /* replaceNameByName */
+  node = sum_of_one_and_square();
+  AST_replaceNameByName(node, "x", "y");
+  check_one_plus_product(node, &f[0], &f[1]);
+  for (i = 0; i < 2; i++) { CK(ASTNode_getType(f[i]) == AST_NAME); CK_STR(ASTNode_getName(f[i]), "y"); }
+  ASTNode_free(node);
+  /* replaceNameByValue */
+  node = sum_of_one_and_square();
+  AST_replaceNameByValue(node, "x", 42.0);
+  check_one_plus_product(node, &f[0], &f[1]);
+  for (i = 0; i < 2; i++) { CK(ASTNode_getType(f[i]) == AST_REAL); CK(ASTNode_getReal(f[i]) == 42.0); }
+  ASTNode_free(node);
+  /* replaceNameByParameters: a list holding parameter x = 2.5 */
+  {
+    Model_t *m = Model_create(2, 4); Reaction_t *r = Model_createReaction(m, "r"); KineticLaw_t *kl = Reaction_createKineticLaw(r, "x");
+    KineticLaw_createParameter(kl, "x", 2.5);
+    node = sum_of_one_and_square();
+    AST_replaceNameByParameters(node, &kl->parameters);
+    check_one_plus_product(node, &f[0], &f[1]);
+    for (i = 0; i < 2; i++) { CK(ASTNode_getType(f[i]) == AST_REAL); CK(ASTNode_getReal(f[i]) == 2.5); }
+    ASTNode_free(node); Model_free(m);
+  }
+  /* replaceFunctionDefinition: f(1, f(x, y)) with f = lambda(a, b, a - b) */
+  node = SBML_parseFormula("f(1, f(x, y))"); n = SBML_parseFormula("lambda(a, b, a - b)");
+  CK(node != NULL && n != NULL);
+  AST_replaceFunctionDefinition(node, "f", n);
+  CK(ASTNode_getType(node) == AST_MINUS); CK(ASTNode_getNumChildren(node) == 2);
+  c = ASTNode_getChild(node, 0); CK(ASTNode_getType(c) == AST_INTEGER); CK(ASTNode_getInteger(c) == 1);
+  c = ASTNode_getChild(node, 1); CK(ASTNode_getType(c) == AST_MINUS); CK(ASTNode_getNumChildren(c) == 2);
+  CK(ASTNode_getType(ASTNode_getChild(c, 0)) == AST_NAME); CK_STR(ASTNode_getName(ASTNode_getChild(c, 0)), "x");
+  CK(ASTNode_getType(ASTNode_getChild(c, 1)) == AST_NAME); CK_STR(ASTNode_getName(ASTNode_getChild(c, 1)), "y");
+  ASTNode_free(n); ASTNode_free(node);
+  /* replaceConstants on the example models */
+  check_constants(dir, "mapk_cascade.xml", "V1 + Ki + K1", "2.5 + 9 + 10");
+  check_constants(dir, "basic_forward.xml", "c + k_1 + k_2", "1 + k_1 + k_2");
+  check_constants(dir, "basic_reversible.xml", "c + k_1 + k_2", "1 + 1 + k_2");
+}
+
 int main(int argc, char **argv)
 {
   test_vary_settings();
   test_solver_error();
-  if (argc > 1) test_sbml_results(argv[1]);
+  if (argc > 1) {
+    char path[4096];
+    snprintf(path, sizeof path, "%s/mapk_cascade.xml", argv[1]);
+    test_sbml_results(path);
+    test_model_simplify(argv[1]);
+  }
   if (failures) { fprintf(stderr, "%d check(s) failed\n", failures); return EXIT_FAILURE; }
   printf("ok\n");
   return EXIT_SUCCESS;

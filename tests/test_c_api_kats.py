@@ -1,5 +1,6 @@
 """Builds and runs tests/c/test_api_kats.c: the reference's unit tests of VarySettings_*, SolverError_* and the
-SBMLResults accessors (unittest/test_odeSolver.c:111-290, test_solverError.c:18-148, test_sbmlResults.c) restated as a
+SBMLResults accessors and the AST_replace* helpers (unittest/test_odeSolver.c:111-290, test_solverError.c:18-148,
+test_sbmlResults.c, test_modelSimplify.c) restated as a
 plain C99 program against libodes_b200.so -- a drop-in caller's view of the kept API."""
 import os
 import subprocess
@@ -19,7 +20,7 @@ def _build(tmp_path, name):
 
 def test_reference_api_unit_tests_in_c(tmp_path):
     exe = _build(tmp_path, "test_api_kats")
-    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
+    r = subprocess.run([str(exe), H.MODELS], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
 
 
