@@ -92,6 +92,14 @@ int ODESBatch_getEventLog(odesBatch_t *, int nsets, unsigned int *fired /* [nout
 int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *results, int *status,
                       int chunk);
 
+/* the same over all GPUs of the box: device k integrates the index range [k n / G, (k+1) n / G) of the caller's arrays
+   (no collective; one plan and one host thread per device).  ndevices <= 0: all devices when every one gets at least
+   2^15 sets (ODES_DEVICES overrides).  Returns the number of devices used, 0 on failure.  IntegratorInstance_integrateBatch
+   and Model_odeSolverBatch[Flat] run through this entry. */
+int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore,
+                                const int *storeIndex /* NULL: all values */, int nsets, const double *values,
+                                double *results, int *status, int ndevices);
+
 /* device utilities */
 int ODES_deviceCount(void);
 int ODES_deviceName(int device, char *buf, int len);

@@ -86,6 +86,7 @@ _SIGS = {
     "ODESBatch_getResults": (c_i, [c_p, c_i, c_p]), "ODESBatch_getTrajectory": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_getStatus": (c_i, [c_p, c_i, c_p]), "ODESBatch_getStats": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_getEventLog": (c_i, [c_p, c_i, c_p]), "ODESBatch_runHost": (c_i, [c_p, c_i, c_p, c_p, c_p, c_i]),
+    "ODESBatch_runHostAllDevices": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_i]),
     "ODES_deviceCount": (c_i, []), "ODES_deviceName": (c_i, [c_i, c_p, c_i]), "ODES_measureFP64Peak": (c_d, [c_i, c_i]),
     "ODES_hostAlloc": (c_p, [C.c_size_t]), "ODES_hostFree": (None, [c_p]),
     "SolverError_getNum": (c_i, [c_i]), "SolverError_getLastCode": (c_i, [c_i]), "SolverError_clear": (None, []),

@@ -21,6 +21,7 @@
 #include <sys/stat.h>
 #include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 #include "sbmlsolver/batchIntegrator.h"
 #include "sbmlsolver/processAST.h"
@@ -777,6 +778,42 @@ extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values
 extern "C" void *ODES_hostAlloc(size_t bytes) { void *p = NULL; if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; } return p; }
 extern "C" void ODES_hostFree(void *p) { if (p) cudaFreeHost(p); }
 
+/* The batch over all GPUs of the box: device k integrates the index range [k n / G, (k+1) n / G) --
+   trajectories are independent, there is no exchange step and no collective.  One plan per device (the generated
+   source is identical, so devices after the first load the cached cubin), one host thread per device driving
+   ODESBatch_runHost on its slice of the caller's arrays.  ndevices <= 0: all devices for batches of at least 2^15
+   sets per device (ODES_DEVICES overrides), else one. */
+extern "C" int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex,
+                                           int nsets, const double *values, double *results, int *status, int ndevices)
+{
+  int have = ODES_deviceCount();
+  if (ndevices <= 0) {
+    ndevices = env_int("ODES_DEVICES", 0);
+    if (ndevices <= 0) { ndevices = have; while (ndevices > 1 && nsets / ndevices < (1 << 15)) ndevices--; }
+  }
+  if (ndevices > have) ndevices = have;
+  if (ndevices < 1) ndevices = 1;                              /* no device: the single plan fails loudly below */
+  std::vector<odesBatch_t *> plans((size_t)ndevices, (odesBatch_t *)NULL);
+  int ok = 1;
+  for (int k = 0; k < ndevices && ok; k++) { plans[(size_t)k] = ODESBatch_create(om, opt, nvary, varyIndex, nstore, storeIndex, k); if (!plans[(size_t)k]) ok = 0; }
+  if (ok) {
+    const size_t rows = (size_t)(opt->PrintStep + 1) * (size_t)plans[0]->nstore;
+    std::vector<int> done((size_t)ndevices, 0);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < ndevices; k++) {
+      size_t lo = ((size_t)nsets * (size_t)k / (size_t)ndevices) & ~(size_t)31, hi = (k + 1 == ndevices) ? (size_t)nsets : (((size_t)nsets * (size_t)(k + 1) / (size_t)ndevices) & ~(size_t)31);
+      workers.emplace_back([&, k, lo, hi]() {
+        done[(size_t)k] = (hi <= lo) ? 1 : ODESBatch_runHost(plans[(size_t)k], (int)(hi - lo), values + lo * (size_t)(nvary > 0 ? nvary : 0),
+                                                             results ? results + lo * rows : NULL, status ? status + lo : NULL, 0);
+      });
+    }
+    for (auto &w : workers) w.join();
+    for (int k = 0; k < ndevices; k++) if (!done[(size_t)k]) ok = 0;
+  }
+  for (int k = 0; k < ndevices; k++) if (plans[(size_t)k]) ODESBatch_free(plans[(size_t)k]);
+  return ok ? ndevices : 0;
+}
+
 /* one-shot drop-in for the reference's batch loop */
 extern "C" int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
                                                  const double *values, double *out, int *status)
@@ -784,15 +821,12 @@ extern "C" int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int n
   if (!ii || nsets < 0) return -1;
   std::vector<int> idx;
   for (int j = 0; j < nvary; j++) idx.push_back(vi[j]->index);
-  odesBatch_t *b = ODESBatch_create(ii->om, ii->opt, nvary, idx.data(), 0, NULL, 0);
-  if (!b) return -1;
   int failed = -1;
-  std::vector<int> st((size_t)nsets);
-  if (ODESBatch_runHost(b, nsets, values, out, st.data(), 0)) {       /* out is already [nsets][nout+1][nvalues] */
+  std::vector<int> st((size_t)(nsets > 0 ? nsets : 1));
+  if (ODESBatch_runHostAllDevices(ii->om, ii->opt, nvary, idx.data(), 0, NULL, nsets, values, out, st.data(), 0)) {       /* out is already [nsets][nout+1][nvalues] */
     failed = 0;
     for (int s = 0; s < nsets; s++) { if (st[(size_t)s] < 0) failed++; if (status) status[s] = st[(size_t)s]; }
   }
-  ODESBatch_free(b);
   return failed;
 }
 

@@ -126,7 +126,7 @@ double BatchResults_getValue(const batchResults_t *r, int set, const char *name,
    the scanned kinetic-law parameters are still globalised (their names appear in the kinetic laws) */
 static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varySettings_t *vs, SBMLResultsArray_t **mapped)
 {
-  int i, j, nvalues, *idx; odeModel_t *om; batchResults_t *res = NULL; odesBatch_t *plan = NULL; double *rows;
+  int i, j, nvalues, *idx; odeModel_t *om; batchResults_t *res = NULL; double *rows;
   for (i = 0; i < vs->nrparams; i++) if (vs->rid[i] && strlen(vs->rid[i]) > 0) Model_globalizeParameter(m, vs->id[i], vs->rid[i]);
   om = ODEModel_create(m);
   if (om) {
@@ -140,8 +140,7 @@ static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varyS
       } else idx[j] = ODEModel_getVariableIndexFields(om, vs->id[j]);
       if (idx[j] < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_SYMBOL_IS_NOT_IN_MODEL, "Symbol %s is not in the model", vs->id[j]); free(idx); idx = NULL; break; }
     }
-    if (idx) plan = ODESBatch_create(om, set, vs->nrparams, idx, 0, NULL, 0);
-    if (plan) {
+    if (idx) {
       nvalues = ODEModel_getNumValues(om);
       rows = (double *)malloc((size_t)vs->nrdesignpoints * (size_t)(vs->nrparams > 0 ? vs->nrparams : 1) * sizeof(double));
       for (i = 0; i < vs->nrdesignpoints; i++) for (j = 0; j < vs->nrparams; j++) rows[(size_t)i * (size_t)vs->nrparams + (size_t)j] = vs->params[i][j];
@@ -153,9 +152,9 @@ static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varyS
       for (i = 0; i < res->nout; i++) res->time[i] = set->TimePoints[i];
       res->value = (double *)malloc((size_t)res->nout * (size_t)nvalues * (size_t)res->nsets * sizeof(double));
       res->status = (int *)calloc((size_t)(res->nsets > 0 ? res->nsets : 1), sizeof(int));
-      if (!ODESBatch_runHost(plan, res->nsets, rows, res->value, res->status, 0)) { BatchResults_free(res); res = NULL; }
+      /* all design points in one batched run, spread over the GPUs of the box when there are enough of them */
+      if (!ODESBatch_runHostAllDevices(om, set, vs->nrparams, idx, 0, NULL, res->nsets, rows, res->value, res->status, 0)) { BatchResults_free(res); res = NULL; }
       free(rows);
-      ODESBatch_free(plan);
       if (res && mapped) *mapped = SBMLResultsArray_fromBatch(m, om, res);
     }
     free(idx);

@@ -296,3 +296,28 @@ def test_steady_state_halt_on_gpu(monkeypatch, warp):
     want = np.transpose(ref["out"], (1, 2, 0))
     assert (st == 0).all() and np.isnan(want[-1, 0, :]).mean() > 0.5        # most sets settle inside the grid
     assert np.array_equal(out, want, equal_nan=True)
+
+
+def test_all_devices_entry_matches_one_device():
+    """ODESBatch_runHostAllDevices: the batch split by index range over every GPU of the box (one plan + one host thread
+    per device, no collective) returns what one device returns, bit for bit.  On a one-GPU box it degenerates to one range."""
+    L = so.lib()
+    w = H.workload("mapk", nout=10)
+    m = w["model"]
+    n = 6000
+    vals = np.ascontiguousarray(H.workload_values(w, n, seed=21))
+    vary = np.asarray(w["vary"], dtype=np.int32)
+    store = np.arange(m.neq, dtype=np.int32)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(store))
+    b.set_values(vals)
+    b.integrate(n)
+    direct = np.transpose(b.results(n), (2, 0, 1)).copy()
+    b.close()
+    ndev = L.ODES_deviceCount()
+    for want in sorted({1, min(2, ndev), ndev}):
+        res = np.full((n, 11, m.neq), -1.0)
+        st = np.full(n, -1, dtype=np.int32)
+        used = L.ODESBatch_runHostAllDevices(m.om, w["opt"], len(vary), vary.ctypes.data, len(store), store.ctypes.data, n,
+                                             vals.ctypes.data, res.ctypes.data, st.ctypes.data, want)
+        assert used == want, so.errors()
+        assert (st == 0).all() and np.array_equal(res, direct)
