@@ -321,3 +321,26 @@ def test_all_devices_entry_matches_one_device():
                                              vals.ctypes.data, res.ctypes.data, st.ctypes.data, want)
         assert used == want, so.errors()
         assert (st == 0).all() and np.array_equal(res, direct)
+
+
+@pytest.mark.parametrize("warp", [0, 1])
+def test_edge_sizes_through_the_host_entries(monkeypatch, warp):
+    """Empty, single and ragged batches through ODESBatch_runHost and ODESBatch_runHostAllDevices, both layouts."""
+    monkeypatch.setenv("ODES_WARP", str(warp))
+    L = so.lib()
+    w = H.workload("mapk", nout=8)
+    m = w["model"]
+    vals = np.ascontiguousarray(H.workload_values(w, 70, seed=31))
+    vary = np.asarray(w["vary"], dtype=np.int32)
+    ref = np.transpose(_oracle(w, vals)["out"], (0, 1, 2))            # [set][row][value]
+    b = so.Batch(m, w["opt"], w["vary"])
+    for n in (0, 1, 33, 70):
+        res = np.full((max(n, 1), 9, m.nvalues), -1.0)
+        st = np.full(max(n, 1), -1, dtype=np.int32)
+        b.run_host(vals[:n], res, st, chunk=0)
+        assert np.array_equal(res[:n], ref[:n]) and (st[:n] == 0).all(), n
+        res[:] = -1.0
+        st[:] = -1
+        used = L.ODESBatch_runHostAllDevices(m.om, w["opt"], len(vary), vary.ctypes.data, 0, None, n, vals.ctypes.data, res.ctypes.data, st.ctypes.data, 1)
+        assert used == 1 and np.array_equal(res[:n], ref[:n]) and (st[:n] == 0).all(), n
+    b.close()
