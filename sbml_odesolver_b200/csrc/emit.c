@@ -57,6 +57,9 @@ static void cbprintf(charBuffer_t *c, const char *fmt, ...)
 }
 
 /* --------------------------------------------------------- expressions */
+/* the time symbol: currenttime is a FLOAT in the reference (src/sbmlsolver/cvodeData.h:116; set from t in f, JacODE and
+   updateData, src/cvodeSolver.c:964, :1068), so a formula sees t rounded to 24 bits */
+#define REF_TIME "((double)(float)t)"
 typedef struct emit_ctx {
   int cuda;                       /* 1: device flavour with exact-case strength reduction */
   int interp;                     /* 1: output-time code (rules, events, stored rows): the reference evaluates these with
@@ -259,7 +262,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
 static void name_value(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "value[%d]", idx); }
 void generateAST(charBuffer_t *s, const ASTNode_t *node)
 {
-  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL; c.leaf = NULL;
+  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = REF_TIME; c.info = NULL; c.leaf = NULL;
   gen(s, node, &c);
 }
 
@@ -294,7 +297,7 @@ char *ODEModel_generateCSource(odeModel_t *om)
 {
   charBuffer_t *b = CharBuffer_create();
   emit_ctx_t c; int i; char *out;
-  c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "t"; c.info = NULL; c.leaf = NULL;
+  c.cuda = 0; c.interp = 0; c.name = name_value; c.time = REF_TIME; c.info = NULL; c.leaf = NULL;
   if (!om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   CharBuffer_append(b, "/* generated by ODEModel_generateCSource: the reference's compiled mode (ode_f, jacobi_f) */\n#include <math.h>\n#define DEV static inline\n#define ODES_POW pow\n");
   generateMacros(b);
@@ -624,7 +627,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   for (i = 0; i < om->nassbeforeodes; i++) { ode_local[om->assignmentsBeforeODEs[i]->i] = 1; mark_refs(om->assignmentsBeforeODEs[i]->ij, used_in_ode); }
   for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) k.slot[i] = npv++; }
 
-  c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = "t"; c.info = &k; c.leaf = NULL;
+  c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = REF_TIME; c.info = &k; c.leaf = NULL;
 
   cbprintf(b, "/* generated by ODEModel_generateCUDASource for model '%s' (sm_100a device functions) */\n",
            om->simple && om->simple->id ? om->simple->id : "odes");

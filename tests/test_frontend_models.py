@@ -148,3 +148,50 @@ def test_chain_models_emulated_kernel_vs_oracle(tmp_path, n):
         y3 = got["out"][1:, 2, :].ravel()
         assert (np.array([math.pow(v, 2.0) for v in y3]) != y3 * y3).any()
     b.close()
+
+
+TIME_MODEL = f'''<?xml version="1.0" encoding="UTF-8"?>
+<sbml xmlns="http://www.sbml.org/sbml/level2" level="2" version="1"><model id="forced">
+ <listOfCompartments><compartment id="c" size="1"/></listOfCompartments>
+ <listOfParameters><parameter id="x" value="0.5" constant="false"/><parameter id="w" value="0.7"/><parameter id="k" value="0.9"/>
+  <parameter id="drive" value="0" constant="false"/><parameter id="flag" value="0" constant="false"/></listOfParameters>
+ <listOfRules>
+  <assignmentRule variable="drive"><math {M}><apply><sin/><apply><times/><ci>w</ci><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol></apply></apply></math></assignmentRule>
+  <rateRule variable="x"><math {M}><apply><minus/><ci>drive</ci><apply><times/><ci>k</ci><ci>x</ci></apply></apply></math></rateRule>
+ </listOfRules>
+ <listOfEvents><event id="late"><trigger><math {M}><apply><gt/><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol><cn>3.3</cn></apply></math></trigger>
+  <listOfEventAssignments><eventAssignment variable="flag"><math {M}><cn>1</cn></math></eventAssignment></listOfEventAssignments></event></listOfEvents>
+</model></sbml>
+'''
+
+
+def test_time_dependent_model_sees_time_as_float(tmp_path):
+    """The reference keeps the current time in a float (src/sbmlsolver/cvodeData.h:116): formulas that mention time see
+    t rounded to 24 bits, in the right-hand side, in the rules of the stored rows and in event triggers (SURVEY
+    appendix A.3).  The emitted code does the same, so the kernel is bit-identical to the oracle driven with the emitted
+    C flavour and within tolerance of the interpreted oracle, with the event at the same output row."""
+    p = tmp_path / "forced.xml"
+    p.write_text(TIME_MODEL)
+    m = so.Model(str(p))
+    assert m.neq == 1 and m.names[0] == "x" and m.equation(0) == "drive - k * x"
+    vary = [m.index("w"), m.index("k"), m.index("x")]
+    rng = np.random.default_rng(8)
+    vals = np.stack([rng.uniform(0.3, 2.0, 10), rng.uniform(0.2, 3.0, 10), rng.uniform(-1, 1, 10)], axis=1)
+    opt = so.settings(7.0, 70, 1e-10, 1e-8)
+    b = so.Batch(m, opt, vary)
+    assert "(float)t" in b.source()
+    base, trig = b.base_values()
+    got = H.Emu(b, "forced").run(base, trig, vals, H.tpoints(opt, 70), 10000, 1e-8, 1e-10)
+    ref = H.oracle_run(m, opt, vary, vals, 70, compiled_so=H.compile_c_model(m, "forced"))
+    assert np.array_equal(got["stats"].T, ref["stats"]) and (got["status"] == 0).all()
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert [int(np.nonzero(f)[0][0]) for f in ref["fired"]] == [34] * 10          # time > 3.3 first holds at t = 3.4
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)))
+    refi = H.oracle_run(m, opt, vary, vals, 70)
+    assert np.array_equal(got["fired"].T, refi["fired"])
+    assert H.parity(got["out"], np.transpose(refi["out"], (1, 2, 0)), 1e-8, 1e-10) <= 1.0
+    # the stored rule value is sin(w * float(t)), not sin(w * t)
+    k = m.index("drive")
+    t = np.float32(0.1 * 33)
+    assert np.allclose(got["out"][33, k, :], np.sin(vals[:, 0] * float(t)), rtol=0, atol=1e-15)
+    b.close()
