@@ -157,7 +157,7 @@ TIME_MODEL = f'''<?xml version="1.0" encoding="UTF-8"?>
   <parameter id="drive" value="0" constant="false"/><parameter id="flag" value="0" constant="false"/></listOfParameters>
  <listOfRules>
   <assignmentRule variable="drive"><math {M}><apply><sin/><apply><times/><ci>w</ci><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol></apply></apply></math></assignmentRule>
-  <rateRule variable="x"><math {M}><apply><minus/><ci>drive</ci><apply><times/><ci>k</ci><ci>x</ci></apply></apply></math></rateRule>
+  <rateRule variable="x"><math {M}><apply><minus/><apply><plus/><cn>2</cn><ci>drive</ci></apply><apply><times/><ci>k</ci><ci>x</ci></apply></apply></math></rateRule>
  </listOfRules>
  <listOfEvents><event id="late"><trigger><math {M}><apply><gt/><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol><cn>3.3</cn></apply></math></trigger>
   <listOfEventAssignments><eventAssignment variable="flag"><math {M}><cn>1</cn></math></eventAssignment></listOfEventAssignments></event></listOfEvents>
@@ -173,10 +173,10 @@ def test_time_dependent_model_sees_time_as_float(tmp_path):
     p = tmp_path / "forced.xml"
     p.write_text(TIME_MODEL)
     m = so.Model(str(p))
-    assert m.neq == 1 and m.names[0] == "x" and m.equation(0) == "drive - k * x"
+    assert m.neq == 1 and m.names[0] == "x" and m.equation(0) == "2 + drive - k * x"
     vary = [m.index("w"), m.index("k"), m.index("x")]
     rng = np.random.default_rng(8)
-    vals = np.stack([rng.uniform(0.3, 2.0, 10), rng.uniform(0.2, 3.0, 10), rng.uniform(-1, 1, 10)], axis=1)
+    vals = np.stack([rng.uniform(0.3, 2.0, 10), rng.uniform(0.2, 3.0, 10), rng.uniform(0.5, 3, 10)], axis=1)
     opt = so.settings(7.0, 70, 1e-10, 1e-8)
     b = so.Batch(m, opt, vary)
     assert "(float)t" in b.source()

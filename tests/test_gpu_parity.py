@@ -355,13 +355,13 @@ def test_time_dependent_model_on_gpu(tmp_path):
     m = so.Model(str(p))
     vary = [m.index("w"), m.index("k"), m.index("x")]
     rng = np.random.default_rng(8)
-    vals = np.stack([rng.uniform(0.3, 2.0, 500), rng.uniform(0.2, 3.0, 500), rng.uniform(-1, 1, 500)], axis=1)
-    opt = so.settings(7.0, 70, 1e-10, 1e-8)
+    vals = np.stack([rng.uniform(0.3, 2.0, 500), rng.uniform(0.2, 3.0, 500), rng.uniform(0.5, 3, 500)], axis=1)
+    opt = so.settings(7.0, 70, 1e-9, 1e-6)
     b = so.Batch(m, opt, vary)
     b.set_values(vals)
     b.integrate(500)
     out, st, fired = b.results(500), b.status(500), b.event_log(500).T
     ref = H.oracle_run(m, opt, vary, vals, 70, compiled_so=H.compile_c_model(m, "forced"), threads=8)
     assert (st == 0).all() and np.array_equal(fired, ref["fired"])
-    assert H.parity(out, np.transpose(ref["out"], (1, 2, 0)), 1e-8, 1e-10) <= 1.0
+    assert H.parity(out, np.transpose(ref["out"], (1, 2, 0)), 1e-6, 1e-9) <= 1.0
     b.close()
