@@ -216,10 +216,10 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
   case AST_FUNCTION_COTH: gen_call(s, n, "odes_coth", c); break;
   case AST_FUNCTION_CSC: gen_call(s, n, "odes_csc", c); break;
   case AST_FUNCTION_CSCH: gen_call(s, n, "odes_csch", c); break;
-  case AST_FUNCTION_EXP: gen_call(s, n, "exp", c); break;
+  case AST_FUNCTION_EXP: gen_call(s, n, c->cuda ? "odes_exp" : "exp", c); break;      /* the host libm's exp, restated (glibc_pow.inc) */
   case AST_FUNCTION_FACTORIAL: gen_call(s, n, "odes_factorial", c); break;
   case AST_FUNCTION_FLOOR: gen_call(s, n, "floor", c); break;
-  case AST_FUNCTION_LN: gen_call(s, n, "log", c); break;
+  case AST_FUNCTION_LN: gen_call(s, n, c->cuda ? "odes_log" : "log", c); break;
   case AST_FUNCTION_LOG: gen_call(s, n, "odes_logbase", c); break;
   case AST_FUNCTION_PIECEWISE: gen_piecewise(s, n, c); break;
   case AST_FUNCTION_ROOT: gen_call(s, n, "odes_root", c); break;
@@ -641,7 +641,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
                        "struct PvRef { double *p; unsigned int s; DEV double &operator[](int k) const { return p[(size_t)k * s]; } };\n");
   CharBuffer_append(b, "__constant__ double c_base[A1(NVAL)];\n__constant__ int c_trigger0[A1(NEVENTS)];\n");
   /* pow as the host libm computes it (glibc_pow.inc, defined after this section) */
-  CharBuffer_append(b, "DEV double odes_pow(double x, double y);\n#define ODES_POW odes_pow\n");
+  CharBuffer_append(b, "DEV double odes_pow(double x, double y);\nDEV double odes_exp(double x);\nDEV double odes_log(double x);\n#define ODES_POW odes_pow\n");
   generateMacros(b);
   /* scatter of the saved sparse Jacobian into column j of M = -gamma*J (the kernel adds the +1 on the diagonal);
      j is warp-uniform at the call site, rows and non-zero indices are compile-time constants */

@@ -2,6 +2,8 @@
 assignments, rate and assignment rules, piecewise terms, stoichiometryMath, relational/logical operators and
 events go through the whole host chain -- reader, ODE construction, symbolic Jacobian, emitter -- and the emulated
 kernel must reproduce the oracle (same emitted right-hand side: bit for bit; interpreter: within tolerance)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -156,8 +158,8 @@ TIME_MODEL = f'''<?xml version="1.0" encoding="UTF-8"?>
  <listOfParameters><parameter id="x" value="0.5" constant="false"/><parameter id="w" value="0.7"/><parameter id="k" value="0.9"/>
   <parameter id="drive" value="0" constant="false"/><parameter id="flag" value="0" constant="false"/></listOfParameters>
  <listOfRules>
-  <assignmentRule variable="drive"><math {M}><apply><sin/><apply><times/><ci>w</ci><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol></apply></apply></math></assignmentRule>
-  <rateRule variable="x"><math {M}><apply><minus/><apply><plus/><cn>2</cn><ci>drive</ci></apply><apply><times/><ci>k</ci><ci>x</ci></apply></apply></math></rateRule>
+  <assignmentRule variable="drive"><math {M}><apply><exp/><apply><times/><apply><minus/><ci>w</ci></apply><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol></apply></apply></math></assignmentRule>
+  <rateRule variable="x"><math {M}><apply><minus/><apply><plus/><cn>2</cn><ci>drive</ci></apply><apply><times/><ci>k</ci><ci>x</ci><apply><ln/><apply><plus/><cn>2</cn><ci>x</ci></apply></apply></apply></apply></math></rateRule>
  </listOfRules>
  <listOfEvents><event id="late"><trigger><math {M}><apply><gt/><csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time">time</csymbol><cn>3.3</cn></apply></math></trigger>
   <listOfEventAssignments><eventAssignment variable="flag"><math {M}><cn>1</cn></math></eventAssignment></listOfEventAssignments></event></listOfEvents>
@@ -173,7 +175,7 @@ def test_time_dependent_model_sees_time_as_float(tmp_path):
     p = tmp_path / "forced.xml"
     p.write_text(TIME_MODEL)
     m = so.Model(str(p))
-    assert m.neq == 1 and m.names[0] == "x" and m.equation(0) == "2 + drive - k * x"
+    assert m.neq == 1 and m.names[0] == "x" and m.equation(0) == "2 + drive - k * x * log(2 + x)"
     vary = [m.index("w"), m.index("k"), m.index("x")]
     rng = np.random.default_rng(8)
     vals = np.stack([rng.uniform(0.3, 2.0, 10), rng.uniform(0.2, 3.0, 10), rng.uniform(0.5, 3, 10)], axis=1)
@@ -190,8 +192,8 @@ def test_time_dependent_model_sees_time_as_float(tmp_path):
     refi = H.oracle_run(m, opt, vary, vals, 70)
     assert np.array_equal(got["fired"].T, refi["fired"])
     assert H.parity(got["out"], np.transpose(refi["out"], (1, 2, 0)), 1e-8, 1e-10) <= 1.0
-    # the stored rule value is sin(w * float(t)), not sin(w * t)
+    # the stored rule value is exp(-w * float(t)), not exp(-w * t)
     k = m.index("drive")
     t = np.float32(0.1 * 33)
-    assert np.allclose(got["out"][33, k, :], np.sin(vals[:, 0] * float(t)), rtol=0, atol=1e-15)
+    assert np.array_equal(got["out"][33, k, :], np.array([math.exp(-w * float(t)) for w in vals[:, 0]]))
     b.close()

@@ -18,6 +18,9 @@ SRC = r'''
 #include "%(root)s/sbml_odesolver_b200/csrc/glibc_pow_tables.h"
 #include "%(root)s/sbml_odesolver_b200/csrc/glibc_pow.inc"
 long check(const double *x, const double *y, long n) { long bad = 0; for (long i = 0; i < n; i++) if (odes_pow(x[i], y[i]) != pow(x[i], y[i])) bad++; return bad; }
+static int same(double a, double b) { return a == b || (a != a && b != b); }
+long check_exp(const double *x, long n) { long bad = 0; for (long i = 0; i < n; i++) if (!same(odes_exp(x[i]), exp(x[i]))) bad++; return bad; }
+long check_log(const double *x, long n) { long bad = 0; for (long i = 0; i < n; i++) if (!same(odes_log(x[i]), log(x[i]))) bad++; return bad; }
 '''
 
 
@@ -29,6 +32,8 @@ def _lib(tmp_path):
     lib = C.CDLL(str(so_))
     lib.check.restype = C.c_long
     lib.check.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    for f in (lib.check_exp, lib.check_log):
+        f.restype, f.argtypes = C.c_long, [C.c_void_p, C.c_long]
     return lib
 
 
@@ -52,6 +57,22 @@ def test_restated_pow_is_bit_identical_to_libm(tmp_path):
     x = np.array([0.0, -2.0, 1.0, 1e-320, 1e305, 2.0, 2.0, np.inf, 3.0])
     y = np.array([0.5, 3.0, 1e300, 0.5, 2.0, 0.0, 1e-20, 0.5, np.nan])
     assert lib.check(x.ctypes.data, y.ctypes.data, len(x)) <= 1          # the NaN exponent compares unequal to itself
+
+
+def test_restated_exp_and_log_are_bit_identical_to_libm(tmp_path):
+    """exp and ln of model expressions (odes_exp, odes_log): the host libm's values on the main paths, the device
+    library outside them (on the host both sides are libm then)."""
+    lib = _lib(tmp_path)
+    rng = np.random.default_rng(6)
+    n = 2_000_000
+    for x in (rng.uniform(-700, 700, n), rng.uniform(-5, 5, n), rng.uniform(-1e-3, 1e-3, n), rng.uniform(-1e-17, 1e-17, n),
+              np.array([0.0, -0.0, 1e-320, 709.0, 710.0, -745.0, -746.0, np.inf, -np.inf, np.nan, 511.9999, 512.0])):
+        x = np.ascontiguousarray(x)
+        assert lib.check_exp(x.ctypes.data, len(x)) == 0
+    for x in (np.power(10.0, rng.uniform(-300, 300, n)), rng.uniform(0.9, 1.1, n), rng.uniform(0.9375, 1.0647, n), 1 + rng.uniform(-1e-9, 1e-9, n),
+              np.array([1.0, 0.0, -0.0, -1.0, 5e-324, 1e-310, np.inf, np.nan, 0.9375, 1.064697265625, 2.0, 0.5])):
+        x = np.ascontiguousarray(x)
+        assert lib.check_log(x.ctypes.data, len(x)) == 0
 
 
 def test_tables_header_matches_this_libm():
