@@ -126,10 +126,10 @@ def chain_model_xml(n):
             f'<listOfParameters>{pars}</listOfParameters><listOfReactions>{"".join(rx)}</listOfReactions></model></sbml>')
 
 
-@pytest.mark.parametrize("n", [3, 12, 17, 20])
+@pytest.mark.parametrize("n", [3, 12, 17, 20, 32])
 def test_chain_models_emulated_kernel_vs_oracle(tmp_path, n):
     """State dimensions around the storage thresholds: one and two 8-row chunks per matrix column, packed and
-    array pivots (n > 16); n = 20 takes the warp-per-trajectory layout.  n = 3 runs enough sets to meet arguments where libm's pow(x, 2) is not x * x rounded
+    array pivots (n > 16); n = 20 and n = 32 (every lane owns a row) take the warp-per-trajectory layout.  n = 3 runs enough sets to meet arguments where libm's pow(x, 2) is not x * x rounded
     (about 3e-4 of the calls): stored assignment-rule values follow the interpreter (pow), the ODEs the compiled x * x."""
     p = tmp_path / f"chain{n}.xml"
     p.write_text(chain_model_xml(n))

@@ -202,10 +202,11 @@ def test_feature_model_on_gpu(tmp_path):
     b.close()
 
 
-@pytest.mark.parametrize("n", [3, 12, 17, 20])
+@pytest.mark.parametrize("n", [3, 12, 17, 20, 32, 40])
 def test_chain_models_on_gpu(tmp_path, n):
     """n = 3 and 12 use tensor memory with one and two chunks per matrix column (12: all 512 columns of one block per
-    SM), n = 17 falls back to the global scratch, n = 20 takes the warp-per-trajectory layout: all bit-identical to the oracle."""
+    SM), n = 17 falls back to the global scratch, n = 20 and 32 take the warp-per-trajectory layout, n = 40 (beyond a warp) the lane layout with the global scratch: all
+    bit-identical to the oracle."""
     from test_frontend_models import chain_model_xml
     p = tmp_path / f"chain{n}.xml"
     p.write_text(chain_model_xml(n))
