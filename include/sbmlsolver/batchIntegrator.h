@@ -86,6 +86,15 @@ int ODESBatch_getTrajectory(odesBatch_t *, int set, double *traj /* [nout+1][nst
 int ODESBatch_getStatus(odesBatch_t *, int nsets, int *status);
 int ODESBatch_getStats(odesBatch_t *, int nsets, int *stats /* [ODES_NUM_STATS][nsets] */);
 int ODESBatch_getEventLog(odesBatch_t *, int nsets, unsigned int *fired /* [nout+1][nsets] bitmasks */);
+/* forward sensitivities (plans created with opt->Sensitivity = 1; parameters from CvodeSettings_setSensParams, default
+   all constants): what the reference keeps in cvodeResults_t.sensitivity[i][j][k] (src/cvodeData.c:555-567, filled by
+   IntegratorInstance_getForwardSens, src/sensSolver.c:108-140), here sens[set][k][j][i] = d y_i(t_k) / d p_j.
+   Rows not reached are not-a-number like the state rows. */
+int ODESBatch_getNsens(const odesBatch_t *);
+int ODESBatch_getSensIndex(const odesBatch_t *, int is);     /* value[] index of sensitivity parameter `is` */
+int ODESBatch_getSensitivities(odesBatch_t *, int nsets, double *sens /* [nsets][nout+1][nsens][neq] */);
+double *ODESBatch_deviceSensitivities(odesBatch_t *);
+
 /* end-to-end helper with host buffers (values [nsets][nvary] in, results [nsets][nout+1][nstore] and status out).
    chunk >= 0: launches of `chunk` sets (0: up to 2^22), the results of finished groups of sets are copied back while
    the kernel runs; chunk < 0: launches of -chunk sets, the copy of launch k-1 overlaps launch k */

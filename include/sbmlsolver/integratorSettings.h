@@ -1,7 +1,7 @@
 /*
  * integratorSettings.h -- cvodeSettings_t, field-for-field the reference's
- * src/sbmlsolver/integratorSettings.h:56-148 for the forward path (adjoint and
- * sensitivity switches are kept as inert fields so callers compile).
+ * src/sbmlsolver/integratorSettings.h:56-148 for the forward path (forward
+ * sensitivities, simultaneous corrector, are honoured by the batched kernel; the adjoint switches are inert fields).
  * Functions: reference integratorSettings.h:172-245.
  */
 #ifndef ODES_B200_INTEGRATORSETTINGS_H
@@ -50,6 +50,10 @@ void CvodeSettings_setSteadyStateThreshold(cvodeSettings_t *, double);
 void CvodeSettings_setStoreResults(cvodeSettings_t *, int);
 void CvodeSettings_setSensitivity(cvodeSettings_t *, int);
 void CvodeSettings_setSensMethod(cvodeSettings_t *, int);
+/* reference src/integratorSettings.c:877-908: ids of the parameters / variables whose sensitivities are wanted;
+   NULL selects the default (all constants of the model) */
+int CvodeSettings_setSensParams(cvodeSettings_t *, char **sensIDs, int nsens);
+void CvodeSettings_unsetSensParams(cvodeSettings_t *);
 void CvodeSettings_dump(cvodeSettings_t *);
 void CvodeSettings_free(cvodeSettings_t *);
 cvodeSettings_t *CvodeSettings_clone(cvodeSettings_t *);

@@ -18,6 +18,7 @@ extern "C" {
 
 typedef struct odeModel odeModel_t;
 typedef struct nonzeroElem nonzeroElem_t;
+typedef struct odeSense odeSense_t;
 typedef struct variableIndex variableIndex_t;
 typedef struct compiled_code compiled_code_t;
 
@@ -53,6 +54,20 @@ struct odeModel {
   void *kernelCache;
   /* kept for source compatibility with callers that test these flags */
   int discrete_observation_data; int compute_vector_v;
+};
+
+/* reference src/sbmlsolver/odeModel.h:214-247: the forward-sensitivity structures derived from an odeModel_t.
+   sens[i][l] = d(ode_i)/d(parameter l) with the assignment rules inlined, differentiated, simplified and indexed
+   (src/odeModel.c:1963-2100); variables (initial-condition sensitivities) have index_sensP == -1 and no column. */
+struct odeSense {
+  odeModel_t *om;
+  int neq, nsens;
+  int *index_sens;          /* [nsens] index into names[] / value[] */
+  int nsensP; int *index_sensP;   /* [nsens] column of sens[][] or -1 */
+  ASTNode_t ***sens;        /* [neq][nsensP] */
+  int sensitivity;          /* 1: matrix constructed */
+  int **sensLogic;          /* [neq][nsensP] structurally non-zero */
+  nonzeroElem_t **sensSparse; int sparsesize;
 };
 
 /* construction */
@@ -120,6 +135,16 @@ void ODEModel_freeJacobian(odeModel_t *);
 const ASTNode_t *ODEModel_getJacobianIJEntry(const odeModel_t *, int i, int j);
 const ASTNode_t *ODEModel_getJacobianEntry(const odeModel_t *, const variableIndex_t *, const variableIndex_t *);
 
+/* forward sensitivities (reference odeModel.h:346-353) */
+odeSense_t *ODEModel_constructSensitivity(odeModel_t *);
+odeSense_t *ODESense_create(odeModel_t *, cvodeSettings_t *);
+void ODESense_free(odeSense_t *);
+variableIndex_t *ODESense_getSensParamIndexByNum(const odeSense_t *, int);
+int ODESense_getNeq(const odeSense_t *);
+int ODESense_getNsens(const odeSense_t *);
+const ASTNode_t *ODESense_getSensIJEntry(const odeSense_t *, int i, int j);
+const ASTNode_t *ODESense_getSensEntry(const odeSense_t *, const variableIndex_t *, const variableIndex_t *);
+
 /* code generation seam (reference: src/processAST.c:2057-2311 generateAST/generateMacros,
    src/odeModel.c:2600-2918 function generators, src/compiler.c:428-509 Compiler_*) */
 typedef struct charBuffer charBuffer_t;
@@ -137,9 +162,14 @@ void generateMacros(charBuffer_t *buffer);
    are per-trajectory inputs (everything else is uniform).  Caller frees. */
 char *ODEModel_generateCUDASource(odeModel_t *, const cvodeSettings_t *, int nvary, const int *vary,
                                   int nstore, const int *store, const double *base /* values after reset, or NULL */);
+/* the same with the forward-sensitivity right-hand side (os may be NULL) */
+char *ODEModel_generateCUDASourceSens(odeModel_t *, const cvodeSettings_t *, int nvary, const int *vary,
+                                      int nstore, const int *store, const double *base, const odeSense_t *os);
 /* Host-C flavour of the same generated functions (the reference's compiled mode), used by
    tests and by the CPU baseline harness.  Caller frees. */
 char *ODEModel_generateCSource(odeModel_t *);
+/* ... plus sense_f (reference src/odeModel.c:2994-3100) when os is given */
+char *ODEModel_generateCSourceSens(odeModel_t *, const odeSense_t *os);
 
 compiled_code_t *Compiler_compile(const char *sourceCode);
 void *CompiledCode_getFunction(compiled_code_t *, const char *symbol);

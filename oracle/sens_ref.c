@@ -1,0 +1,164 @@
+/*
+ * sens_ref.c -- ORACLE (test infrastructure, not product code).
+ *
+ * Forward sensitivity analysis with the reference's vendored, UNMODIFIED SUNDIALS 2.1.1 CVODES 2.3.0 (compiled from
+ * /root/reference/Win32/WinCVODE/sundials/cvodes where the sources lie, see oracle/Makefile) set up the way the
+ * reference sets it up:
+ *   src/sensSolver.c:197-346   simultaneous corrector (SensMethod 0), analytic sensitivity right-hand side, one
+ *                              sensitivity at a time (CVodeSensInit1 / CVSensRhs1Fn), CVodeSetSensParams(p, NULL, NULL),
+ *                              estimated tolerances (CV_EE), CVodeSetSensErrCon(FALSE)
+ *   src/cvodeSolver.c:412-703  BDF + Newton, scalar rtol, vector atol of equal entries, CVDense + analytic Jacobian
+ *   src/sensSolver.c:108-140   CVodeGetSens at the output time after every CVode call
+ *   src/cvodeData.c:453-461    initial sensitivities: 1 for a variable with respect to its own initial value, else 0
+ *   src/odeSolver.c:313-330    the design-point loop: reset, setVariableValue x nvary, integrate
+ * The model functions are the emitted host-C flavour (ODEModel_generateCSourceSens: ode_f, jacobi_f, sense_f = the
+ * reference's compiled mode, src/odeModel.c:2673-2918, :2994-3100) loaded from a shared object.
+ * There is no restated port behind this file: for the sensitivity row of SURVEY section 8(f) the checker is the
+ * reference's own CVODES arithmetic.  Models with events are not handled here.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "cvodes.h"
+#include "cvdense.h"
+#include "nvector_serial.h"
+
+typedef void (*c_ode_fn)(double t, const double *y, double *ydot, double *value);
+typedef void (*c_jac_fn)(double t, const double *y, double *J, double *value);
+typedef void (*c_sens_fn)(int iS, double t, const double *y, const double *yS, double *ySdot, double *value);
+
+typedef struct { int neq; double *value; c_ode_fn f; c_jac_fn j; c_sens_fn s; } ctx_t;
+
+static void f_cb(realtype t, N_Vector y, N_Vector ydot, void *f_data)
+{ ctx_t *c = (ctx_t *)f_data; c->f(t, NV_DATA_S(y), NV_DATA_S(ydot), c->value); }
+static void jac_cb(long int N, DenseMat J, realtype t, N_Vector y, N_Vector fy, void *jac_data, N_Vector t1, N_Vector t2, N_Vector t3)
+{ ctx_t *c = (ctx_t *)jac_data; (void)N; (void)fy; (void)t1; (void)t2; (void)t3; c->j(t, NV_DATA_S(y), J->data[0], c->value); }
+static void fs_cb(int Ns, realtype t, N_Vector y, N_Vector ydot, int iS, N_Vector yS, N_Vector ySdot, void *fS_data, N_Vector t1, N_Vector t2)
+{ ctx_t *c = (ctx_t *)fS_data; (void)Ns; (void)ydot; (void)t1; (void)t2; c->s(iS, t, NV_DATA_S(y), NV_DATA_S(yS), NV_DATA_S(ySdot), c->value); }
+
+typedef struct {
+  int first, last, neq, nvalues, nsens, nvary, nout; long mxstep;
+  const int *vary_idx, *sens_variable; const double *values, *base, *tpoints;
+  double rtol, atol;
+  double *out, *sens; int *status, *stats;
+  c_ode_fn f; c_jac_fn j; c_sens_fn s;
+  int failed;
+} job_t;
+
+static void *run_range(void *arg)
+{
+  job_t *jb = (job_t *)arg;
+  int neq = jb->neq, ns = jb->nsens, nout = jb->nout, s, i, k, is;
+  ctx_t ctx; void *mem = NULL; int created = 0;
+  N_Vector y = N_VNew_Serial(neq), abstol = N_VNew_Serial(neq);
+  N_Vector *yS = N_VNewVectorArray_Serial(ns, neq);
+  double *p = (double *)calloc((size_t)ns, sizeof(double));
+  ctx.neq = neq; ctx.value = (double *)malloc((size_t)jb->nvalues * sizeof(double)); ctx.f = jb->f; ctx.j = jb->j; ctx.s = jb->s;
+
+  for (s = jb->first; s < jb->last; s++) {
+    double t = jb->tpoints[0]; int flag = 0, iout;
+    double *rows = jb->out + (size_t)s * (size_t)(nout + 1) * (size_t)neq;
+    double *srows = jb->sens + (size_t)s * (size_t)(nout + 1) * (size_t)ns * (size_t)neq;
+    memcpy(ctx.value, jb->base, (size_t)jb->nvalues * sizeof(double));
+    for (k = 0; k < jb->nvary; k++) ctx.value[jb->vary_idx[k]] = jb->values[(size_t)s * (size_t)jb->nvary + (size_t)k];
+    for (i = 0; i < neq; i++) { NV_Ith_S(y, i) = ctx.value[i]; NV_Ith_S(abstol, i) = jb->atol; rows[i] = ctx.value[i]; }
+    for (is = 0; is < ns; is++) for (i = 0; i < neq; i++) {
+      NV_Ith_S(yS[is], i) = (jb->sens_variable[is] == i) ? 1.0 : 0.0;
+      srows[(size_t)is * (size_t)neq + (size_t)i] = NV_Ith_S(yS[is], i);
+    }
+    if (!created) {
+      mem = CVodeCreate(CV_BDF, CV_NEWTON);
+      CVodeSetErrFile(mem, NULL);
+      flag = CVodeMalloc(mem, f_cb, t, y, CV_SV, jb->rtol, abstol);
+      if (flag == CV_SUCCESS) flag = CVodeSensMalloc(mem, ns, CV_SIMULTANEOUS, yS);
+      created = 1;
+    } else {
+      flag = CVodeReInit(mem, f_cb, t, y, CV_SV, jb->rtol, abstol);
+      if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, CV_SIMULTANEOUS, yS);
+    }
+    if (flag == CV_SUCCESS) {
+      CVodeSetFdata(mem, &ctx);
+      CVodeSetMaxNumSteps(mem, jb->mxstep);
+      CVDense(mem, neq);
+      CVDenseSetJacFn(mem, jac_cb, &ctx);
+      CVodeSetSensRhs1Fn(mem, fs_cb);
+      CVodeSetSensFdata(mem, &ctx);
+      CVodeSetSensParams(mem, p, NULL, NULL);
+      CVodeSetSensTolerances(mem, CV_EE, 0.0, NULL);
+      CVodeSetSensErrCon(mem, FALSE);
+    }
+    jb->status[s] = 0;
+    iout = 1;
+    if (flag == CV_SUCCESS) {
+      for (; iout <= nout; iout++) {
+        realtype tret = 0;
+        flag = CVode(mem, jb->tpoints[iout], y, &tret, CV_NORMAL);
+        if (flag < 0) break;
+        flag = CVodeGetSens(mem, tret, yS);
+        if (flag < 0) break;
+        for (i = 0; i < neq; i++) rows[(size_t)iout * (size_t)neq + (size_t)i] = NV_Ith_S(y, i);
+        for (is = 0; is < ns; is++) for (i = 0; i < neq; i++)
+          srows[((size_t)iout * (size_t)ns + (size_t)is) * (size_t)neq + (size_t)i] = NV_Ith_S(yS[is], i);
+      }
+    }
+    if (flag < 0) {
+      jb->status[s] = flag; jb->failed++;
+      for (; iout <= nout; iout++) {
+        for (i = 0; i < neq; i++) rows[(size_t)iout * (size_t)neq + (size_t)i] = NAN;
+        for (i = 0; i < ns * neq; i++) srows[(size_t)iout * (size_t)ns * (size_t)neq + (size_t)i] = NAN;
+      }
+    }
+    if (jb->stats && mem) {
+      long v = 0; int *st = jb->stats + (size_t)s * 8;
+      CVodeGetNumSteps(mem, &v); st[0] = (int)v;
+      CVodeGetNumRhsEvals(mem, &v); st[1] = (int)v;
+      CVodeGetNumLinSolvSetups(mem, &v); st[2] = (int)v;
+      CVDenseGetNumJacEvals(mem, &v); st[3] = (int)v;
+      CVodeGetNumNonlinSolvIters(mem, &v); st[4] = (int)v;
+      CVodeGetNumNonlinSolvConvFails(mem, &v); st[5] = (int)v;
+      CVodeGetNumErrTestFails(mem, &v); st[6] = (int)v;
+      CVodeGetNumSensRhsEvals(mem, &v); st[7] = (int)v;
+    }
+  }
+  if (mem) CVodeFree(mem);
+  N_VDestroy_Serial(y); N_VDestroy_Serial(abstol); N_VDestroyVectorArray_Serial(yS, ns);
+  free(ctx.value); free(p);
+  return NULL;
+}
+
+/* out [nsets][nout+1][neq], sens [nsets][nout+1][nsens][neq], status [nsets], stats [nsets][8] (nst, nfe, nsetups, nje,
+   nni, ncfn, netf, nfSe) or NULL.  sens_variable[is]: equation index of an initial-condition sensitivity, or -1.
+   Returns the number of failed sets, -1 on a set-up error. */
+int refcvs_integrate_batch(const char *compiled_so, int neq, int nvalues, int nsens, const int *sens_variable,
+                           const double *base, int nsets, int nvary, const int *vary_idx, const double *values,
+                           const double *tpoints, int nout, double rtol, double atol, long mxstep,
+                           double *out, double *sens, int *status, int *stats, int nthreads)
+{
+  void *so = dlopen(compiled_so, RTLD_NOW | RTLD_LOCAL);
+  job_t *jobs; pthread_t *th; int k, failed = 0;
+  c_ode_fn f; c_jac_fn j; c_sens_fn s;
+  if (!so) return -1;
+  f = (c_ode_fn)dlsym(so, "ode_f"); j = (c_jac_fn)dlsym(so, "jacobi_f"); s = (c_sens_fn)dlsym(so, "sense_f");
+  if (!f || !j || !s) { dlclose(so); return -1; }
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > nsets) nthreads = nsets > 0 ? nsets : 1;
+  jobs = (job_t *)calloc((size_t)nthreads, sizeof *jobs);
+  th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+  for (k = 0; k < nthreads; k++) {
+    job_t *jb = &jobs[k];
+    jb->first = (int)((long long)nsets * k / nthreads); jb->last = (int)((long long)nsets * (k + 1) / nthreads);
+    jb->neq = neq; jb->nvalues = nvalues; jb->nsens = nsens; jb->nvary = nvary; jb->nout = nout; jb->mxstep = mxstep;
+    jb->vary_idx = vary_idx; jb->sens_variable = sens_variable; jb->values = values; jb->base = base; jb->tpoints = tpoints;
+    jb->rtol = rtol; jb->atol = atol; jb->out = out; jb->sens = sens; jb->status = status; jb->stats = stats;
+    jb->f = f; jb->j = j; jb->s = s;
+    if (nthreads == 1) run_range(jb); else pthread_create(&th[k], NULL, run_range, jb);
+  }
+  for (k = 0; k < nthreads; k++) { if (nthreads > 1) pthread_join(th[k], NULL); failed += jobs[k].failed; }
+  free(jobs); free(th);
+  dlclose(so);
+  return failed;
+}

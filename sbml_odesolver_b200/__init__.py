@@ -42,7 +42,15 @@ _SIGS = {
     "ODEModel_getOde": (c_p, [c_p, c_p]), "ODEModel_getAssignment": (c_p, [c_p, c_p]),
     "ODEModel_constructJacobian": (c_i, [c_p]), "ODEModel_getJacobiElement": (c_p, [c_p, c_i]),
     "ODEModel_getJacobianIJEntry": (c_p, [c_p, c_i, c_i]),
-    "ODEModel_generateCSource": (c_p, [c_p]),
+    "ODEModel_generateCSource": (c_p, [c_p]), "ODEModel_generateCSourceSens": (c_p, [c_p, c_p]),
+    "ODESense_create": (c_p, [c_p, c_p]), "ODESense_free": (None, [c_p]), "ODESense_getNsens": (c_i, [c_p]), "ODESense_getNeq": (c_i, [c_p]),
+    "ODESense_getSensIJEntry": (c_p, [c_p, c_i, c_i]), "ODESense_getSensParamIndexByNum": (c_p, [c_p, c_i]),
+    "ODEModel_constructSensitivity": (c_p, [c_p]),
+    "CvodeSettings_setSensParams": (c_i, [c_p, c_p, c_i]), "CvodeSettings_unsetSensParams": (None, [c_p]),
+    "CvodeSettings_setSensitivity": (None, [c_p, c_i]), "CvodeSettings_setSensMethod": (None, [c_p, c_i]),
+    "CvodeSettings_getSensitivity": (c_i, [c_p]),
+    "ODESBatch_getNsens": (c_i, [c_p]), "ODESBatch_getSensIndex": (c_i, [c_p, c_i]), "ODESBatch_getSensitivities": (c_i, [c_p, c_i, c_p]),
+    "ODESBatch_deviceSensitivities": (c_p, [c_p]),
     "ODEModel_generateCUDASource": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p, c_p]),
     "CvodeSettings_create": (c_p, []), "CvodeSettings_createWithTime": (c_p, [c_d, c_i]),
     "CvodeSettings_createWith": (c_p, [c_d, c_i, c_d, c_d] + [c_i] * 10), "CvodeSettings_free": (None, [c_p]),
@@ -194,10 +202,16 @@ class Model:
         return out
 
 
-def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1, steady_state=0, ss_threshold=None):
-    """CvodeSettings_createWith(Time, PrintStep, Error, RError, Mxstep, Method=BDF, Iter=Newton, ...)."""
-    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, 0, 0, use_jacobian, 0, halt_on_event, steady_state, store_results, 0, 0)
+def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1, steady_state=0, ss_threshold=None,
+             sensitivity=0, sens_ids=None):
+    """CvodeSettings_createWith(Time, PrintStep, Error, RError, Mxstep, Method=BDF, Iter=Newton, ...).
+    sensitivity=1 switches forward sensitivity analysis on (simultaneous corrector); sens_ids: ids of the parameters /
+    variables (CvodeSettings_setSensParams), None = all constants of the model."""
+    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, 0, 0, use_jacobian, 0, halt_on_event, steady_state, store_results, sensitivity, 0)
     _check(opt, "CvodeSettings_createWith")
+    if sens_ids is not None:
+        arr = (c_s * len(sens_ids))(*[x.encode() for x in sens_ids])
+        lib().CvodeSettings_setSensParams(opt, arr, len(sens_ids))
     if ss_threshold is not None:
         lib().CvodeSettings_setSteadyStateThreshold(opt, ss_threshold)
     return opt
@@ -217,6 +231,13 @@ class Batch:
         _check(self.h, "ODESBatch_create")
         self.nrows = L.ODESBatch_getNout(self.h)
         self.nstore = L.ODESBatch_getNstore(self.h)
+        self.nsens = L.ODESBatch_getNsens(self.h)
+
+    def sensitivities(self, nsets):
+        """Forward sensitivities [set][row][sensitivity parameter][equation]."""
+        out = np.empty((nsets, self.nrows, self.nsens, self.model.neq))
+        _check(lib().ODESBatch_getSensitivities(self.h, nsets, out.ctypes.data), "ODESBatch_getSensitivities")
+        return out
 
     def source(self):
         return lib().ODESBatch_getSource(self.h).decode()

@@ -34,6 +34,7 @@ struct OdesArgs {
   const double *vary; double *out; int *status; int *stats; unsigned int *fired; const double *tpoints;
   unsigned long long *counter; double *scratch; unsigned long long stride; int nsets, nout, mxstep, pad; double reltol, abstol;
   unsigned int *groupDone; unsigned int *hostFlags; int groupShift, pad2;
+  double *sens;
 };
 
 /* --------------------------------------------------------------- driver API */
@@ -304,6 +305,7 @@ struct odesBatch {
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
   std::vector<double> base; std::vector<int> trigger0;
+  odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
 };
 
 /* values after CvodeData_initialize with the model's own parameters (uniform for the whole batch) */
@@ -328,6 +330,7 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
     cudaSetDevice(b->device);
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
     cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch); cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
+    cudaFree(b->d_sens);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copyIn) cudaStreamDestroy(b->copyIn);
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
@@ -338,12 +341,13 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
     for (int i = 0; i < 2; i++) { if (b->evIn[i]) cudaEventDestroy(b->evIn[i]); if (b->evK[i]) cudaEventDestroy(b->evK[i]); if (b->evOut[i]) cudaEventDestroy(b->evOut[i]); }
   }
   CompiledCode_free(b->code);
+  ODESense_free(b->os);
   delete b;
 }
 
 static std::string build_source(odesBatch_t *b)
 {
-  char *model = ODEModel_generateCUDASource(b->om, b->opt, b->nvary, b->vary.data(), b->nstore, b->store.data(), env_int("ODES_FOLD_CONSTANTS", 1) ? b->base.data() : NULL);
+  char *model = ODEModel_generateCUDASourceSens(b->om, b->opt, b->nvary, b->vary.data(), b->nstore, b->store.data(), env_int("ODES_FOLD_CONSTANTS", 1) ? b->base.data() : NULL, b->os);
   const int neq = b->om->neq;
   const int usejac = b->opt->UseJacobian && b->om->jacobian;
   int npv = 0;
@@ -366,13 +370,15 @@ static std::string build_source(odesBatch_t *b)
   /* crossover measured with tools/gpu_layout_crossover.py (chain models, 10^5 sets): n = 16 lane 1.09 M vs warp 0.69 M,
      n = 20 0.51 M vs 0.56 M, n = 24 0.26 M vs 0.48 M, n = 32 0.11 M vs 0.38 M trajectories/s; huang96 (n = 22) 82 k vs 174 k */
   if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
+  if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
   if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
   b->warpMode = warp;
   if (warp) {
     const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);
     b->laMode = 0; b->tmemCols = 0; b->block = 32 * wpb; b->matLocal = 0; b->smemBytes = 0;
     /* measured on huang96 (B200): 8 warps per SM 113 k, 12 warps 145 k, 16 warps (128 registers, spills) 136 k trajectories/s */
-    b->minblocks = env_int("ODES_MINBLOCKS", wpb == 4 ? 3 : 1); b->maxBlocksPerSM = 32;
+    /* with sensitivities a lane carries 10 more vector elements per sensitivity: fewer resident warps, more registers */
+    b->minblocks = env_int("ODES_MINBLOCKS", b->nsens > 0 ? (b->nsens <= 2 ? 2 : 1) : (wpb == 4 ? 3 : 1)); b->maxBlocksPerSM = 32;
     char headw[512];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
              env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
@@ -428,6 +434,23 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
   else { for (int j = 0; j < b->nvalues; j++) b->store.push_back(j); b->nstore = b->nvalues; }
   if (opt->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   if (!compute_base(om, opt, b->base, b->trigger0)) { delete b; return NULL; }
+  /* forward sensitivities (src/sensSolver.c:197-346): simultaneous corrector, analytic sense_f, no error control on the
+     sensitivity variables -- the reference's set-up; it needs the Jacobian and the parametric matrix */
+  b->os = NULL; b->nsens = 0; b->d_sens = NULL;
+  if (opt->Sensitivity) {
+    const char *why = NULL;
+    if (!(opt->UseJacobian && om->jacobian)) why = "forward sensitivities need the analytic Jacobian";
+    else if (opt->SensMethod != 0) why = "the batched kernel implements the simultaneous corrector (SensMethod 0) only";
+    else if (om->neq < 1 || om->neq > 32) why = "forward sensitivities are implemented for 1..32 equations (one trajectory per warp)";
+    else if (om->nevents > 0) why = "forward sensitivities with events are not supported by the batched kernel";
+    if (!why) {
+      b->os = ODESense_create(om, opt);
+      if (!b->os || !b->os->sensitivity) why = "the parametric matrix could not be constructed";
+      else if (b->os->nsens < 1 || b->os->nsens > 16) why = "between 1 and 16 sensitivity parameters are supported";
+    }
+    if (why) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "%s", why); ODESense_free(b->os); delete b; return NULL; }
+    b->nsens = b->os->nsens;
+  }
 
   /* code generation + compilation need no device (NVRTC targets sm_100a explicitly) */
   std::string src = build_source(b);
@@ -489,7 +512,7 @@ extern "C" int ODESBatch_reserve(odesBatch_t *b, int capacity)
   if (!ensure_loaded(b)) return 0;
   if (capacity <= b->capacity) return 1;
   capacity = (capacity + 31) & ~31;            /* rows start 256-byte aligned */
-  cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired);
+  cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_sens); b->d_sens = NULL;
   b->d_vary = b->d_out = NULL; b->d_status = b->d_stats = NULL; b->d_fired = NULL; b->capacity = 0;
   const size_t cap = (size_t)capacity;
   CUDA_OK(cudaMalloc(&b->d_vary, sizeof(double) * cap * (size_t)(b->nvary > 0 ? b->nvary : 1)));
@@ -497,6 +520,7 @@ extern "C" int ODESBatch_reserve(odesBatch_t *b, int capacity)
   CUDA_OK(cudaMalloc(&b->d_status, sizeof(int) * cap));
   CUDA_OK(cudaMalloc(&b->d_stats, sizeof(int) * cap * ODES_NUM_STATS));
   CUDA_OK(cudaMalloc(&b->d_fired, sizeof(unsigned int) * cap * (size_t)(b->opt->PrintStep + 1)));
+  if (b->nsens > 0) CUDA_OK(cudaMalloc(&b->d_sens, sizeof(double) * cap * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nsens * (size_t)b->om->neq));
   b->capacity = capacity;
   return 1;
 }
@@ -527,6 +551,19 @@ extern "C" void ODESBatch_getBaseValues(const odesBatch_t *b, double *values, in
 extern "C" int ODESBatch_getCapacity(const odesBatch_t *b) { return b->capacity; }
 extern "C" int ODESBatch_getNout(const odesBatch_t *b) { return b->nout + 1; }
 extern "C" int ODESBatch_getNstore(const odesBatch_t *b) { return b->nstore; }
+extern "C" int ODESBatch_getNsens(const odesBatch_t *b) { return b->nsens; }
+extern "C" int ODESBatch_getSensIndex(const odesBatch_t *b, int is) { return (b->os && is >= 0 && is < b->nsens) ? b->os->index_sens[is] : -1; }
+extern "C" double *ODESBatch_deviceSensitivities(odesBatch_t *b) { return b->d_sens; }
+extern "C" int ODESBatch_getSensitivities(odesBatch_t *b, int nsets, double *sens)
+{
+  if (b->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the plan was created without sensitivity analysis"); return 0; }
+  if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  CUDA_OK(cudaSetDevice(b->device));
+  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nsens * (size_t)b->om->neq;
+  CUDA_OK(cudaMemcpyAsync(sens, b->d_sens, sizeof(double) * per * (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  return 1;
+}
 extern "C" const char *ODESBatch_getSource(const odesBatch_t *b) { return b->code ? b->code->source : NULL; }
 extern "C" const char *ODESBatch_getCompileLog(const odesBatch_t *b) { return b->code ? b->code->log : NULL; }
 extern "C" double *ODESBatch_deviceValues(odesBatch_t *b) { return b->d_vary; }
@@ -600,6 +637,7 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   if (groupShift >= 0) { a.groupDone = b->d_groupDone; a.hostFlags = b->d_flags; a.groupShift = groupShift; }
   a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
+  a.sens = b->d_sens ? b->d_sens + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nsens * (size_t)b->om->neq : NULL;
   a.counter = b->d_counter + (b->counterSlot++ & 63);
   a.scratch = b->d_scratch;
   a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;

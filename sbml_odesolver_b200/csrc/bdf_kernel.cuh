@@ -190,6 +190,9 @@ __device__ __forceinline__ unsigned long long odes_take_sets(unsigned long long 
 #define CV_FAIL_BAD_J 1
 #define CV_FAIL_OTHER 2
 
+#ifndef NSENS
+#define NSENS 0
+#endif
 struct OdesArgs {
   const double *vary;          /* [NVARY][stride]                       */
   double *out;                 /* [nsets][nout+1][NSTORE]               */
@@ -208,6 +211,7 @@ struct OdesArgs {
   unsigned int *groupDone;     /* [groups] device counters, zeroed before the launch; NULL: no signalling */
   unsigned int *hostFlags;     /* [groups] mapped pinned host memory */
   int groupShift, pad2;
+  double *sens;                /* [nsets][nout+1][NSENS][NEQ] forward sensitivities (warp kernel with NSENS > 0), or NULL */
 };
 #ifndef ODES_HOST_EMULATION
 __device__ __forceinline__ void odes_signal_done(const OdesArgs &a, size_t set)

@@ -293,7 +293,8 @@ void generateMacros(charBuffer_t *b)
 }
 
 /* ------------------------------------------------------- host C flavour */
-char *ODEModel_generateCSource(odeModel_t *om)
+char *ODEModel_generateCSource(odeModel_t *om) { return ODEModel_generateCSourceSens(om, NULL); }
+char *ODEModel_generateCSourceSens(odeModel_t *om, const odeSense_t *os)
 {
   charBuffer_t *b = CharBuffer_create();
   emit_ctx_t c; int i; char *out;
@@ -315,6 +316,26 @@ char *ODEModel_generateCSource(odeModel_t *om)
     cbprintf(b, "  J[%d] = ", nz->j * om->neq + nz->i); gen(b, nz->ij, &c); CharBuffer_append(b, ";\n");
   }
   CharBuffer_append(b, "}\n");
+  /* sense_f: src/odeModel.c:2994-3100 -- per row: 0, += J_ij * yS[j] for the non-zero Jacobian entries, += df_i/dp for
+     the parameter of sensitivity iS */
+  if (os && om->jacobian) {
+    int j, k;
+    CharBuffer_append(b, "void sense_f(int iS, double t, const double *y, const double *yS, double *ySdot, double *value)\n{\n  (void)t; (void)iS;\n");
+    for (i = 0; i < om->neq; i++) cbprintf(b, "  value[%d] = y[%d];\n", i, i);
+    for (i = 0; i < om->neq; i++) {
+      cbprintf(b, "  ySdot[%d] = 0.0;\n", i);
+      for (j = 0; j < om->sparsesize; j++) {
+        nonzeroElem_t *nz = om->jacobSparse[j];
+        if (nz->i != i) continue;
+        cbprintf(b, "  ySdot[%d] += ( ", i); gen(b, nz->ij, &c); cbprintf(b, ") * yS[%d];\n", nz->j);
+      }
+      for (k = 0; k < os->nsens; k++) {
+        if (os->index_sensP[k] == -1 || !os->sens || !os->sensLogic[i][os->index_sensP[k]]) continue;
+        cbprintf(b, "  if ( %d == iS ) ySdot[%d] += ", k, i); gen(b, os->sens[i][os->index_sensP[k]], &c); CharBuffer_append(b, ";\n");
+      }
+    }
+    CharBuffer_append(b, "}\n");
+  }
   out = b->b; b->b = NULL; CharBuffer_free(b);
   return out;
 }
@@ -437,7 +458,7 @@ static int w_flatten_sum(const ASTNode_t *n, int neg, const wspace_t *w, int *of
   }
   return cnt;
 }
-static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k, emit_ctx_t *c, int *ode_local, int usejac, int npv)
+static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k, emit_ctx_t *c, int *ode_local, int usejac, int npv, const odeSense_t *os)
 {
   int nb = om->nassbeforeodes, nlev = 0, lev, i, j, g, ngroups = 0, nvalues = om->neq + om->nass + om->nconst;
   int *depth = (int *)calloc((size_t)nb + 1, sizeof(int)), *refs = (int *)calloc((size_t)nvalues + 1, sizeof(int));
@@ -593,13 +614,42 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
       if (open) CharBuffer_append(b, "    break;\n");
     }
   }
-  CharBuffer_append(b, "  default: break;\n  }\n}\n#endif\n");
+  CharBuffer_append(b, "  default: break;\n  }\n}\n");
+  /* forward sensitivities: which variable a sensitivity belongs to (initial value 1 on that element), and the emitted
+     sense_f row by row -- 0, += J_ij * yS[j] over the row's non-zero Jacobian entries, += df_i/dp_is */
+  if (os && usejac) {
+    CharBuffer_append(b, "DEV int w_sens_variable(int is)\n{\n  switch (is) {\n");
+    for (i = 0; i < os->nsens; i++) if (os->index_sensP[i] == -1) cbprintf(b, "  case %d: return %d;\n", i, os->index_sens[i]);
+    CharBuffer_append(b, "  default: return -1;\n  }\n}\n");
+    CharBuffer_append(b, "DEV double w_sens_row(int lane, int is, double t, const double *y, const PvRef pv, const double *jr, const double *ys)\n{\n"
+                         "  double r = 0.0; (void)is; (void)t; (void)y; (void)pv; (void)jr; (void)ys;\n  switch (lane) {\n");
+    for (i = 0; i < om->neq; i++) {
+      int kk, any = 0;
+      cbprintf(b, "  case %d:\n", i);
+      for (j = 0; j < om->sparsesize; j++) if (om->jacobSparse[j]->i == i) cbprintf(b, "    r += JR(%d) * ys[%d];\n", om->jacobSparse[j]->j, om->jacobSparse[j]->j);
+      for (kk = 0; kk < os->nsens; kk++) if (os->index_sensP[kk] != -1 && os->sens && os->sensLogic[i][os->index_sensP[kk]]) any = 1;
+      if (any) {
+        CharBuffer_append(b, "    switch (is) {\n");
+        for (kk = 0; kk < os->nsens; kk++) {
+          if (os->index_sensP[kk] == -1 || !os->sensLogic[i][os->index_sensP[kk]]) continue;
+          cbprintf(b, "    case %d: r += ", kk); gen(b, os->sens[i][os->index_sensP[kk]], c); CharBuffer_append(b, "; break;\n");
+        }
+        CharBuffer_append(b, "    default: break;\n    }\n");
+      }
+      CharBuffer_append(b, "    break;\n");
+    }
+    CharBuffer_append(b, "  default: break;\n  }\n  return r;\n}\n");
+  }
+  CharBuffer_append(b, "#endif\n");
   for (i = 0; i < nb; i++) free(text[i]);
   free(text); free(leaves); free(group); free(depth); free(refs); free(odeoff); free(odeneg); free(odecnt); free(odediv); free(w.lit);
 }
 
 char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
                                   int nstore, const int *store, const double *base)
+{ return ODEModel_generateCUDASourceSens(om, opt, nvary, vary, nstore, store, base, NULL); }
+char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
+                                      int nstore, const int *store, const double *base, const odeSense_t *os)
 {
   int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac;
   charBuffer_t *b = CharBuffer_create();
@@ -634,6 +684,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   cbprintf(b, "#define NEQ %d\n#define NASS %d\n#define NVAL %d\n#define NEVENTS %d\n#define NPV %d\n#define NVARY %d\n#define NSTORE %d\n#define NNZ %d\n#define HAS_JAC %d\n#define USE_TSTOP %d\n",
            om->neq, om->nass, nvalues, om->nevents, npv, nvary, nstore, usejac ? om->sparsesize : 0, usejac, (opt->SetTStop || om->npiecewise) ? 1 : 0);
   cbprintf(b, "#define RESET_ON_EVENT %d\n#define HALT_ON_EVENT %d\n", opt->ResetCvodeOnEvent ? 1 : 0, opt->HaltOnEvent ? 1 : 0);
+  cbprintf(b, "#define NSENS %d\n", (os && usejac) ? os->nsens : 0);
   CharBuffer_append(b, "#define A1(n) ((n) > 0 ? (n) : 1)\n#define DEV __device__ __forceinline__\n");
   /* per-trajectory constants live in strided shared memory (word k of this thread at p[k*s]) */
   CharBuffer_append(b, "#ifndef ODES_BLOCK\n#define ODES_BLOCK 64\n#endif\n#ifndef ODES_MAT_LOCAL\n#define ODES_MAT_LOCAL 0\n#endif\n"
@@ -690,7 +741,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
   if (usejac) for (i = 0; i < om->sparsesize; i++) { cbprintf(b, "  jnz[%d] = ", i); gen(b, om->jacobSparse[i]->ij, &c); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "}\n");
 
-  emit_warp_flavour(b, om, &k, &c, ode_local, usejac, npv);
+  emit_warp_flavour(b, om, &k, &c, ode_local, usejac, npv, os);
 
   /* event_f: interpreter semantics of IntegratorInstance_processEventsAndAssignments */
   CharBuffer_append(b, "DEV unsigned int event_f(double t, double (&y)[A1(NEQ)], const PvRef pv, int (&trigger)[A1(NEVENTS)], int &reinit)\n{\n"

@@ -632,6 +632,114 @@ int ODEModel_constructJacobian(odeModel_t *om)
   return om->jacobian;
 }
 
+/* ------------------------------------------------- forward sensitivities */
+/* src/odeModel.c:1963-2100 ODESense_constructMatrix */
+static int ODESense_constructMatrix(odeSense_t *os, odeModel_t *om)
+{
+  int i, j, l, failed = 0, nvalues = om->neq + om->nass + om->nconst, cap = 16;
+  nonzeroElem_t **sparse = (nonzeroElem_t **)malloc((size_t)cap * sizeof *sparse);
+  os->sens = (ASTNode_t ***)calloc((size_t)(om->neq > 0 ? om->neq : 1), sizeof(ASTNode_t **));
+  os->sensLogic = (int **)calloc((size_t)(om->neq > 0 ? om->neq : 1), sizeof(int *));
+  os->sparsesize = 0;
+  for (i = 0; i < om->neq; i++) {
+    ASTNode_t *ode = copyAST(om->ode[i]);
+    os->sens[i] = (ASTNode_t **)calloc((size_t)(os->nsensP > 0 ? os->nsensP : 1), sizeof(ASTNode_t *));
+    os->sensLogic[i] = (int *)calloc((size_t)(os->nsensP > 0 ? os->nsensP : 1), sizeof(int));
+    for (j = om->nass - 1; j >= 0; j--) AST_replaceNameByFormula(ode, om->names[om->neq + j], om->assignment[j]);
+    l = 0;
+    for (j = 0; j < os->nsens; j++) {
+      ASTNode_t *fprime, *simple, *index; double val = 1; unsigned int k; List_t *names;
+      if (os->index_sens[j] < om->neq) continue;                /* variables have no column */
+      fprime = differentiateAST(ode, om->names[os->index_sens[j]]);
+      simple = simplifyAST(fprime);
+      index = indexAST(simple, nvalues, om->names);
+      ASTNode_free(fprime); ASTNode_free(simple);
+      os->sens[i][l] = index;
+      if (ASTNode_isInteger(index)) val = (double)ASTNode_getInteger(index);
+      if (ASTNode_isReal(index)) val = ASTNode_getReal(index);
+      if (val != 0.0) {
+        if (os->sparsesize == cap) { cap *= 2; sparse = (nonzeroElem_t **)realloc(sparse, (size_t)cap * sizeof *sparse); }
+        sparse[os->sparsesize++] = elem_new(i, j, index);
+        os->sensLogic[i][l] = 1;
+      }
+      l++;
+      names = ASTNode_getListOfNodes(index, (ASTNodePredicate)ASTNode_isName);
+      for (k = 0; k < List_size(names); k++) {
+        const char *nm = ASTNode_getName((ASTNode_t *)List_get(names, k));
+        if (nm && strcmp(nm, "differentiation_failed") == 0) failed++;
+      }
+      List_free(names);
+    }
+    ASTNode_free(ode);
+  }
+  os->sensSparse = sparse;
+  if (failed != 0) {
+    SolverError_error(WARNING_ERROR_TYPE, SOLVER_ERROR_ENTRIES_OF_THE_PARAMETRIC_MATRIX_COULD_NOT_BE_CONSTRUCTED,
+                      "%d entries of the parametric `Jacobian' matrix could not be constructed, due to failure of "
+                      "differentiation. Cvode will use internal approximation instead.", failed);
+    return 0;
+  }
+  return 1;
+}
+/* src/odeModel.c:2188-2278 */
+odeSense_t *ODESense_create(odeModel_t *om, cvodeSettings_t *opt)
+{
+  int i, k, all, construct = 0;
+  odeSense_t *os;
+  if (!om) return NULL;
+  os = (odeSense_t *)calloc(1, sizeof *os);
+  if (!opt) { all = 1; construct = 1; }
+  else { all = (opt->sensIDs == NULL); if (opt->DoAdjoint || om->jacobian) construct = 1; }
+  os->om = om; os->neq = om->neq;
+  os->nsens = all ? om->nconst : opt->nsens;
+  os->index_sens = (int *)calloc((size_t)(os->nsens > 0 ? os->nsens : 1), sizeof(int));
+  os->index_sensP = (int *)calloc((size_t)(os->nsens > 0 ? os->nsens : 1), sizeof(int));
+  if (all) {
+    for (i = 0; i < os->nsens; i++) { os->index_sens[i] = om->neq + om->nass + i; os->index_sensP[i] = i; }
+    os->nsensP = om->nconst;
+  } else {
+    k = 0;
+    for (i = 0; i < os->nsens; i++) {
+      os->index_sens[i] = ODEModel_getVariableIndexFields(om, opt->sensIDs[i]);
+      if (os->index_sens[i] < 0 || (os->index_sens[i] >= om->neq && os->index_sens[i] < om->neq + om->nass)) {
+        SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_SYMBOL_IS_NOT_IN_MODEL, "sensitivity requested for %s, which is not a variable or constant of the model", opt->sensIDs[i]);
+        ODESense_free(os);
+        return NULL;
+      }
+      if (os->index_sens[i] < om->neq) os->index_sensP[i] = -1;
+      else os->index_sensP[i] = k++;
+    }
+    os->nsensP = k;
+  }
+  os->sensitivity = construct ? ODESense_constructMatrix(os, om) : 0;
+  return os;
+}
+odeSense_t *ODEModel_constructSensitivity(odeModel_t *om) { return ODESense_create(om, NULL); }
+void ODESense_free(odeSense_t *os)
+{
+  int i, j;
+  if (!os) return;
+  if (os->sens) for (i = 0; i < os->neq; i++) { if (os->sens[i]) for (j = 0; j < os->nsensP; j++) ASTNode_free(os->sens[i][j]); free(os->sens[i]); }
+  if (os->sensLogic) for (i = 0; i < os->neq; i++) free(os->sensLogic[i]);
+  for (i = 0; i < os->sparsesize; i++) free(os->sensSparse[i]);
+  free(os->sens); free(os->sensLogic); free(os->sensSparse); free(os->index_sens); free(os->index_sensP); free(os);
+}
+variableIndex_t *ODESense_getSensParamIndexByNum(const odeSense_t *os, int i)
+{ return (i >= 0 && i < os->nsens) ? ODEModel_getVariableIndexByNum(os->om, os->index_sens[i]) : NULL; }
+int ODESense_getNeq(const odeSense_t *os) { return os->neq; }
+int ODESense_getNsens(const odeSense_t *os) { return os->nsens; }
+const ASTNode_t *ODESense_getSensIJEntry(const odeSense_t *os, int i, int j)
+{
+  if (!os->sens || i < 0 || i >= os->neq || j < 0 || j >= os->nsens || os->index_sensP[j] < 0) return NULL;
+  return os->sens[i][os->index_sensP[j]];
+}
+const ASTNode_t *ODESense_getSensEntry(const odeSense_t *os, const variableIndex_t *vi1, const variableIndex_t *vi2)
+{
+  int j;
+  for (j = 0; j < os->nsens; j++) if (os->index_sens[j] == vi2->index) return ODESense_getSensIJEntry(os, vi1->index, j);
+  return NULL;
+}
+
 void ODEModel_freeJacobian(odeModel_t *om)
 {
   int i, j;

@@ -45,9 +45,27 @@ cvodeSettings_t *CvodeSettings_clone(cvodeSettings_t *set)
     c->TimePoints = (double *)malloc((size_t)(set->PrintStep + 1) * sizeof(double));
     for (i = 0; i <= set->PrintStep; i++) c->TimePoints[i] = set->TimePoints[i];
   }
+  if (set->sensIDs) CvodeSettings_setSensParams(c, set->sensIDs, set->nsens);
   return c;
 }
-void CvodeSettings_free(cvodeSettings_t *set) { if (!set) return; free(set->TimePoints); free(set); }
+void CvodeSettings_unsetSensParams(cvodeSettings_t *set)
+{
+  int i;
+  if (set->sensIDs) for (i = 0; i < set->nsens; i++) free(set->sensIDs[i]);
+  free(set->sensIDs); set->sensIDs = NULL; set->nsens = 0;
+}
+int CvodeSettings_setSensParams(cvodeSettings_t *set, char **sensIDs, int nsens)
+{
+  int i;
+  CvodeSettings_unsetSensParams(set);
+  if (sensIDs) {
+    set->sensIDs = (char **)calloc((size_t)(nsens > 0 ? nsens : 1), sizeof(char *));
+    for (i = 0; i < nsens; i++) { set->sensIDs[i] = (char *)malloc(strlen(sensIDs[i]) + 1); strcpy(set->sensIDs[i], sensIDs[i]); }
+    set->nsens = nsens;
+  }
+  return 1;
+}
+void CvodeSettings_free(cvodeSettings_t *set) { if (!set) return; CvodeSettings_unsetSensParams(set); free(set->TimePoints); free(set); }
 
 int CvodeSettings_setTime(cvodeSettings_t *set, double EndTime, int PrintStep)
 {

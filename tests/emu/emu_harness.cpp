@@ -20,12 +20,13 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 
 extern "C" int emu_run(const double *base, const int *trig0, const double *vary, double *out, int *status, int *stats,
                        unsigned int *fired, const double *tpoints, unsigned long long stride, int nsets, int nout,
-                       int mxstep, double reltol, double abstol)
+                       int mxstep, double reltol, double abstol, double *sens)
 {
   for (int i = 0; i < NVAL; i++) c_base[i] = base[i];
   for (int i = 0; i < NEVENTS; i++) c_trigger0[i] = trig0[i];
   OdesArgs a;
   a.vary = vary; a.out = out; a.status = status; a.stats = stats; a.fired = fired; a.tpoints = tpoints;
+  a.sens = sens;
   a.groupDone = 0; a.hostFlags = 0; a.groupShift = 0; a.pad2 = 0;
   a.stride = stride; a.nsets = nsets; a.nout = nout; a.mxstep = mxstep; a.pad = 0; a.reltol = reltol; a.abstol = abstol;
   unsigned long long counter = 0;

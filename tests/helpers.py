@@ -58,9 +58,17 @@ def oracle_run(model, opt, vary, values, nout, backend=PORT, threads=1, compiled
     return dict(out=out, status=status, stats=stats, fired=fired, margin=margin)
 
 
-def compile_c_model(model, tag):
-    """gcc-compiles ODEModel_generateCSource (the reference's compiled mode) into a shared object."""
-    src = so.take_string(so.lib().ODEModel_generateCSource(model.om))
+def compile_c_model(model, tag, opt=None):
+    """gcc-compiles ODEModel_generateCSource (the reference's compiled mode) into a shared object; with a settings object
+    that asks for sensitivities the source also holds sense_f for its parameters."""
+    if opt is not None and so.lib().CvodeSettings_getSensitivity(opt):
+        if not so.lib().ODEModel_getNumJacobiElements(model.om):
+            so.lib().ODEModel_constructJacobian(model.om)
+        os_ = so.lib().ODESense_create(model.om, opt)
+        src = so.take_string(so.lib().ODEModel_generateCSourceSens(model.om, os_))
+        so.lib().ODESense_free(os_)
+    else:
+        src = so.take_string(so.lib().ODEModel_generateCSource(model.om))
     h = hashlib.sha1(src.encode()).hexdigest()[:12]
     d = os.path.join(ROOT, "oracle", "_ref", "models")
     os.makedirs(d, exist_ok=True)
@@ -70,6 +78,44 @@ def compile_c_model(model, tag):
         open(cpath, "w").write(src)
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", cpath, "-o", path, "-lm"])
     return path
+
+
+REFS_LIB = os.path.join(ROOT, "oracle", "_ref", "libcvodes_ref.so")
+_refs = None
+
+
+def have_sens_ref():
+    return os.path.exists(REFS_LIB)
+
+
+def sens_ref_run(model, opt, batch, vary, values, tpoints, mxstep, rtol, atol, threads=1, tag="sens"):
+    """Forward sensitivities from the reference's vendored CVODES 2.3.0 (oracle/sens_ref.c) driven with the emitted host-C
+    model functions.  Returns dict(out[nsets][nout+1][neq], sens[nsets][nout+1][nsens][neq], status, stats[nsets][8])."""
+    global _refs
+    if _refs is None:
+        _refs = C.CDLL(REFS_LIB)
+        _refs.refcvs_integrate_batch.restype = C.c_int
+    path = compile_c_model(model, tag, opt)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    nsets, nout, neq, ns = values.shape[0], len(tpoints) - 1, model.neq, batch.nsens
+    vary = np.ascontiguousarray(vary, dtype=np.int32)
+    base, _ = batch.base_values()
+    base = np.ascontiguousarray(base, dtype=np.float64)
+    sens_idx = [so.lib().ODESBatch_getSensIndex(batch.h, k) for k in range(ns)]
+    sens_var = np.array([i if i < neq else -1 for i in sens_idx], dtype=np.int32)
+    tp = np.ascontiguousarray(tpoints, dtype=np.float64)
+    out = np.zeros((nsets, nout + 1, neq))
+    sens = np.zeros((nsets, nout + 1, ns, neq))
+    status = np.zeros(nsets, dtype=np.int32)
+    stats = np.zeros((nsets, 8), dtype=np.int32)
+    r = _refs.refcvs_integrate_batch(path.encode(), C.c_int(neq), C.c_int(model.nvalues), C.c_int(ns), C.c_void_p(sens_var.ctypes.data),
+                                     C.c_void_p(base.ctypes.data), C.c_int(nsets), C.c_int(len(vary)), C.c_void_p(vary.ctypes.data),
+                                     C.c_void_p(values.ctypes.data), C.c_void_p(tp.ctypes.data), C.c_int(nout), C.c_double(rtol), C.c_double(atol),
+                                     C.c_long(mxstep), C.c_void_p(out.ctypes.data), C.c_void_p(sens.ctypes.data), C.c_void_p(status.ctypes.data),
+                                     C.c_void_p(stats.ctypes.data), C.c_int(threads))
+    if r < 0:
+        raise RuntimeError("sensitivity reference failed to set up")
+    return dict(out=out, sens=sens, status=status, stats=stats)
 
 
 class Emu:
@@ -104,10 +150,12 @@ class Emu:
         base = np.ascontiguousarray(base, dtype=np.float64)
         trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
         tp = np.ascontiguousarray(tpoints, dtype=np.float64)
+        sens = np.zeros((nsets, nout + 1, max(b.nsens, 1), b.model.neq))
         self.lib.emu_run(C.c_void_p(base.ctypes.data), C.c_void_p(trig0.ctypes.data), C.c_void_p(vary.ctypes.data), C.c_void_p(raw.ctypes.data),
                          C.c_void_p(status.ctypes.data), C.c_void_p(stats.ctypes.data), C.c_void_p(fired.ctypes.data), C.c_void_p(tp.ctypes.data),
-                         C.c_ulonglong(nsets), C.c_int(nsets), C.c_int(nout), C.c_int(mxstep), C.c_double(rtol), C.c_double(atol))
-        return dict(out=out, status=status, stats=stats, fired=fired)
+                         C.c_ulonglong(nsets), C.c_int(nsets), C.c_int(nout), C.c_int(mxstep), C.c_double(rtol), C.c_double(atol),
+                         C.c_void_p(sens.ctypes.data))
+        return dict(out=out, status=status, stats=stats, fired=fired, sens=sens)
 
 
 def mapk_scan_model():
