@@ -446,7 +446,7 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
     if (!why) {
       b->os = ODESense_create(om, opt);
       if (!b->os || !b->os->sensitivity) why = "the parametric matrix could not be constructed";
-      else if (b->os->nsens < 1 || b->os->nsens > 16) why = "between 1 and 16 sensitivity parameters are supported";
+      else if (b->os->nsens < 1 || b->os->nsens > 32) why = "between 1 and 32 sensitivity parameters are supported";
     }
     if (why) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "%s", why); ODESense_free(b->os); delete b; return NULL; }
     b->nsens = b->os->nsens;

@@ -212,7 +212,7 @@ HUANG_LOCALS = sorted(HUANG_LOCALS + [("r1b", "k2")] + [(f"r{i}b", f"k{i}") for 
                       key=lambda rp: (int(rp[0][1:-1]), rp[0][-1], rp[1][0] != "a"))
 
 
-def workload(name, nout=None):
+def workload(name, nout=None, **settings_kw):
     """Returns dict(model, opt, vary, nominal, span, log10, rtol, atol, nout, end, store) for a config name."""
     rtol, atol = 1e-6, 1e-9
     if name == "mapk":
@@ -242,6 +242,7 @@ def workload(name, nout=None):
         raise KeyError(name)
     if nout is not None:
         end, n_out = end * nout / n_out, nout
+    kw.update(settings_kw)
     opt = so.settings(end, n_out, atol, rtol, **kw)
     return dict(name=name, model=m, opt=opt, vary=vary, nominal=nominal, span=span, log10=log10,
                 rtol=rtol, atol=atol, nout=n_out, end=end)

@@ -1,0 +1,210 @@
+"""Forward sensitivity analysis through the batched warp-per-trajectory kernel.
+
+The reference integrates the sensitivity equations with CVODES: simultaneous corrector, analytic right-hand side
+built from the Jacobian and the parametric matrix, estimated tolerances, no error control on the sensitivity
+variables (src/sensSolver.c:197-346), and reads them back after every output step (src/sensSolver.c:108-140).  The
+checker is the reference's vendored CVODES 2.3.0 itself (oracle/sens_ref.c, compiled unmodified into
+oracle/_ref/libcvodes_ref.so) driven with the emitted host-C model functions (the reference's compiled mode): the
+kernel has to take the same steps (identical work counters) and produce BIT-IDENTICAL states and sensitivities --
+far inside the north star's tolerance max(10 rtol |x|, 10 atol), which is asserted as well.
+The reference's own unit test (unittest/test_sensSolver.c:14-31) runs MAPK.xml with the parameters MAPK, MAPK_P, K1, Ki;
+it holds no numbers (smoke only), so the same selection is pinned here against the vendored CVODES."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+REF_IDS = ["MAPK", "MAPK_P", "K1", "Ki"]                       # unittest/test_sensSolver.c:14-19
+CASES = {
+    "mapk": dict(ids=REF_IDS, nout=None),
+    "repressilator": dict(ids=["alpha", "beta", "x1"], nout=100),
+    "huang": dict(ids=["r_r1a_a1", "KKK", "r_r10b_k10"], nout=None),
+    "goodwin": dict(ids=None, nout=20),                        # default: every constant of the model
+}
+needs_ref = pytest.mark.skipif(not H.have_sens_ref(), reason="oracle/_ref/libcvodes_ref.so not built")
+
+
+def _case(name, nout=None):
+    c = CASES[name]
+    w = H.workload(name, nout=nout if nout is not None else c["nout"], sensitivity=1, sens_ids=c["ids"])
+    return w
+
+
+def test_sense_structures_follow_the_reference():
+    """ODESense_create (src/odeModel.c:2188-2278): index maps for variables and parameters, parametric matrix entries."""
+    L = so.lib()
+    m, _, _ = H.mapk_scan_model()
+    L.ODEModel_constructJacobian(m.om)
+    opt = so.settings(1000.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=REF_IDS)
+    os_ = L.ODESense_create(m.om, opt)
+    assert L.ODESense_getNsens(os_) == 4 and L.ODESense_getNeq(os_) == 8
+    idx = []
+    for k in range(4):
+        vi = L.ODESense_getSensParamIndexByNum(os_, k)
+        idx.append(L.ODEModel_getVariableName(m.om, vi).decode())
+        L.VariableIndex_free(vi)
+    assert idx == REF_IDS
+    # variables have no column in the parametric matrix; d(dMKKK/dt)/dK1 is an expression, d(dMAPK/dt)/dK1 is zero
+    assert L.ODESense_getSensIJEntry(os_, 0, 0) is None and L.ODESense_getSensIJEntry(os_, 0, 1) is None
+    e = so.take_string(L.SBML_formulaToString(L.ODESense_getSensIJEntry(os_, 0, 2)))
+    assert "K1" in e and "MKKK" in e
+    assert so.take_string(L.SBML_formulaToString(L.ODESense_getSensIJEntry(os_, 5, 2))) == "0"
+    L.ODESense_free(os_)
+    # default selection: all constants, in value[] order
+    os_ = L.ODEModel_constructSensitivity(m.om)
+    assert L.ODESense_getNsens(os_) == m.nconst
+    L.ODESense_free(os_)
+
+
+def test_emitted_sense_function_follows_the_reference_generator():
+    """src/odeModel.c:2994-3100: per row `= 0.0`, `+= (J_ij) * yS[j]` over the non-zero Jacobian entries, then the guarded
+    parametric term."""
+    L = so.lib()
+    m, _, _ = H.mapk_scan_model()
+    L.ODEModel_constructJacobian(m.om)
+    opt = so.settings(1000.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=REF_IDS)
+    os_ = L.ODESense_create(m.om, opt)
+    src = so.take_string(L.ODEModel_generateCSourceSens(m.om, os_))
+    L.ODESense_free(os_)
+    body = src[src.index("void sense_f"):]
+    assert body.count(" = 0.0;") == 8
+    assert body.count(") * yS[") == len(m.jacobian_structure())
+    assert "if ( 2 == iS ) ySdot[0] += " in body and "if ( 0 == iS )" not in body and "if ( 1 == iS )" not in body
+
+
+@needs_ref
+@pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6)])
+def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
+    w = _case(name)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=11)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    assert b.nsens == (len(CASES[name]["ids"]) if CASES[name]["ids"] else m.nconst)
+    tp = H.tpoints(w["opt"], w["nout"])
+    base, trig = b.base_values()
+    got = H.Emu(b, name + "_sens").run(base, trig, vals, tp, 10000, w["rtol"], w["atol"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag=name + "_sens")
+    b.close()
+    assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(got["stats"].T, ref["stats"][:, :7])                       # same steps, Newton and Jacobian decisions
+    assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"])         # bit for bit
+    assert np.array_equal(got["sens"], ref["sens"])
+    # the stated gate, on the sensitivities as well
+    assert H.parity(got["sens"], ref["sens"], w["rtol"], w["atol"]) <= 1.0
+    # row 0: 1 for a variable with respect to its own initial value, else 0 (src/cvodeData.c:453-461)
+    for k in range(b.nsens):
+        i = so.lib().ODESBatch_getSensIndex(b.h, k) if b.h else None
+    assert set(np.unique(got["sens"][:, 0])) <= {0.0, 1.0}
+
+
+@needs_ref
+def test_sensitivities_change_the_step_sequence_only_through_the_newton_test():
+    """With errconS == FALSE the error test sees the state alone, but the corrector's convergence test sees every variable
+    (cvodes.c:3907-3914): the reference's state trajectory with sensitivities is close to, not identical with, the plain
+    run -- and the kernel reproduces whichever the reference produces."""
+    w = _case("mapk", nout=20)
+    wp = H.workload("mapk", nout=20)
+    m = w["model"]
+    vals = H.workload_values(w, 8, seed=5)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    tp = H.tpoints(w["opt"], 20)
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag="mapk_sens")
+    b.close()
+    plain = H.oracle_run(wp["model"], wp["opt"], wp["vary"], vals, 20, compiled_so=H.compile_c_model(wp["model"], "mapk"))
+    assert H.parity(np.transpose(ref["out"], (1, 2, 0)), np.transpose(plain["out"][:, :, :m.neq], (1, 2, 0)), 1e-4, 1e-7) <= 1.0
+
+
+@needs_ref
+def test_sensitivities_agree_with_central_differences():
+    """Size-independent property: dy/dp from the kernel against (y(p + d) - y(p - d)) / 2d of plain integrations at
+    tight tolerances."""
+    name = "mapk"
+    w = H.workload(name, nout=10, sensitivity=1, sens_ids=["K1", "MKKK"])
+    wp = H.workload(name, nout=10)
+    m = w["model"]
+    vals = H.workload_values(w, 2, seed=9)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    tp = H.tpoints(w["opt"], 10)
+    base, trig = b.base_values()
+    got = H.Emu(b, "mapk_sens_fd").run(base, trig, vals, tp, 10000, 1e-6, 1e-9)
+    b.close()
+    tight = so.settings(w["end"], 10, 1e-13, 1e-11)
+    k1 = w["vary"].index(m.index("K1"))
+    vary_fd = list(w["vary"]) + [m.index("MKKK")]
+    for col, j in ((k1, 0), (len(vary_fd) - 1, 1)):
+        v0 = np.concatenate([vals, np.full((2, 1), m.base_values()[m.index("MKKK")])], axis=1)
+        d = 1e-5 * v0[:, col]
+        vp, vm = v0.copy(), v0.copy()
+        vp[:, col] += d
+        vm[:, col] -= d
+        yp = H.oracle_run(wp["model"], tight, vary_fd, vp, 10)["out"][:, :, :m.neq]
+        ym = H.oracle_run(wp["model"], tight, vary_fd, vm, 10)["out"][:, :, :m.neq]
+        fd = (yp - ym) / (2 * d)[:, None, None]
+        s = got["sens"][:, :, j, :]
+        assert np.allclose(s[:, 1:], fd[:, 1:], rtol=2e-3, atol=2e-4 * np.abs(fd).max()), (np.abs(s - fd).max(), np.abs(fd).max())
+
+
+def test_unsupported_sensitivity_configurations_fail_loudly():
+    m = so.Model(H.model_path("two_events_one_assignment.xml"))
+    opt = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1)
+    with pytest.raises(so.OdesError, match="events"):
+        so.Batch(m, opt, [m.index("S1")])
+    m2, vary, _ = H.mapk_scan_model()
+    opt2 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["K1"])
+    so.lib().CvodeSettings_setSensMethod(opt2, 1)
+    with pytest.raises(so.OdesError, match="simultaneous"):
+        so.Batch(m2, opt2, vary)
+    opt3 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["no_such_symbol"])
+    with pytest.raises(so.OdesError):
+        so.Batch(m2, opt3, vary)
+    b = so.Batch(m2, so.settings(10.0, 10, 1e-9, 1e-6), vary)
+    assert b.nsens == 0
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------------ GPU tier
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64)])
+def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
+    w = _case(name)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=2027)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    n = b.set_values(vals)
+    ms = b.integrate(n)
+    out, sens, status, stats = b.results(n), b.sensitivities(n), b.status(n), b.stats(n).T
+    tp = H.tpoints(w["opt"], w["nout"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=8, tag=name + "_sens")
+    print(name, "nsens", b.nsens, f"{n / ms * 1e3:.0f} trajectories/s", b.kernel_info())
+    b.close()
+    assert np.array_equal(status, ref["status"])
+    assert np.array_equal(stats, ref["stats"][:, :7])
+    assert H.parity(sens, ref["sens"], w["rtol"], w["atol"]) <= 1.0                  # the gate
+    assert np.array_equal(np.transpose(out, (2, 0, 1)), ref["out"], equal_nan=True)  # and bit for bit
+    assert np.array_equal(sens, ref["sens"], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_respect_the_conservation_laws_at_scale():
+    """Full-size property (no oracle): MKKK + MKKK_P is conserved, so the sensitivities of the pair sum to zero for a
+    parameter and to one for the initial value of MKKK; failed rows are not-a-number in states and sensitivities alike."""
+    w = H.workload("mapk", sensitivity=1, sens_ids=["K1", "MKKK", "r_J1_V2"])
+    m = w["model"]
+    nsets = 50_000
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    lo, hi = np.full(len(w["vary"]), -1.0), np.full(len(w["vary"]), 1.0)
+    b.generate_values(nsets, 20261019, 0, w["nominal"], lo, hi)
+    ms = b.integrate(nsets)
+    sens, status = b.sensitivities(nsets), b.status(nsets)
+    print(f"MAPK + 3 sensitivities: {nsets / ms * 1e3:.0f} trajectories/s", b.kernel_info())
+    b.close()
+    assert (status == 0).all()
+    pair = sens[:, :, :, 0] + sens[:, :, :, 1]                    # [set][row][sens]
+    scale = np.abs(sens[:, :, :, :2]).max(axis=3) + 1.0
+    assert (np.abs(pair[:, :, 0]) <= 1e-6 * scale[:, :, 0]).all()
+    assert (np.abs(pair[:, :, 2]) <= 1e-6 * scale[:, :, 2]).all()
+    assert (np.abs(pair[:, :, 1] - 1.0) <= 1e-6 * scale[:, :, 1]).all()
