@@ -16,7 +16,9 @@ struct cvodeResults {
   double *time;        /* [nout+1] */
   int nvalues;
   double **value;      /* [nvalues][nout+1], one time row per variable (cvodeData.c:596-613) */
-  int neq, nsens; double ***sensitivity;   /* unused on this path, kept NULL */
+  /* forward sensitivities (reference cvodeData.h:178-184): sensitivity[i][j][k] = d value_i(t_k) / d p_j */
+  int neq, nsens; int *index_sens; double ***sensitivity;
+  double **directional;  /* [neq][nout+1] sum_j sensitivity[i][j][k] * dp[j] (CvodeResults_computeDirectional) */
 };
 
 struct cvodeData {
@@ -30,6 +32,8 @@ struct cvodeData {
   cvodeSettings_t *opt;
   cvodeResults_t *results;
   int run;
+  /* current sensitivities d value_i / d p_j, [neq][nsens] (reference cvodeData.h:95-122) */
+  odeSense_t *os; int nsens; double **sensitivity;
 };
 
 cvodeData_t *CvodeData_create(odeModel_t *);
@@ -41,6 +45,12 @@ void CvodeResults_free(cvodeResults_t *);
 double CvodeResults_getTime(const cvodeResults_t *, int);
 double CvodeResults_getValue(cvodeResults_t *, variableIndex_t *, int);
 int CvodeResults_getNout(const cvodeResults_t *);
+/* reference cvodeData.h:212-226 */
+double CvodeResults_getSensitivityByNum(cvodeResults_t *, int value, int parameter, int timestep);
+double CvodeResults_getSensitivity(cvodeResults_t *, variableIndex_t *y, variableIndex_t *p, int timestep);
+void CvodeResults_computeDirectional(cvodeResults_t *, const double *dp);
+int CvodeResults_allocateSens(cvodeResults_t *, int neq, int nsens, int nout);
+int CvodeData_initializeSensitivities(cvodeData_t *, cvodeSettings_t *, odeModel_t *, odeSense_t *);
 
 #ifdef __cplusplus
 }

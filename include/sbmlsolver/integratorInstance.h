@@ -27,6 +27,8 @@ struct cvodeSolver {
   double *course;      /* [nsteps][nvalues] rows computed ahead by the device */
   int *courseFired;    /* [nsteps] event bitmask per row                       */
   int courseFirst, courseLen, courseStatus, courseFailRow;
+  double *courseSens;  /* [nsteps][nsens][neq] forward sensitivities of the course, or NULL */
+  int nsens;
   long nst, nfe, nsetups, nje, nni, ncfn, netf;
 };
 
@@ -35,6 +37,7 @@ struct integratorInstance {
   odeModel_t *om; cvodeSettings_t *opt; cvodeData_t *data; cvodeSolver_t *solver; cvodeResults_t *results;
   int run; int UseJacobian; int processEvents;
   int clockStarted; clock_t startTime;
+  odeSense_t *os;      /* forward-sensitivity structures (opt->Sensitivity), owned by the instance */
 };
 
 integratorInstance_t *IntegratorInstance_create(odeModel_t *, cvodeSettings_t *);
@@ -73,6 +76,14 @@ void IntegratorInstance_dumpNames(integratorInstance_t *);
 void IntegratorInstance_dumpSolver(integratorInstance_t *);
 int IntegratorInstance_checkTrigger(integratorInstance_t *);
 int IntegratorInstance_updateModel(integratorInstance_t *);
+/* forward sensitivities (reference integratorInstance.h:180-187, src/integratorInstance.c:687-790) */
+odeSense_t *IntegratorInstance_getSensitivityModel(integratorInstance_t *);
+double IntegratorInstance_getSensitivity(integratorInstance_t *, variableIndex_t *y, variableIndex_t *p);
+double IntegratorInstance_getSensitivityByNum(integratorInstance_t *, int y, int p);
+int IntegratorInstance_getNsens(integratorInstance_t *);
+char *IntegratorInstance_getSensVariableName(integratorInstance_t *, int);
+void IntegratorInstance_dumpYSensitivities(integratorInstance_t *, variableIndex_t *);
+void IntegratorInstance_dumpPSensitivities(integratorInstance_t *, variableIndex_t *);
 
 #ifdef __cplusplus
 }

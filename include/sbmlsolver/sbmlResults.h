@@ -2,8 +2,8 @@
  * sbmlResults.h -- simulation results mapped back onto SBML structures: time courses of all species, of the
  * non-constant compartments and global parameters, and of the reaction fluxes.
  * Reference: src/sbmlsolver/sbmlResults.h:66-135 (same struct layouts and entry points), src/sbmlResults.c:66-560,
- * src/odeSolver.c:441-543 (SBMLResults_fromIntegrator).  Sensitivity fields are kept for layout compatibility and
- * stay empty (forward/adjoint sensitivities are outside the batched path).
+ * src/odeSolver.c:441-543 (SBMLResults_fromIntegrator).  Forward sensitivities are mapped by SBMLResults_createSens' restatement
+ * (src/odeSolver.c:545-575).
  */
 #ifndef ODES_B200_SBMLRESULTS_H
 #define ODES_B200_SBMLRESULTS_H
@@ -22,7 +22,7 @@ struct timeCourse {
   int timepoints;        /* number of time points, including the initial one */
   char *name;            /* SBML id */
   double *values;        /* [timepoints] */
-  double **sensitivity;  /* unused (NULL) */
+  double **sensitivity;  /* [nsens][timepoints] of an ODE variable when sensitivities were computed, else NULL */
 };
 struct timeCourseArray { int num_val; timeCourse_t **tc; };
 struct _SBMLResults {
@@ -31,7 +31,7 @@ struct _SBMLResults {
   timeCourseArray_t *compartments;   /* non-constant compartments */
   timeCourseArray_t *parameters;     /* non-constant global parameters */
   timeCourseArray_t *fluxes;         /* one per reaction */
-  int nsens; char **param;           /* unused (0, NULL) */
+  int nsens; char **param;           /* ids of the sensitivity parameters (src/odeSolver.c:545-575) */
 };
 struct _SBMLResultsMatrix { SBMLResults_t ***results; int i; int j; };
 struct _SBMLResultsArray { SBMLResults_t **results; int size; };

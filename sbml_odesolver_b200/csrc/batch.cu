@@ -305,6 +305,7 @@ struct odesBatch {
   cudaStream_t stream, copyIn, copyOut; cudaEvent_t e0, e1, t0, t1, evIn[2], evK[2], evOut[2];
   float lastMs; int launches;
   std::vector<double> base; std::vector<int> trigger0;
+  int sensFromRow0;                               /* initial sensitivities supplied by the host (single-instance restarts) */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
 };
 
@@ -376,9 +377,10 @@ static std::string build_source(odesBatch_t *b)
   if (warp) {
     const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);
     b->laMode = 0; b->tmemCols = 0; b->block = 32 * wpb; b->matLocal = 0; b->smemBytes = 0;
-    /* measured on huang96 (B200): 8 warps per SM 113 k, 12 warps 145 k, 16 warps (128 registers, spills) 136 k trajectories/s */
+    /* measured on huang96 (B200): 8 warps per SM 113 k, 12 warps 145 k, 16 warps (128 registers, spills) 136 k trajectories/s;
+       after the solver state left local memory (136 registers unconstrained): 12 warps 227 k, 16 warps (128 registers) 267 k */
     /* with sensitivities a lane carries 10 more vector elements per sensitivity: fewer resident warps, more registers */
-    b->minblocks = env_int("ODES_MINBLOCKS", b->nsens > 0 ? (b->nsens <= 2 ? 2 : 1) : (wpb == 4 ? 3 : 1)); b->maxBlocksPerSM = 32;
+    b->minblocks = env_int("ODES_MINBLOCKS", b->nsens > 0 ? (b->nsens <= 2 ? 2 : 1) : (wpb == 4 ? 4 : 1)); b->maxBlocksPerSM = 32;
     char headw[512];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
              env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
@@ -406,7 +408,7 @@ static std::string build_source(odesBatch_t *b)
   char head[640];
   snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 8), env_int("ODES_ALIGN_MASK", 7),
+           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   src += model;
@@ -436,7 +438,7 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
   if (!compute_base(om, opt, b->base, b->trigger0)) { delete b; return NULL; }
   /* forward sensitivities (src/sensSolver.c:197-346): simultaneous corrector, analytic sense_f, no error control on the
      sensitivity variables -- the reference's set-up; it needs the Jacobian and the parametric matrix */
-  b->os = NULL; b->nsens = 0; b->d_sens = NULL;
+  b->os = NULL; b->nsens = 0; b->d_sens = NULL; b->sensFromRow0 = 0;
   if (opt->Sensitivity) {
     const char *why = NULL;
     if (!(opt->UseJacobian && om->jacobian)) why = "forward sensitivities need the analytic Jacobian";
@@ -531,6 +533,15 @@ extern "C" int ODESBatch_setTimeGrid(odesBatch_t *b, int nout, const double *tpo
   if (nout > b->opt->PrintStep || nout < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "time grid longer than the plan's"); return 0; }
   CUDA_OK(cudaMemcpy(b->d_tpoints, tpoints, sizeof(double) * (size_t)(nout + 1), cudaMemcpyHostToDevice));
   b->nout = nout;
+  return 1;
+}
+/* private: initial sensitivities [nsens][neq] of set 0 for a continued course; NULL switches back to the 0 / 1 start */
+extern "C" int ODESBatch_setInitialSensitivities(odesBatch_t *b, const double *s0)
+{
+  if (b->nsens <= 0) return 1;
+  if (!ODESBatch_reserve(b, 1)) return 0;
+  b->sensFromRow0 = s0 ? 1 : 0;
+  if (s0) CUDA_OK(cudaMemcpy(b->d_sens, s0, sizeof(double) * (size_t)b->nsens * (size_t)b->om->neq, cudaMemcpyHostToDevice));
   return 1;
 }
 extern "C" int ODESBatch_setInitialTriggers(odesBatch_t *b, const int *trigger)
@@ -633,7 +644,7 @@ extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long
 static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream, int timed, int groupShift = -1)
 {
   OdesArgs a;
-  a.groupDone = NULL; a.hostFlags = NULL; a.groupShift = 0; a.pad2 = 0;
+  a.groupDone = NULL; a.hostFlags = NULL; a.groupShift = 0; a.pad2 = b->sensFromRow0;
   if (groupShift >= 0) { a.groupDone = b->d_groupDone; a.hostFlags = b->d_flags; a.groupShift = groupShift; }
   a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;

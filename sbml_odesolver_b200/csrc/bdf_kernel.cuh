@@ -80,7 +80,7 @@
 #define ODES_LOCKSTEP 0
 #endif
 #ifndef ODES_GESL_UNROLL
-#define ODES_GESL_UNROLL 8
+#define ODES_GESL_UNROLL 4            /* measured on MAPK (B200): 8 (full) 4.07 M, 4 4.17 M trajectories/s */
 #endif
 /* ODES_LOCKSTEP 2 re-aligns the warps of a block before every block of the pass as well */
 #ifndef ODES_ALIGN_MASK
@@ -210,7 +210,7 @@ struct OdesArgs {
      in mapped host memory and the host copies that group's results while the kernel is still integrating the rest */
   unsigned int *groupDone;     /* [groups] device counters, zeroed before the launch; NULL: no signalling */
   unsigned int *hostFlags;     /* [groups] mapped pinned host memory */
-  int groupShift, pad2;
+  int groupShift, pad2;        /* pad2 != 0: the initial sensitivities are read from row 0 of sens */
   double *sens;                /* [nsets][nout+1][NSENS][NEQ] forward sensitivities (warp kernel with NSENS > 0), or NULL */
 };
 #ifndef ODES_HOST_EMULATION

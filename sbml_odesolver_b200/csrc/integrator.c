@@ -25,11 +25,12 @@
 /* private plan entry points (batch.cu) */
 int ODESBatch_setTimeGrid(odesBatch_t *, int nout, const double *tpoints);
 int ODESBatch_setInitialTriggers(odesBatch_t *, const int *trigger);
+int ODESBatch_setInitialSensitivities(odesBatch_t *, const double *s0);
 
 static void drop_course(cvodeSolver_t *s)
 {
-  free(s->course); free(s->courseFired);
-  s->course = NULL; s->courseFired = NULL; s->courseLen = 0; s->courseFirst = 0; s->courseStatus = 0;
+  free(s->course); free(s->courseFired); free(s->courseSens);
+  s->course = NULL; s->courseFired = NULL; s->courseSens = NULL; s->courseLen = 0; s->courseFirst = 0; s->courseStatus = 0;
 }
 
 static int initialize_solver(integratorInstance_t *engine, cvodeData_t *data, cvodeSettings_t *opt, odeModel_t *om)
@@ -48,6 +49,15 @@ static int initialize_solver(integratorInstance_t *engine, cvodeData_t *data, cv
     results->time[0] = data->currenttime;
     for (i = 0; i < data->nvalues; i++) results->value[i][0] = data->value[i];
   }
+  /* forward sensitivities (IntegratorInstance_initializeSolver, src/integratorInstance.c:360-420): structures for the
+     selected parameters, current sensitivities 0 / 1, row 0 of the stored courses */
+  if (engine->os) { ODESense_free(engine->os); engine->os = NULL; }
+  if (opt->Sensitivity) {
+    engine->os = ODESense_create(om, opt);
+    if (!engine->os) return 0;
+  }
+  if (!CvodeData_initializeSensitivities(data, opt, om, engine->os)) return 0;
+  solver->nsens = engine->os ? engine->os->nsens : 0;
   engine->run++;
   engine->isValid = 0;
   engine->clockStarted = 0;
@@ -85,6 +95,7 @@ void IntegratorInstance_free(integratorInstance_t *engine)
   if (!engine) return;
   if (engine->solver) { drop_course(engine->solver); if (engine->solver->plan) ODESBatch_free(engine->solver->plan); free(engine->solver); }
   CvodeData_free(engine->data);
+  ODESense_free(engine->os);
   free(engine);
 }
 cvodeSettings_t *IntegratorInstance_getSettings(integratorInstance_t *engine) { return engine->opt; }
@@ -176,6 +187,14 @@ static int compute_course(integratorInstance_t *engine)
   for (i = 0, j = 0; i < nvalues; i++) if (i < om->neq || i >= om->neq + om->nass) values[j++] = data->value[i];
   rows = (double *)malloc((size_t)(nrem + 1) * (size_t)nvalues * sizeof(double));
   fired = (unsigned int *)malloc((size_t)(solver->nout + 2) * sizeof(unsigned int));
+  if (solver->nsens > 0) {                     /* the course continues from the current sensitivities (src/sensSolver.c:268-277) */
+    double *s0 = (double *)malloc((size_t)solver->nsens * (size_t)om->neq * sizeof(double));
+    int ok;
+    for (j = 0; j < solver->nsens; j++) for (i = 0; i < om->neq; i++) s0[(size_t)j * (size_t)om->neq + (size_t)i] = data->sensitivity[i][j];
+    ok = ODESBatch_setInitialSensitivities(solver->plan, s0);
+    free(s0);
+    if (!ok) { free(grid); free(values); free(rows); free(fired); return 0; }
+  }
   if (!ODESBatch_setTimeGrid(solver->plan, nrem, grid) || !ODESBatch_setInitialTriggers(solver->plan, data->trigger) ||
       !ODESBatch_setValues(solver->plan, 1, values) || !ODESBatch_integrate(solver->plan, 1) || !ODESBatch_synchronize(solver->plan) ||
       !ODESBatch_getTrajectory(solver->plan, 0, rows) || !ODESBatch_getStatus(solver->plan, 1, &st) ||
@@ -184,6 +203,10 @@ static int compute_course(integratorInstance_t *engine)
     return 0;
   }
   drop_course(solver);
+  if (solver->nsens > 0) {
+    solver->courseSens = (double *)malloc((size_t)(engine->opt->PrintStep + 1) * (size_t)solver->nsens * (size_t)om->neq * sizeof(double));
+    if (!ODESBatch_getSensitivities(solver->plan, 1, solver->courseSens)) { free(grid); free(values); free(rows); free(fired); return 0; }
+  }
   solver->course = rows; solver->courseFirst = solver->iout; solver->courseLen = nrem; solver->courseStatus = st;
   solver->courseFired = (int *)malloc((size_t)(nrem + 1) * sizeof(int));
   for (i = 0; i <= nrem; i++) solver->courseFired[i] = (int)fired[i];
@@ -220,6 +243,10 @@ int IntegratorInstance_updateData(integratorInstance_t *engine)
     results->nout = solver->iout;
     results->time[solver->iout] = solver->t;
     for (i = 0; i < data->nvalues; i++) results->value[i][solver->iout] = data->value[i];
+    if (results->sensitivity && data->sensitivity) {
+      int j;
+      for (i = 0; i < results->neq; i++) for (j = 0; j < results->nsens; j++) results->sensitivity[i][j][solver->iout] = data->sensitivity[i][j];
+    }
   }
   if (opt->SteadyState == 1 && IntegratorInstance_checkSteadyState(engine)) flag = 0;
   solver->iout++;
@@ -260,6 +287,11 @@ int IntegratorInstance_cvodeOneStep(integratorInstance_t *engine)
   }
   solver->t = solver->tout;
   for (i = 0; i < data->nvalues; i++) data->value[i] = solver->course[(size_t)row * (size_t)data->nvalues + (size_t)i];
+  if (solver->courseSens && data->sensitivity) {             /* IntegratorInstance_getForwardSens (src/sensSolver.c:108-140) */
+    int j, neq = engine->om->neq;
+    for (j = 0; j < solver->nsens; j++) for (i = 0; i < neq; i++)
+      data->sensitivity[i][j] = solver->courseSens[((size_t)row * (size_t)solver->nsens + (size_t)j) * (size_t)neq + (size_t)i];
+  }
   /* a fired event with re-initialisation was already handled inside the device course */
   return IntegratorInstance_updateData(engine);
 }
@@ -408,4 +440,48 @@ int IntegratorInstance_updateModel(integratorInstance_t *engine)
     else return 0;
   }
   return 1;
+}
+
+/* ----------------------------------------------------------- forward sensitivities (src/integratorInstance.c:687-790) */
+odeSense_t *IntegratorInstance_getSensitivityModel(integratorInstance_t *engine) { return engine->os; }
+int IntegratorInstance_getNsens(integratorInstance_t *engine) { return engine->os ? engine->os->nsens : 0; }
+double IntegratorInstance_getSensitivityByNum(integratorInstance_t *engine, int y, int p)
+{
+  if (!engine->os || !engine->data->sensitivity || y < 0 || y >= engine->om->neq || p < 0 || p >= engine->os->nsens) return 0.0;
+  return engine->data->sensitivity[y][p];
+}
+double IntegratorInstance_getSensitivity(integratorInstance_t *engine, variableIndex_t *y, variableIndex_t *s)
+{
+  int i;
+  if (!engine->os || !engine->data->sensitivity) { fprintf(stderr, "WARNING: sensitivity analysis has not been initialized\n"); return 0.0; }
+  if (y->index >= engine->om->neq) {
+    fprintf(stderr, "WARNING: ID is not a variable, no sensitivities can be calculated for %s \n", engine->om->names[y->index]);
+    return 0.0;
+  }
+  for (i = 0; i < engine->os->nsens && engine->os->index_sens[i] != s->index; i++) ;
+  if (i == engine->os->nsens) {
+    fprintf(stderr, "WARNING: No sensitivities have been calculated for requested ID %s\n", engine->om->names[s->index]);
+    return 0.0;
+  }
+  return engine->data->sensitivity[y->index][i];
+}
+char *IntegratorInstance_getSensVariableName(integratorInstance_t *engine, int i)
+{ return (engine->os && i >= 0 && i < engine->os->nsens) ? engine->om->names[engine->os->index_sens[i]] : NULL; }
+void IntegratorInstance_dumpYSensitivities(integratorInstance_t *engine, variableIndex_t *y)
+{
+  int j;
+  if (!engine->os || !engine->data->sensitivity || y->index >= engine->om->neq) { printf("WARNING: no sensitivities for %s\n", engine->om->names[y->index]); return; }
+  printf("%g ", engine->solver->t);
+  for (j = 0; j < engine->os->nsens; j++) printf("%g ", engine->data->sensitivity[y->index][j]);
+  printf("\n");
+}
+void IntegratorInstance_dumpPSensitivities(integratorInstance_t *engine, variableIndex_t *p)
+{
+  int i, j;
+  if (!engine->os || !engine->data->sensitivity) return;
+  for (j = 0; j < engine->os->nsens && engine->os->index_sens[j] != p->index; j++) ;
+  if (j == engine->os->nsens) { printf("WARNING: no sensitivities for %s\n", engine->om->names[p->index]); return; }
+  printf("%g ", engine->solver->t);
+  for (i = 0; i < engine->om->neq; i++) printf("%g ", engine->data->sensitivity[i][j]);
+  printf("\n");
 }

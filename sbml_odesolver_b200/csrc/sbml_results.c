@@ -97,6 +97,18 @@ void SBMLResults_dump(const SBMLResults_t *r)
 void SBMLResults_free(SBMLResults_t *r)
 {
   if (!r) return;
+  if (r->nsens > 0) {                          /* sensitivity courses hang off the species' time courses */
+    timeCourseArray_t *arrs[3]; int a, i, j;
+    arrs[0] = r->species; arrs[1] = r->compartments; arrs[2] = r->parameters;
+    for (a = 0; a < 3; a++) for (i = 0; arrs[a] && i < arrs[a]->num_val; i++) {
+      timeCourse_t *tc = arrs[a]->tc[i];
+      if (!tc || !tc->sensitivity) continue;
+      for (j = 0; j < r->nsens; j++) free(tc->sensitivity[j]);
+      free(tc->sensitivity); tc->sensitivity = NULL;
+    }
+    for (j = 0; j < r->nsens; j++) free(r->param[j]);
+    free(r->param);
+  }
   TimeCourse_free(r->time);
   TimeCourseArray_free(r->species); TimeCourseArray_free(r->compartments);
   TimeCourseArray_free(r->parameters); TimeCourseArray_free(r->fluxes);
@@ -213,7 +225,23 @@ SBMLResults_t *SBMLResults_fromIntegrator(Model_t *m, integratorInstance_t *ii)
   }
   free(row);
   ResultMap_free(map);
+  /* SBMLResults_createSens (src/odeSolver.c:545-575): parameter ids, and per ODE variable its sensitivity courses */
   r->nsens = 0;
+  if (cv->nsens > 0 && cv->sensitivity && data->os) {
+    int i, k;
+    r->nsens = cv->nsens;
+    r->param = (char **)calloc((size_t)cv->nsens, sizeof(char *));
+    for (j = 0; j < cv->nsens; j++) r->param[j] = sdup(om->names[data->os->index_sens[j]]);
+    for (i = 0; i < cv->neq; i++) {
+      timeCourse_t *tc = SBMLResults_getTimeCourse(r, om->names[i]);
+      if (!tc) continue;
+      tc->sensitivity = (double **)calloc((size_t)cv->nsens, sizeof(double *));
+      for (j = 0; j < cv->nsens; j++) {
+        tc->sensitivity[j] = (double *)calloc((size_t)(cv->nout + 1), sizeof(double));
+        for (k = 0; k <= cv->nout; k++) tc->sensitivity[j][k] = cv->sensitivity[i][j][k];
+      }
+    }
+  }
   return r;
 }
 

@@ -34,3 +34,19 @@ def test_integrator_instance_unit_tests_in_c(tmp_path):
     exe = _build(tmp_path, "test_integrator_kats")
     r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_sensitivity_unit_tests_in_c_host_part(tmp_path):
+    """unittest/test_cvodeData.c:131-215 (sensitivity result accessors, directional sensitivities) and the settings."""
+    exe = _build(tmp_path, "test_sens_kats")
+    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml"), "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+@pytest.mark.gpu
+def test_sensitivity_unit_tests_in_c(tmp_path):
+    """The fixture of unittest/test_sensSolver.c:14-62 (MAPK; MAPK, MAPK_P, K1, Ki; simultaneous) through
+    IntegratorInstance_cvodeOneStep and SBML_odeSolver."""
+    exe = _build(tmp_path, "test_sens_kats")
+    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
