@@ -380,7 +380,9 @@ static std::string build_source(odesBatch_t *b)
     /* measured on huang96 (B200): 8 warps per SM 113 k, 12 warps 145 k, 16 warps (128 registers, spills) 136 k trajectories/s;
        after the solver state left local memory (136 registers unconstrained): 12 warps 227 k, 16 warps (128 registers) 267 k */
     /* with sensitivities a lane carries 10 more vector elements per sensitivity: fewer resident warps, more registers */
-    b->minblocks = env_int("ODES_MINBLOCKS", b->nsens > 0 ? (b->nsens <= 2 ? 2 : 1) : (wpb == 4 ? 4 : 1)); b->maxBlocksPerSM = 32;
+    int slabs = 1;                            /* register slabs of the packed layout (bdf_warp_kernel.cuh: W_S) */
+    if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
+    b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[512];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
              env_int("ODES_FMAD", 0) ? "true" : "false", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
