@@ -100,6 +100,9 @@ double *ODESBatch_deviceSensitivities(odesBatch_t *);
    the kernel runs; chunk < 0: launches of -chunk sets, the copy of launch k-1 overlaps launch k */
 int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *results, int *status,
                       int chunk);
+/* ... with the forward sensitivities [nsets][nout+1][nsens][neq] streamed back as well (sens may be NULL) */
+int ODESBatch_runHostSens(odesBatch_t *, int nsets, const double *values, double *results, double *sens, int *status,
+                          int chunk);
 
 /* the same over all GPUs of the box: device k integrates the index range [k n / G, (k+1) n / G) of the caller's arrays
    (no collective; one plan and one host thread per device).  ndevices <= 0: all devices when every one gets at least
@@ -108,6 +111,13 @@ int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *re
 int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore,
                                 const int *storeIndex /* NULL: all values */, int nsets, const double *values,
                                 double *results, int *status, int ndevices);
+
+int ODESBatch_runHostAllDevicesSens(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore,
+                                    const int *storeIndex, int nsets, const double *values, double *results,
+                                    double *sens /* NULL or [nsets][nout+1][nsens][neq] */, int *status, int ndevices);
+/* one-shot entry with sensitivities: sens NULL or [nsets][nout+1][nsens][neq], nsens as IntegratorInstance_getNsens(ii) */
+int IntegratorInstance_integrateBatchSens(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
+                                          const double *values, double *out, double *sens, int *status);
 
 /* device utilities */
 int ODES_deviceCount(void);

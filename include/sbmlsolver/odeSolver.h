@@ -28,6 +28,8 @@ typedef struct batchResults {
   double *time;                  /* [nout] */
   double *value;                 /* [nsets][nout][nvalues] */
   int *status;                   /* [nsets] */
+  /* forward sensitivities when set->Sensitivity was on: sens[set][time][parameter][equation], else nsens == 0 */
+  int nsens, neq; char **sensParam; double *sens;
 } batchResults_t;
 
 varySettings_t *VarySettings_allocate(int nrparams, int nrdesignpoints);

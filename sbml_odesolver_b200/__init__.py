@@ -51,6 +51,11 @@ _SIGS = {
     "CvodeSettings_getSensitivity": (c_i, [c_p]),
     "ODESBatch_getNsens": (c_i, [c_p]), "ODESBatch_getSensIndex": (c_i, [c_p, c_i]), "ODESBatch_getSensitivities": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_deviceSensitivities": (c_p, [c_p]),
+    "ODESBatch_runHostSens": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_i]),
+    "ODESBatch_runHostAllDevicesSens": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i]),
+    "IntegratorInstance_integrateBatchSens": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "IntegratorInstance_getNsens": (c_i, [c_p]), "IntegratorInstance_getSensitivityByNum": (c_d, [c_p, c_i, c_i]),
+    "SBMLResults_getNumSens": (c_i, [c_p]), "SBMLResults_getSensParam": (c_s, [c_p, c_i]), "TimeCourse_getSensitivity": (c_d, [c_p, c_i, c_i]),
     "ODEModel_generateCUDASource": (c_p, [c_p, c_p, c_i, c_p, c_i, c_p, c_p]),
     "CvodeSettings_create": (c_p, []), "CvodeSettings_createWithTime": (c_p, [c_d, c_i]),
     "CvodeSettings_createWith": (c_p, [c_d, c_i, c_d, c_d] + [c_i] * 10), "CvodeSettings_free": (None, [c_p]),
@@ -304,11 +309,12 @@ class Batch:
         _check(lib().ODESBatch_getKernelInfo(self.h, *[C.byref(x) for x in v]), "ODESBatch_getKernelInfo")
         return dict(zip(("regs", "smem_bytes_per_block", "local_bytes_per_thread", "threads_per_block", "blocks_per_sm"), (x.value for x in v)))
 
-    def run_host(self, values, results=None, status=None, chunk=0):
+    def run_host(self, values, results=None, status=None, chunk=0, sens=None):
         v = np.ascontiguousarray(values, dtype=np.float64)
         n = v.shape[0]
-        _check(lib().ODESBatch_runHost(self.h, n, v.ctypes.data, None if results is None else results.ctypes.data,
-                                       None if status is None else status.ctypes.data, chunk), "ODESBatch_runHost")
+        _check(lib().ODESBatch_runHostSens(self.h, n, v.ctypes.data, None if results is None else results.ctypes.data,
+                                           None if sens is None else sens.ctypes.data,
+                                           None if status is None else status.ctypes.data, chunk), "ODESBatch_runHost")
 
     def close(self):
         if self.h:

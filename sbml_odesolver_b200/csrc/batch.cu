@@ -772,8 +772,13 @@ static int run_host_chunked(odesBatch_t *b, int nsets, const double *values, dou
   return 1;
 }
 extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
+{ return ODESBatch_runHostSens(b, nsets, values, results, NULL, status, chunk); }
+extern "C" int ODESBatch_runHostSens(odesBatch_t *b, int nsets, const double *values, double *results, double *sens, int *status, int chunk)
 {
+  if (sens && b->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the plan was created without sensitivity analysis"); return 0; }
+  if (sens && chunk < 0) chunk = -chunk;              /* sensitivities travel with the streamed pipeline only */
   if (!ODESBatch_reserve(b, nsets)) return 0;
+  const size_t srows = (size_t)(b->nout + 1) * (size_t)(b->nsens > 0 ? b->nsens : 0) * (size_t)b->om->neq;
   const size_t rows = (size_t)(b->nout + 1) * (size_t)b->nstore;
   const size_t need = (size_t)nsets * (size_t)(b->nvary > 0 ? b->nvary : 1);
   if (need > b->rowsCap) { cudaFree(b->d_rows); b->d_rows = NULL; CUDA_OK(cudaMalloc(&b->d_rows, need * sizeof(double))); b->rowsCap = need; }
@@ -816,6 +821,7 @@ extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values
         const size_t cnt = (size_t)(upto == ngroups ? n : upto * gsize) - (size_t)next * (size_t)gsize;
         if (results) CUDA_OK(cudaMemcpyAsync(results + s0 * rows, b->d_out + s0 * rows, sizeof(double) * cnt * rows, cudaMemcpyDeviceToHost, b->copyOut));
         if (status) CUDA_OK(cudaMemcpyAsync(status + s0, b->d_status + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, b->copyOut));
+        if (sens) CUDA_OK(cudaMemcpyAsync(sens + s0 * srows, b->d_sens + s0 * srows, sizeof(double) * cnt * srows, cudaMemcpyDeviceToHost, b->copyOut));
         next = upto;
       } else sched_yield();
     }
@@ -836,6 +842,9 @@ extern "C" void ODES_hostFree(void *p) { if (p) cudaFreeHost(p); }
    sets per device (ODES_DEVICES overrides), else one. */
 extern "C" int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex,
                                            int nsets, const double *values, double *results, int *status, int ndevices)
+{ return ODESBatch_runHostAllDevicesSens(om, opt, nvary, varyIndex, nstore, storeIndex, nsets, values, results, NULL, status, ndevices); }
+extern "C" int ODESBatch_runHostAllDevicesSens(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex,
+                                               int nsets, const double *values, double *results, double *sens, int *status, int ndevices)
 {
   int have = ODES_deviceCount();
   if (ndevices <= 0) {
@@ -849,13 +858,15 @@ extern "C" int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt,
   for (int k = 0; k < ndevices && ok; k++) { plans[(size_t)k] = ODESBatch_create(om, opt, nvary, varyIndex, nstore, storeIndex, k); if (!plans[(size_t)k]) ok = 0; }
   if (ok) {
     const size_t rows = (size_t)(opt->PrintStep + 1) * (size_t)plans[0]->nstore;
+    const size_t srows = (size_t)(opt->PrintStep + 1) * (size_t)(plans[0]->nsens > 0 ? plans[0]->nsens : 0) * (size_t)om->neq;
+    if (sens && plans[0]->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "sensitivities requested but opt->Sensitivity is off"); ok = 0; }
     std::vector<int> done((size_t)ndevices, 0);
     std::vector<std::thread> workers;
-    for (int k = 0; k < ndevices; k++) {
+    for (int k = 0; k < ndevices && ok; k++) {
       size_t lo = ((size_t)nsets * (size_t)k / (size_t)ndevices) & ~(size_t)31, hi = (k + 1 == ndevices) ? (size_t)nsets : (((size_t)nsets * (size_t)(k + 1) / (size_t)ndevices) & ~(size_t)31);
       workers.emplace_back([&, k, lo, hi]() {
-        done[(size_t)k] = (hi <= lo) ? 1 : ODESBatch_runHost(plans[(size_t)k], (int)(hi - lo), values + lo * (size_t)(nvary > 0 ? nvary : 0),
-                                                             results ? results + lo * rows : NULL, status ? status + lo : NULL, 0);
+        done[(size_t)k] = (hi <= lo) ? 1 : ODESBatch_runHostSens(plans[(size_t)k], (int)(hi - lo), values + lo * (size_t)(nvary > 0 ? nvary : 0),
+                                                                 results ? results + lo * rows : NULL, sens ? sens + lo * srows : NULL, status ? status + lo : NULL, 0);
       });
     }
     for (auto &w : workers) w.join();
@@ -868,13 +879,16 @@ extern "C" int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt,
 /* one-shot drop-in for the reference's batch loop */
 extern "C" int IntegratorInstance_integrateBatch(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
                                                  const double *values, double *out, int *status)
+{ return IntegratorInstance_integrateBatchSens(ii, nsets, nvary, vi, values, out, NULL, status); }
+extern "C" int IntegratorInstance_integrateBatchSens(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
+                                                     const double *values, double *out, double *sens, int *status)
 {
   if (!ii || nsets < 0) return -1;
   std::vector<int> idx;
   for (int j = 0; j < nvary; j++) idx.push_back(vi[j]->index);
   int failed = -1;
   std::vector<int> st((size_t)(nsets > 0 ? nsets : 1));
-  if (ODESBatch_runHostAllDevices(ii->om, ii->opt, nvary, idx.data(), 0, NULL, nsets, values, out, st.data(), 0)) {       /* out is already [nsets][nout+1][nvalues] */
+  if (ODESBatch_runHostAllDevicesSens(ii->om, ii->opt, nvary, idx.data(), 0, NULL, nsets, values, out, sens, st.data(), 0)) {       /* out is already [nsets][nout+1][nvalues] */
     failed = 0;
     for (int s = 0; s < nsets; s++) { if (st[(size_t)s] < 0) failed++; if (status) status[s] = st[(size_t)s]; }
   }

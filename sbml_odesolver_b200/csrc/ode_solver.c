@@ -111,6 +111,8 @@ void BatchResults_free(batchResults_t *r)
   int i;
   if (!r) return;
   for (i = 0; i < r->nvalues; i++) free(r->names[i]);
+  for (i = 0; i < r->nsens; i++) free(r->sensParam[i]);
+  free(r->sensParam); free(r->sens);
   free(r->names); free(r->time); free(r->value); free(r->status); free(r);
 }
 double BatchResults_getValue(const batchResults_t *r, int set, const char *name, int timestep)
@@ -153,7 +155,19 @@ static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varyS
       res->value = (double *)malloc((size_t)res->nout * (size_t)nvalues * (size_t)res->nsets * sizeof(double));
       res->status = (int *)calloc((size_t)(res->nsets > 0 ? res->nsets : 1), sizeof(int));
       /* all design points in one batched run, spread over the GPUs of the box when there are enough of them */
-      if (!ODESBatch_runHostAllDevices(om, set, vs->nrparams, idx, 0, NULL, res->nsets, rows, res->value, res->status, 0)) { BatchResults_free(res); res = NULL; }
+      if (set->Sensitivity) {           /* per design point what SBMLResults_createSens maps (src/odeSolver.c:545-575) */
+        odeSense_t *os;
+        if (set->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
+        os = ODESense_create(om, set);
+        if (os && os->nsens > 0) {
+          res->nsens = os->nsens; res->neq = om->neq;
+          res->sensParam = (char **)calloc((size_t)os->nsens, sizeof(char *));
+          for (i = 0; i < os->nsens; i++) res->sensParam[i] = sdup(om->names[os->index_sens[i]]);
+          res->sens = (double *)malloc((size_t)res->nsets * (size_t)res->nout * (size_t)os->nsens * (size_t)om->neq * sizeof(double));
+        }
+        ODESense_free(os);
+      }
+      if (!ODESBatch_runHostAllDevicesSens(om, set, vs->nrparams, idx, 0, NULL, res->nsets, rows, res->value, res->sens, res->status, 0)) { BatchResults_free(res); res = NULL; }
       free(rows);
       if (res && mapped) *mapped = SBMLResultsArray_fromBatch(m, om, res);
     }

@@ -280,6 +280,22 @@ SBMLResultsArray_t *SBMLResultsArray_fromBatch(Model_t *m, odeModel_t *om, const
     while (np > 1 && b->nvalues > 0 && v[(size_t)(np - 1) * (size_t)b->nvalues] != v[(size_t)(np - 1) * (size_t)b->nvalues]) np--;
     a->results[i] = SBMLResults_create(m, np);
     for (n = 0; n < np; n++) ResultMap_fill(map, a->results[i], n, b->time[n], v + (size_t)n * (size_t)b->nvalues, data);
+    if (b->nsens > 0 && b->sens) {             /* SBMLResults_createSens per design point (src/odeSolver.c:545-575) */
+      SBMLResults_t *r = a->results[i]; int j, e;
+      const double *sv = b->sens + (size_t)i * (size_t)b->nout * (size_t)b->nsens * (size_t)b->neq;
+      r->nsens = b->nsens;
+      r->param = (char **)calloc((size_t)b->nsens, sizeof(char *));
+      for (j = 0; j < b->nsens; j++) r->param[j] = sdup(b->sensParam[j]);
+      for (e = 0; e < b->neq; e++) {
+        timeCourse_t *tc = SBMLResults_getTimeCourse(r, om->names[e]);
+        if (!tc) continue;
+        tc->sensitivity = (double **)calloc((size_t)b->nsens, sizeof(double *));
+        for (j = 0; j < b->nsens; j++) {
+          tc->sensitivity[j] = (double *)calloc((size_t)np, sizeof(double));
+          for (n = 0; n < np; n++) tc->sensitivity[j][n] = sv[((size_t)n * (size_t)b->nsens + (size_t)j) * (size_t)b->neq + (size_t)e];
+        }
+      }
+    }
   }
   ResultMap_free(map);
   CvodeData_free(data);

@@ -17,7 +17,8 @@ import sbml_odesolver_b200 as so
 
 class BatchResults(C.Structure):
     _fields_ = [("nsets", C.c_int), ("nout", C.c_int), ("nvalues", C.c_int), ("names", C.c_void_p),
-                ("time", C.POINTER(C.c_double)), ("value", C.POINTER(C.c_double)), ("status", C.POINTER(C.c_int))]
+                ("time", C.POINTER(C.c_double)), ("value", C.POINTER(C.c_double)), ("status", C.POINTER(C.c_int)),
+                ("nsens", C.c_int), ("neq", C.c_int), ("sensParam", C.c_void_p), ("sens", C.POINTER(C.c_double))]
 
 
 def _flat(out, status, times):
@@ -26,7 +27,7 @@ def _flat(out, status, times):
     status = np.ascontiguousarray(status, dtype=np.int32)
     times = np.ascontiguousarray(times, dtype=np.float64)
     b = BatchResults(out.shape[0], out.shape[1], out.shape[2], None, times.ctypes.data_as(C.POINTER(C.c_double)),
-                     out.ctypes.data_as(C.POINTER(C.c_double)), status.ctypes.data_as(C.POINTER(C.c_int)))
+                     out.ctypes.data_as(C.POINTER(C.c_double)), status.ctypes.data_as(C.POINTER(C.c_int)), 0, 0, None, None)
     b._keep = (out, status, times)
     return b
 

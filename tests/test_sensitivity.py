@@ -208,3 +208,61 @@ def test_gpu_sensitivities_respect_the_conservation_laws_at_scale():
     assert (np.abs(pair[:, :, 0]) <= 1e-6 * scale[:, :, 0]).all()
     assert (np.abs(pair[:, :, 2]) <= 1e-6 * scale[:, :, 2]).all()
     assert (np.abs(pair[:, :, 1] - 1.0) <= 1e-6 * scale[:, :, 1]).all()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_host_entries_return_the_sensitivities():
+    """ODESBatch_runHostSens (streamed host pipeline), IntegratorInstance_integrateBatchSens (one-shot entry, all values
+    stored) and Model_odeSolverBatch (SBMLResults per design point) deliver the device-resident sensitivities."""
+    L = so.lib()
+    w = _case("mapk", nout=20)
+    m = w["model"]
+    vals = H.workload_values(w, 700, seed=4)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    n = b.set_values(vals)
+    b.integrate(n)
+    out, sens = b.results(n), b.sensitivities(n)
+    res = np.zeros((n, b.nrows, b.nstore)); hs = np.zeros((n, b.nrows, b.nsens, m.neq)); st = np.zeros(n, dtype=np.int32)
+    b.run_host(vals, res, st, chunk=256, sens=hs)
+    assert np.array_equal(hs, sens) and np.array_equal(np.transpose(res, (1, 2, 0)), out) and (st == 0).all()
+    b.close()
+    # one-shot entry through an integrator instance
+    ii = L.IntegratorInstance_create(m.om, w["opt"])
+    assert ii and L.IntegratorInstance_getNsens(ii) == 4
+    vis = (C.c_void_p * len(w["vary"]))(*[L.ODEModel_getVariableIndexByNum(m.om, i) for i in w["vary"]])
+    full = np.zeros((n, 21, m.nvalues)); hs2 = np.zeros_like(hs); st2 = np.zeros(n, dtype=np.int32)
+    v = np.ascontiguousarray(vals)
+    failed = L.IntegratorInstance_integrateBatchSens(ii, n, len(w["vary"]), vis, v.ctypes.data, full.ctypes.data, hs2.ctypes.data, st2.ctypes.data)
+    assert failed == 0 and np.array_equal(hs2, sens) and np.array_equal(full[:, :, :m.neq], np.transpose(out, (2, 0, 1)))
+    for p in vis:
+        L.VariableIndex_free(p)
+    L.IntegratorInstance_free(ii)
+
+
+@pytest.mark.gpu
+def test_model_odesolverbatch_maps_sensitivities_per_design_point():
+    L = so.lib()
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    opt = so.settings(100.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=REF_IDS)
+    vs = L.VarySettings_allocate(1, 3)
+    L.VarySettings_addParameter(vs, b"K1", None)
+    for x in (5.0, 10.0, 20.0):
+        arr = (C.c_double * 1)(x)
+        L.VarySettings_addDesignPoint(vs, arr)
+    res = L.Model_odeSolverBatch(m.sbml, opt, vs)
+    assert res and L.SBMLResultsArray_getNumResults(res) == 3
+    # the same design points through a plan
+    b = so.Batch(m, opt, [m.index("K1")], store=list(range(m.neq)))
+    b.set_values(np.array([[5.0], [10.0], [20.0]]))
+    b.integrate(3)
+    sens = b.sensitivities(3)
+    b.close()
+    for k in range(3):
+        r = L.SBMLResultsArray_getResults(res, k)
+        assert L.SBMLResults_getNumSens(r) == 4 and L.SBMLResults_getSensParam(r, 2) == b"K1"
+        tc = L.SBMLResults_getTimeCourse(r, b"MKKK_P")
+        got = np.array([[L.TimeCourse_getSensitivity(tc, j, t) for t in range(11)] for j in range(4)])
+        assert np.array_equal(got, sens[k, :, :, 1].T)
+    L.SBMLResultsArray_free(res)
+    L.VarySettings_free(vs)
