@@ -14,7 +14,12 @@
  * The model functions are the emitted host-C flavour (ODEModel_generateCSourceSens: ode_f, jacobi_f, sense_f = the
  * reference's compiled mode, src/odeModel.c:2673-2918, :2994-3100) loaded from a shared object.
  * There is no restated port behind this file: for the sensitivity row of SURVEY section 8(f) the checker is the
- * reference's own CVODES arithmetic.  Models with events are not handled here.
+ * reference's own CVODES arithmetic.
+ * Events (optional, om != NULL): examined at output times only, edge-triggered, in model order, exactly as in
+ * oracle/driver.c (src/integratorInstance.c:1029-1077); a fired event that changes a variable (or any value with
+ * ResetCvodeOnEvent) invalidates the solver, which is then re-initialised at the output time from the current values
+ * AND the current sensitivities (src/sensSolver.c:268-277: "yS are 0.0 or 1.0 in a new run or old values in case of
+ * events") with CVodeReInit + CVodeSensReInit.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -26,6 +31,7 @@
 #include "cvodes.h"
 #include "cvdense.h"
 #include "nvector_serial.h"
+#include "oracle.h"            /* odeModel_t and the independent AST interpreter, for the output-time event handling */
 
 typedef void (*c_ode_fn)(double t, const double *y, double *ydot, double *value);
 typedef void (*c_jac_fn)(double t, const double *y, double *J, double *value);
@@ -47,20 +53,48 @@ typedef struct {
   double *out, *sens; int *status, *stats;
   c_ode_fn f; c_jac_fn j; c_sens_fn s;
   int failed;
+  odeModel_t *om; int resetOnEvent, haltOnEvent; unsigned int *fired; const int *trigger0;
 } job_t;
+
+static void set_up_solver(void *mem, ctx_t *ctx, job_t *jb, double *p)
+{
+  CVodeSetFdata(mem, ctx);
+  CVodeSetMaxNumSteps(mem, jb->mxstep);
+  CVDense(mem, jb->neq);
+  CVDenseSetJacFn(mem, jac_cb, ctx);
+  CVodeSetSensRhs1Fn(mem, fs_cb);
+  CVodeSetSensFdata(mem, ctx);
+  CVodeSetSensParams(mem, p, NULL, NULL);
+  CVodeSetSensTolerances(mem, CV_EE, 0.0, NULL);
+  CVodeSetSensErrCon(mem, FALSE);
+}
+static void fold_stats(void *mem, long *tot)
+{
+  long v = 0;
+  CVodeGetNumSteps(mem, &v); tot[0] += v;
+  CVodeGetNumRhsEvals(mem, &v); tot[1] += v;
+  CVodeGetNumLinSolvSetups(mem, &v); tot[2] += v;
+  CVDenseGetNumJacEvals(mem, &v); tot[3] += v;
+  CVodeGetNumNonlinSolvIters(mem, &v); tot[4] += v;
+  CVodeGetNumNonlinSolvConvFails(mem, &v); tot[5] += v;
+  CVodeGetNumErrTestFails(mem, &v); tot[6] += v;
+  CVodeGetNumSensRhsEvals(mem, &v); tot[7] += v;
+}
 
 static void *run_range(void *arg)
 {
   job_t *jb = (job_t *)arg;
-  int neq = jb->neq, ns = jb->nsens, nout = jb->nout, s, i, k, is;
-  ctx_t ctx; void *mem = NULL; int created = 0;
+  int neq = jb->neq, ns = jb->nsens, nout = jb->nout, s, i, k, is, e;
+  ctx_t ctx; void *mem = NULL; int created = 0; long tot[8];
+  odeModel_t *om = jb->om;
+  int *trigger = (int *)calloc((size_t)((om && om->nevents > 0) ? om->nevents : 1), sizeof(int));
   N_Vector y = N_VNew_Serial(neq), abstol = N_VNew_Serial(neq);
   N_Vector *yS = N_VNewVectorArray_Serial(ns, neq);
   double *p = (double *)calloc((size_t)ns, sizeof(double));
   ctx.neq = neq; ctx.value = (double *)malloc((size_t)jb->nvalues * sizeof(double)); ctx.f = jb->f; ctx.j = jb->j; ctx.s = jb->s;
 
   for (s = jb->first; s < jb->last; s++) {
-    double t = jb->tpoints[0]; int flag = 0, iout;
+    double t = jb->tpoints[0]; int flag = 0, iout, halted = 0;
     double *rows = jb->out + (size_t)s * (size_t)(nout + 1) * (size_t)neq;
     double *srows = jb->sens + (size_t)s * (size_t)(nout + 1) * (size_t)ns * (size_t)neq;
     memcpy(ctx.value, jb->base, (size_t)jb->nvalues * sizeof(double));
@@ -80,56 +114,80 @@ static void *run_range(void *arg)
       flag = CVodeReInit(mem, f_cb, t, y, CV_SV, jb->rtol, abstol);
       if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, CV_SIMULTANEOUS, yS);
     }
-    if (flag == CV_SUCCESS) {
-      CVodeSetFdata(mem, &ctx);
-      CVodeSetMaxNumSteps(mem, jb->mxstep);
-      CVDense(mem, neq);
-      CVDenseSetJacFn(mem, jac_cb, &ctx);
-      CVodeSetSensRhs1Fn(mem, fs_cb);
-      CVodeSetSensFdata(mem, &ctx);
-      CVodeSetSensParams(mem, p, NULL, NULL);
-      CVodeSetSensTolerances(mem, CV_EE, 0.0, NULL);
-      CVodeSetSensErrCon(mem, FALSE);
-    }
+    if (flag == CV_SUCCESS) set_up_solver(mem, &ctx, jb, p);
     jb->status[s] = 0;
     iout = 1;
+    for (i = 0; i < 8; i++) tot[i] = 0;
+    if (om) for (e = 0; e < om->nevents; e++) trigger[e] = jb->trigger0[e];
+    if (jb->fired) jb->fired[(size_t)s * (size_t)(nout + 1)] = 0;
     if (flag == CV_SUCCESS) {
       for (; iout <= nout; iout++) {
-        realtype tret = 0;
+        realtype tret = 0; unsigned int firedmask = 0; int isValid = 1;
         flag = CVode(mem, jb->tpoints[iout], y, &tret, CV_NORMAL);
         if (flag < 0) break;
         flag = CVodeGetSens(mem, tret, yS);
         if (flag < 0) break;
+        if (om && om->nevents > 0) {                 /* oracle/driver.c: rules before events, edge-triggered firing */
+          double *value = ctx.value; int jj;
+          for (i = 0; i < neq; i++) value[i] = NV_Ith_S(y, i);
+          for (i = 0; i < om->nassbeforeevents; i++) { nonzeroElem_t *o = om->assignmentsBeforeEvents[i]; value[o->i] = oracle_eval(o->ij, value, tret); }
+          for (e = 0; e < om->nevents; e++) {
+            if (trigger[e] == 0) {
+              if (oracle_eval(om->event[e], value, tret)) {
+                firedmask |= (1u << e);
+                trigger[e] = 1;
+                for (jj = 0; jj < om->neventAss[e]; jj++) {
+                  double r = oracle_eval(om->eventAssignment[e][jj], value, tret);
+                  int idx = om->eventIndex[e][jj], a;
+                  if (idx >= neq && idx < neq + om->nass) continue;
+                  value[idx] = r;
+                  if (idx < neq || jb->resetOnEvent) isValid = 0;
+                  for (a = 0; a < om->nass; a++) { nonzeroElem_t *o = om->assignmentOrder[a]; value[o->i] = oracle_eval(o->ij, value, tret); }
+                }
+              }
+            } else if (!oracle_eval(om->event[e], value, tret)) trigger[e] = 0;
+          }
+          for (i = 0; i < neq; i++) NV_Ith_S(y, i) = value[i];
+        }
         for (i = 0; i < neq; i++) rows[(size_t)iout * (size_t)neq + (size_t)i] = NV_Ith_S(y, i);
         for (is = 0; is < ns; is++) for (i = 0; i < neq; i++)
           srows[((size_t)iout * (size_t)ns + (size_t)is) * (size_t)neq + (size_t)i] = NV_Ith_S(yS[is], i);
+        if (jb->fired) jb->fired[(size_t)s * (size_t)(nout + 1) + (size_t)iout] = firedmask;
+        if (firedmask && jb->haltOnEvent) { iout++; halted = 1; break; }
+        if (!isValid && iout < nout) {               /* lazy re-creation at the next step in the reference; same arithmetic */
+          fold_stats(mem, tot);
+          flag = CVodeReInit(mem, f_cb, tret, y, CV_SV, jb->rtol, abstol);
+          if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, CV_SIMULTANEOUS, yS);
+          if (flag != CV_SUCCESS) { iout++; break; }
+          set_up_solver(mem, &ctx, jb, p);
+        }
       }
     }
-    if (flag < 0) {
-      jb->status[s] = flag; jb->failed++;
+    if (flag < 0 || halted) {
+      if (flag < 0) { jb->status[s] = flag; jb->failed++; }
       for (; iout <= nout; iout++) {
+        if (jb->fired) jb->fired[(size_t)s * (size_t)(nout + 1) + (size_t)iout] = 0;
         for (i = 0; i < neq; i++) rows[(size_t)iout * (size_t)neq + (size_t)i] = NAN;
         for (i = 0; i < ns * neq; i++) srows[(size_t)iout * (size_t)ns * (size_t)neq + (size_t)i] = NAN;
       }
     }
     if (jb->stats && mem) {
-      long v = 0; int *st = jb->stats + (size_t)s * 8;
-      CVodeGetNumSteps(mem, &v); st[0] = (int)v;
-      CVodeGetNumRhsEvals(mem, &v); st[1] = (int)v;
-      CVodeGetNumLinSolvSetups(mem, &v); st[2] = (int)v;
-      CVDenseGetNumJacEvals(mem, &v); st[3] = (int)v;
-      CVodeGetNumNonlinSolvIters(mem, &v); st[4] = (int)v;
-      CVodeGetNumNonlinSolvConvFails(mem, &v); st[5] = (int)v;
-      CVodeGetNumErrTestFails(mem, &v); st[6] = (int)v;
-      CVodeGetNumSensRhsEvals(mem, &v); st[7] = (int)v;
+      int *st = jb->stats + (size_t)s * 8;
+      fold_stats(mem, tot);
+      for (i = 0; i < 8; i++) st[i] = (int)tot[i];
     }
   }
   if (mem) CVodeFree(mem);
   N_VDestroy_Serial(y); N_VDestroy_Serial(abstol); N_VDestroyVectorArray_Serial(yS, ns);
-  free(ctx.value); free(p);
+  free(ctx.value); free(p); free(trigger);
   return NULL;
 }
 
+int refcvs_integrate_batch_events(const char *compiled_so, int neq, int nvalues, int nsens, const int *sens_variable,
+                                  const double *base, int nsets, int nvary, const int *vary_idx, const double *values,
+                                  const double *tpoints, int nout, double rtol, double atol, long mxstep,
+                                  double *out, double *sens, int *status, int *stats, int nthreads,
+                                  odeModel_t *om, int resetOnEvent, int haltOnEvent, const int *trigger0, unsigned int *fired);
 /* out [nsets][nout+1][neq], sens [nsets][nout+1][nsens][neq], status [nsets], stats [nsets][8] (nst, nfe, nsetups, nje,
    nni, ncfn, netf, nfSe) or NULL.  sens_variable[is]: equation index of an initial-condition sensitivity, or -1.
    Returns the number of failed sets, -1 on a set-up error. */
@@ -137,6 +195,17 @@ int refcvs_integrate_batch(const char *compiled_so, int neq, int nvalues, int ns
                            const double *base, int nsets, int nvary, const int *vary_idx, const double *values,
                            const double *tpoints, int nout, double rtol, double atol, long mxstep,
                            double *out, double *sens, int *status, int *stats, int nthreads)
+{
+  return refcvs_integrate_batch_events(compiled_so, neq, nvalues, nsens, sens_variable, base, nsets, nvary, vary_idx, values, tpoints, nout, rtol, atol,
+                                       mxstep, out, sens, status, stats, nthreads, NULL, 0, 0, NULL, NULL);
+}
+/* the same with the model's events handled at the output times (om from libodes_b200.so, initial trigger flags from the
+   plan); fired: NULL or [nsets][nout+1] event bit masks */
+int refcvs_integrate_batch_events(const char *compiled_so, int neq, int nvalues, int nsens, const int *sens_variable,
+                                  const double *base, int nsets, int nvary, const int *vary_idx, const double *values,
+                                  const double *tpoints, int nout, double rtol, double atol, long mxstep,
+                                  double *out, double *sens, int *status, int *stats, int nthreads,
+                                  odeModel_t *om, int resetOnEvent, int haltOnEvent, const int *trigger0, unsigned int *fired)
 {
   void *so = dlopen(compiled_so, RTLD_NOW | RTLD_LOCAL);
   job_t *jobs; pthread_t *th; int k, failed = 0;
@@ -155,6 +224,7 @@ int refcvs_integrate_batch(const char *compiled_so, int neq, int nvalues, int ns
     jb->vary_idx = vary_idx; jb->sens_variable = sens_variable; jb->values = values; jb->base = base; jb->tpoints = tpoints;
     jb->rtol = rtol; jb->atol = atol; jb->out = out; jb->sens = sens; jb->status = status; jb->stats = stats;
     jb->f = f; jb->j = j; jb->s = s;
+    jb->om = om; jb->resetOnEvent = resetOnEvent; jb->haltOnEvent = haltOnEvent; jb->trigger0 = trigger0; jb->fired = fired;
     if (nthreads == 1) run_range(jb); else pthread_create(&th[k], NULL, run_range, jb);
   }
   for (k = 0; k < nthreads; k++) { if (nthreads > 1) pthread_join(th[k], NULL); failed += jobs[k].failed; }

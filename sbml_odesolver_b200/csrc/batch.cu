@@ -446,7 +446,6 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
     if (!(opt->UseJacobian && om->jacobian)) why = "forward sensitivities need the analytic Jacobian";
     else if (opt->SensMethod != 0) why = "the batched kernel implements the simultaneous corrector (SensMethod 0) only";
     else if (om->neq < 1 || om->neq > 32) why = "forward sensitivities are implemented for 1..32 equations (one trajectory per warp)";
-    else if (om->nevents > 0) why = "forward sensitivities with events are not supported by the batched kernel";
     if (!why) {
       b->os = ODESense_create(om, opt);
       if (!b->os || !b->os->sensitivity) why = "the parametric matrix could not be constructed";

@@ -93,6 +93,7 @@ def sens_ref_run(model, opt, batch, vary, values, tpoints, mxstep, rtol, atol, t
     model functions.  Returns dict(out[nsets][nout+1][neq], sens[nsets][nout+1][nsens][neq], status, stats[nsets][8])."""
     global _refs
     if _refs is None:
+        oracle()                                          # liboracle.so (AST interpreter for the events) first
         _refs = C.CDLL(REFS_LIB)
         _refs.refcvs_integrate_batch.restype = C.c_int
     path = compile_c_model(model, tag, opt)
@@ -108,14 +109,21 @@ def sens_ref_run(model, opt, batch, vary, values, tpoints, mxstep, rtol, atol, t
     sens = np.zeros((nsets, nout + 1, ns, neq))
     status = np.zeros(nsets, dtype=np.int32)
     stats = np.zeros((nsets, 8), dtype=np.int32)
-    r = _refs.refcvs_integrate_batch(path.encode(), C.c_int(neq), C.c_int(model.nvalues), C.c_int(ns), C.c_void_p(sens_var.ctypes.data),
-                                     C.c_void_p(base.ctypes.data), C.c_int(nsets), C.c_int(len(vary)), C.c_void_p(vary.ctypes.data),
-                                     C.c_void_p(values.ctypes.data), C.c_void_p(tp.ctypes.data), C.c_int(nout), C.c_double(rtol), C.c_double(atol),
-                                     C.c_long(mxstep), C.c_void_p(out.ctypes.data), C.c_void_p(sens.ctypes.data), C.c_void_p(status.ctypes.data),
-                                     C.c_void_p(stats.ctypes.data), C.c_int(threads))
+    fired = np.zeros((nsets, nout + 1), dtype=np.uint32)
+    _, trig0 = batch.base_values()
+    trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
+    L = so.lib()
+    _refs.refcvs_integrate_batch_events.restype = C.c_int
+    r = _refs.refcvs_integrate_batch_events(path.encode(), C.c_int(neq), C.c_int(model.nvalues), C.c_int(ns), C.c_void_p(sens_var.ctypes.data),
+                                            C.c_void_p(base.ctypes.data), C.c_int(nsets), C.c_int(len(vary)), C.c_void_p(vary.ctypes.data),
+                                            C.c_void_p(values.ctypes.data), C.c_void_p(tp.ctypes.data), C.c_int(nout), C.c_double(rtol), C.c_double(atol),
+                                            C.c_long(mxstep), C.c_void_p(out.ctypes.data), C.c_void_p(sens.ctypes.data), C.c_void_p(status.ctypes.data),
+                                            C.c_void_p(stats.ctypes.data), C.c_int(threads), C.c_void_p(model.om),
+                                            C.c_int(L.CvodeSettings_getResetCvodeOnEvent(opt)), C.c_int(L.CvodeSettings_getHaltOnEvent(opt)),
+                                            C.c_void_p(trig0.ctypes.data), C.c_void_p(fired.ctypes.data))
     if r < 0:
         raise RuntimeError("sensitivity reference failed to set up")
-    return dict(out=out, sens=sens, status=status, stats=stats)
+    return dict(out=out, sens=sens, status=status, stats=stats, fired=fired)
 
 
 class Emu:

@@ -23,6 +23,7 @@ CASES = {
     "repressilator": dict(ids=["alpha", "beta", "x1"], nout=100),
     "huang": dict(ids=["r_r1a_a1", "KKK", "r_r10b_k10"], nout=None),
     "goodwin": dict(ids=None, nout=20),                        # default: every constant of the model
+    "events": dict(ids=["S1", "compartment", "S2"], nout=None),  # events re-initialise the solver from the current sensitivities
 }
 needs_ref = pytest.mark.skipif(not H.have_sens_ref(), reason="oracle/_ref/libcvodes_ref.so not built")
 
@@ -76,7 +77,7 @@ def test_emitted_sense_function_follows_the_reference_generator():
 
 
 @needs_ref
-@pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6)])
+@pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6), ("events", 24)])
 def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
     w = _case(name)
     m = w["model"]
@@ -89,6 +90,7 @@ def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets
     ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag=name + "_sens")
     b.close()
     assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(got["fired"].T, ref["fired"]) and (name != "events" or ref["fired"].any())
     assert np.array_equal(got["stats"].T, ref["stats"][:, :7])                       # same steps, Newton and Jacobian decisions
     assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"])         # bit for bit
     assert np.array_equal(got["sens"], ref["sens"])
@@ -148,10 +150,6 @@ def test_sensitivities_agree_with_central_differences():
 
 
 def test_unsupported_sensitivity_configurations_fail_loudly():
-    m = so.Model(H.model_path("two_events_one_assignment.xml"))
-    opt = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1)
-    with pytest.raises(so.OdesError, match="events"):
-        so.Batch(m, opt, [m.index("S1")])
     m2, vary, _ = H.mapk_scan_model()
     opt2 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["K1"])
     so.lib().CvodeSettings_setSensMethod(opt2, 1)
@@ -168,7 +166,7 @@ def test_unsupported_sensitivity_configurations_fail_loudly():
 # ------------------------------------------------------------------------------------------------ GPU tier
 @pytest.mark.gpu
 @needs_ref
-@pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64)])
+@pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64), ("events", 512)])
 def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
     w = _case(name)
     m = w["model"]
@@ -177,11 +175,13 @@ def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
     n = b.set_values(vals)
     ms = b.integrate(n)
     out, sens, status, stats = b.results(n), b.sensitivities(n), b.status(n), b.stats(n).T
+    fired = b.event_log(n).T
     tp = H.tpoints(w["opt"], w["nout"])
     ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=8, tag=name + "_sens")
     print(name, "nsens", b.nsens, f"{n / ms * 1e3:.0f} trajectories/s", b.kernel_info())
     b.close()
     assert np.array_equal(status, ref["status"])
+    assert np.array_equal(fired, ref["fired"])
     assert np.array_equal(stats, ref["stats"][:, :7])
     assert H.parity(sens, ref["sens"], w["rtol"], w["atol"]) <= 1.0                  # the gate
     assert np.array_equal(np.transpose(out, (2, 0, 1)), ref["out"], equal_nan=True)  # and bit for bit
