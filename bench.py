@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--sets", type=int, default=1_000_000, help="trajectories per GPU per step")
+    ap.add_argument("--sets", type=int, default=0, help="trajectories per GPU per step (default 10^6; 10^5 with --sens)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mapk", choices=["mapk", "repressilator", "goodwin", "huang"],
                     help="mapk = the headline configuration (BASELINE configs[1]); the others are the parity-test configurations, for profiles/")
@@ -184,7 +184,11 @@ def main():
     ap.add_argument("--cpu-sets", type=int, default=0, help="sample size of the cpu_baseline leg (default: scaled to the core count)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sens", default="", help="forward sensitivities (SURVEY 8f rank 4): comma-separated ids, or 'all' for every constant; "
+                                               "not the headline -- a line for profiles/ with the vendored CVODES timed beside it")
     args = ap.parse_args()
+    if args.sets <= 0:
+        args.sets = 100_000 if args.sens else 1_000_000
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,7 +221,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    w = H.workload(args.workload)
+    sens_ids = None if args.sens in ("", "all") else args.sens.split(",")
+    w = H.workload(args.workload, sensitivity=1, sens_ids=sens_ids) if args.sens else H.workload(args.workload)
     m, nv, n = w["model"], len(w["vary"]), args.sets
     store = list(range(m.neq))
     b = so.Batch(m, w["opt"], w["vary"], store=store, device=local)
@@ -265,15 +270,21 @@ def main():
         vals = np.ctypeslib.as_array(C.cast(hv, C.POINTER(C.c_double)), shape=(n, nv))
         res = np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_double)), shape=(n, b.nrows, b.nstore))     # [set][row][value]
         hst = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_int)), shape=(n,))
+        hsens, hsp = None, None
+        if b.nsens:
+            hsp = L.ODES_hostAlloc(n * b.nrows * b.nsens * m.neq * 8)
+            if not hsp:
+                raise SystemExit("bench.py: pinned host allocation failed")
+            hsens = np.ctypeslib.as_array(C.cast(hsp, C.POINTER(C.c_double)), shape=(n, b.nrows, b.nsens, m.neq))
         chunk = 0                                                  # one launch; finished groups of sets stream back while it runs
         vals[:] = b.get_values(n)                                  # this step's device-generated sets, as host rows
         for _ in range(2):
-            b.run_host(vals, res, hst, chunk=chunk)
+            b.run_host(vals, res, hst, chunk=chunk, sens=hsens)
         launches1 = L.ODESBatch_getNumLaunches(b.h)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            b.run_host(vals, res, hst, chunk=chunk)
+            b.run_host(vals, res, hst, chunk=chunk, sens=hsens)
         dt = time.perf_counter() - t0
         barrier()
         dt = max_over_ranks(dt)
@@ -282,9 +293,12 @@ def main():
         # the host-buffer path must deliver the device-resident results (same seeded sets)
         probe = b.results(min(n, 4096))
         assert np.array_equal(probe, np.transpose(res[:probe.shape[2]], (1, 2, 0))), "host path and device-resident path disagree"
-        e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * nv * 8, "d2h_bytes_per_step": rows * n * 8 + n * 4,
+        if hsens is not None:
+            assert np.array_equal(hsens[:256], b.sensitivities(256)), "host path and device-resident sensitivities disagree"
+        e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * nv * 8,
+               "d2h_bytes_per_step": rows * n * 8 + n * 4 + (n * b.nrows * b.nsens * m.neq * 8 if b.nsens else 0),
                "ms_per_step": 1e3 * dt / args.steps, "chunk": chunk, "gpu_launches": e2e_launches}
-        L.ODES_hostFree(hv); L.ODES_hostFree(hr); L.ODES_hostFree(hs)
+        L.ODES_hostFree(hv); L.ODES_hostFree(hr); L.ODES_hostFree(hs); L.ODES_hostFree(hsp)
 
     # ---------------- CPU baseline on the same seeded sets (rank 0, N = 1 only) ----------------
     cpu = None
@@ -292,34 +306,57 @@ def main():
         cores = os.cpu_count() or 1
         kind = "reference" if H.have_ref() else "port"
         ns = args.cpu_sets or max(2048, min(4000 * cores, 400_000, n))
+        if b.nsens:
+            ns = args.cpu_sets or max(512, min(600 * cores, n))
         vals = b.get_values(ns)
-        cso = H.compile_c_model(m, args.workload)
-        t0 = time.perf_counter()
-        ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
-        dt = time.perf_counter() - t0
+        if b.nsens:                                                # the reference's vendored CVODES (oracle/_ref/libcvodes_ref.so)
+            if not H.have_sens_ref():
+                raise SystemExit("bench.py: oracle/_ref/libcvodes_ref.so is missing (build() makes it where /root/reference exists)")
+            tp = H.tpoints(w["opt"], w["nout"])
+            H.sens_ref_run(m, w["opt"], b, w["vary"], vals[:32], tp, 10000, w["rtol"], w["atol"], threads=cores, tag=args.workload + "_sens")
+            t0 = time.perf_counter()
+            ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=cores, tag=args.workload + "_sens")
+            dt = time.perf_counter() - t0
+            ref["stats"] = ref["stats"][:, :7]
+            sens_same = bool(np.array_equal(b.sensitivities(ns), ref["sens"], equal_nan=True))
+        else:
+            cso = H.compile_c_model(m, args.workload)
+            t0 = time.perf_counter()
+            ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
+            dt = time.perf_counter() - t0
+            sens_same = None
         gpu = b.results(ns)
         rep = H.parity_report(gpu, np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), stats[:, :ns].T, ref["stats"], w["rtol"], w["atol"])
         cpu = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"first {ns} sets of this step's batch, {cores} threads, vendored CVODE 2.3.0 + emitted C rhs/Jacobian, gcc -O2 -ffp-contract=off",
+               "sample": f"first {ns} sets of this step's batch, {cores} threads, vendored {'CVODES 2.3.0 + emitted C rhs/Jacobian/sense_f' if b.nsens else 'CVODE 2.3.0 + emitted C rhs/Jacobian'}, gcc -O2 -ffp-contract=off",
+               "sensitivities_bit_identical_on_sample": sens_same,
                "parity_on_sample": {"frac_within_10rtol": rep["frac_within"], "frac_same_step_sequence": rep["frac_same_path"], "max_ratio": rep["max_ratio"]},
                "oracle_mean_stats": dict(zip("nst nfe nsetups nje nni ncfn netf".split(), [float(x) for x in ref["stats"].mean(axis=0)]))}
 
     if rank == 0:
         Ff, FJ = count_ops(b.source())
         F = algorithmic_flops(m.neq, Ff, FJ, mean_stats)
+        if b.nsens:
+            # the simultaneous corrector adds, per right-hand-side evaluation, one Jacobian and per sensitivity a sparse
+            # matrix-vector product (2 nnz; the parametric term is neglected), per Newton iteration one more solve per
+            # sensitivity, per step the history operations of every sensitivity vector
+            nnz, nS, nn, qb = len(m.jacobian_structure()), b.nsens, m.neq, 4.0
+            F += mean_stats["nfe"] * (FJ + nS * 2 * nnz) + mean_stats["nni"] * nS * (2 * nn * nn + 6 * nn) + mean_stats["nst"] * nS * nn * (qb * (qb + 1) / 2 + 2 * (qb + 1) + 10)
         achieved = F * n / (kernel_ms * 1e-3) / 1e12
-        out_bytes = 8 * b.nrows * b.nstore + 8 * nv
+        out_bytes = 8 * b.nrows * b.nstore + 8 * nv + 8 * b.nrows * b.nsens * m.neq
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")
-        if os.path.exists(prof) and args.workload == "mapk":
+        if os.path.exists(prof) and args.workload == "mapk" and not b.nsens:
             pj = json.load(open(prof))
             if pj.get("sets") and pj.get("dram_bytes") is not None:
                 traffic = pj["dram_bytes"] / pj["sets"] * n        # per launch of this size, scaled from the capture
         info = b.kernel_info()
         workload_text = ("MAPK.xml parameter scan (BASELINE configs[1]): 21 kinetic constants x 2^U(-1,1), rtol 1e-6 atol 1e-9, t=0..1000, 100 output points, 8 species stored"
-                         if args.workload == "mapk" else
+                         if args.workload == "mapk" and not b.nsens else
+                         f"{args.workload} + {b.nsens} forward sensitivities ({args.sens}; SURVEY 8f rank 4, not the headline): CVODES simultaneous corrector, {nv} varied values, rtol 1e-6 atol 1e-9, t=0..{w['end']:g}, {w['nout']} output points, {m.neq} variables and {b.nsens} x {m.neq} sensitivities stored"
+                         if b.nsens else
                          f"{args.workload} (BASELINE parity configuration, not the headline): {nv} varied values, rtol 1e-6 atol 1e-9, t=0..{w['end']:g}, {w['nout']} output points, {m.neq} variables stored")
-        line = {"metric": METRIC if args.workload == "mapk" else f"trajectories/sec ({args.workload}, rtol 1e-6)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        line = {"metric": METRIC if args.workload == "mapk" and not b.nsens else f"trajectories/sec ({args.workload}{' + %d sensitivities' % b.nsens if b.nsens else ''}, rtol 1e-6)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_text,
                            "sets_per_gpu": n, "nvary": nv, "seed": SEED, "sharding": f"range x{world}, no collective", "host_affinity": numa,
