@@ -37,6 +37,9 @@ typedef void (*c_ode_fn)(double t, const double *y, double *ydot, double *value)
 typedef void (*c_jac_fn)(double t, const double *y, double *J, double *value);
 typedef void (*c_sens_fn)(int iS, double t, const double *y, const double *yS, double *ySdot, double *value);
 
+/* SensMethod of the next batch calls (0 simultaneous, 1 staggered); set by the test helper before a run */
+int refcvs_sens_method = 0;
+
 typedef struct { int neq; double *value; c_ode_fn f; c_jac_fn j; c_sens_fn s; } ctx_t;
 
 static void f_cb(realtype t, N_Vector y, N_Vector ydot, void *f_data)
@@ -54,6 +57,7 @@ typedef struct {
   c_ode_fn f; c_jac_fn j; c_sens_fn s;
   int failed;
   odeModel_t *om; int resetOnEvent, haltOnEvent; unsigned int *fired; const int *trigger0;
+  int ism;                       /* CV_SIMULTANEOUS or CV_STAGGERED (cvodeSettings_t.SensMethod 0 / 1, src/sensSolver.c:286-290) */
 } job_t;
 
 static void set_up_solver(void *mem, ctx_t *ctx, job_t *jb, double *p)
@@ -108,11 +112,11 @@ static void *run_range(void *arg)
       mem = CVodeCreate(CV_BDF, CV_NEWTON);
       CVodeSetErrFile(mem, NULL);
       flag = CVodeMalloc(mem, f_cb, t, y, CV_SV, jb->rtol, abstol);
-      if (flag == CV_SUCCESS) flag = CVodeSensMalloc(mem, ns, CV_SIMULTANEOUS, yS);
+      if (flag == CV_SUCCESS) flag = CVodeSensMalloc(mem, ns, jb->ism, yS);
       created = 1;
     } else {
       flag = CVodeReInit(mem, f_cb, t, y, CV_SV, jb->rtol, abstol);
-      if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, CV_SIMULTANEOUS, yS);
+      if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, jb->ism, yS);
     }
     if (flag == CV_SUCCESS) set_up_solver(mem, &ctx, jb, p);
     jb->status[s] = 0;
@@ -157,7 +161,7 @@ static void *run_range(void *arg)
         if (!isValid && iout < nout) {               /* lazy re-creation at the next step in the reference; same arithmetic */
           fold_stats(mem, tot);
           flag = CVodeReInit(mem, f_cb, tret, y, CV_SV, jb->rtol, abstol);
-          if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, CV_SIMULTANEOUS, yS);
+          if (flag == CV_SUCCESS) flag = CVodeSensReInit(mem, jb->ism, yS);
           if (flag != CV_SUCCESS) { iout++; break; }
           set_up_solver(mem, &ctx, jb, p);
         }
@@ -225,6 +229,7 @@ int refcvs_integrate_batch_events(const char *compiled_so, int neq, int nvalues,
     jb->rtol = rtol; jb->atol = atol; jb->out = out; jb->sens = sens; jb->status = status; jb->stats = stats;
     jb->f = f; jb->j = j; jb->s = s;
     jb->om = om; jb->resetOnEvent = resetOnEvent; jb->haltOnEvent = haltOnEvent; jb->trigger0 = trigger0; jb->fired = fired;
+    jb->ism = refcvs_sens_method == 1 ? CV_STAGGERED : CV_SIMULTANEOUS;
     if (nthreads == 1) run_range(jb); else pthread_create(&th[k], NULL, run_range, jb);
   }
   for (k = 0; k < nthreads; k++) { if (nthreads > 1) pthread_join(th[k], NULL); failed += jobs[k].failed; }

@@ -114,6 +114,13 @@ def sens_ref_run(model, opt, batch, vary, values, tpoints, mxstep, rtol, atol, t
     trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
     L = so.lib()
     _refs.refcvs_integrate_batch_events.restype = C.c_int
+
+    class _Opt(C.Structure):                     # head of cvodeSettings_t up to SensMethod (include/sbmlsolver/integratorSettings.h)
+        _fields_ = [("Time", C.c_double), ("PrintStep", C.c_int), ("StepResolution", C.c_int), ("TimePoints", C.c_void_p), ("Indefinitely", C.c_int),
+                    ("Error", C.c_double), ("RError", C.c_double), ("Mxstep", C.c_int), ("DetectNegState", C.c_int),
+                    ("CvodeMethod", C.c_int), ("IterMethod", C.c_int), ("MaxOrder", C.c_int), ("ResetCvodeOnEvent", C.c_int), ("SetTStop", C.c_int),
+                    ("Sensitivity", C.c_int), ("sensIDs", C.c_void_p), ("nsens", C.c_int), ("SensMethod", C.c_int)]
+    C.c_int.in_dll(_refs, "refcvs_sens_method").value = C.cast(opt, C.POINTER(_Opt)).contents.SensMethod
     r = _refs.refcvs_integrate_batch_events(path.encode(), C.c_int(neq), C.c_int(model.nvalues), C.c_int(ns), C.c_void_p(sens_var.ctypes.data),
                                             C.c_void_p(base.ctypes.data), C.c_int(nsets), C.c_int(len(vary)), C.c_void_p(vary.ctypes.data),
                                             C.c_void_p(values.ctypes.data), C.c_void_p(tp.ctypes.data), C.c_int(nout), C.c_double(rtol), C.c_double(atol),

@@ -28,9 +28,9 @@ CASES = {
 needs_ref = pytest.mark.skipif(not H.have_sens_ref(), reason="oracle/_ref/libcvodes_ref.so not built")
 
 
-def _case(name, nout=None):
+def _case(name, nout=None, method=0):
     c = CASES[name]
-    w = H.workload(name, nout=nout if nout is not None else c["nout"], sensitivity=1, sens_ids=c["ids"])
+    w = H.workload(name, nout=nout if nout is not None else c["nout"], sensitivity=1, sens_ids=c["ids"], sens_method=method)
     return w
 
 
@@ -77,16 +77,18 @@ def test_emitted_sense_function_follows_the_reference_generator():
 
 
 @needs_ref
+@pytest.mark.parametrize("method", [0, 1])
 @pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6), ("events", 24)])
-def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
-    w = _case(name)
+def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets, method):
+    """method 0: CV_SIMULTANEOUS (the reference's default), 1: CV_STAGGERED (src/sensSolver.c:286-290)."""
+    w = _case(name, method=method)
     m = w["model"]
     vals = H.workload_values(w, nsets, seed=11)
     b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
     assert b.nsens == (len(CASES[name]["ids"]) if CASES[name]["ids"] else m.nconst)
     tp = H.tpoints(w["opt"], w["nout"])
     base, trig = b.base_values()
-    got = H.Emu(b, name + "_sens").run(base, trig, vals, tp, 10000, w["rtol"], w["atol"])
+    got = H.Emu(b, name + "_sens%d" % method).run(base, trig, vals, tp, 10000, w["rtol"], w["atol"])
     ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag=name + "_sens")
     b.close()
     assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
@@ -152,8 +154,8 @@ def test_sensitivities_agree_with_central_differences():
 def test_unsupported_sensitivity_configurations_fail_loudly():
     m2, vary, _ = H.mapk_scan_model()
     opt2 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["K1"])
-    so.lib().CvodeSettings_setSensMethod(opt2, 1)
-    with pytest.raises(so.OdesError, match="simultaneous"):
+    so.lib().CvodeSettings_setSensMethod(opt2, 2)
+    with pytest.raises(so.OdesError, match="staggered1"):
         so.Batch(m2, opt2, vary)
     opt3 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["no_such_symbol"])
     with pytest.raises(so.OdesError):
@@ -166,9 +168,10 @@ def test_unsupported_sensitivity_configurations_fail_loudly():
 # ------------------------------------------------------------------------------------------------ GPU tier
 @pytest.mark.gpu
 @needs_ref
+@pytest.mark.parametrize("method", [0, 1])
 @pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64), ("events", 512)])
-def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
-    w = _case(name)
+def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets, method):
+    w = _case(name, method=method)
     m = w["model"]
     vals = H.workload_values(w, nsets, seed=2027)
     b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
@@ -178,7 +181,7 @@ def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets):
     fired = b.event_log(n).T
     tp = H.tpoints(w["opt"], w["nout"])
     ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=8, tag=name + "_sens")
-    print(name, "nsens", b.nsens, f"{n / ms * 1e3:.0f} trajectories/s", b.kernel_info())
+    print(name, "method", method, "nsens", b.nsens, f"{n / ms * 1e3:.0f} trajectories/s", b.kernel_info())
     b.close()
     assert np.array_equal(status, ref["status"])
     assert np.array_equal(fired, ref["fired"])
