@@ -72,6 +72,12 @@ char *writeSBMLToString(const SBMLDocument_t *);       /* Level 2 Version 1 text
 int writeSBML(const SBMLDocument_t *, const char *filename);
 SBMLDocument_t *SBMLDocument_create(void);
 void SBMLDocument_free(SBMLDocument_t *);
+/* libSBML's reader object, as the reference's examples use it (examples/integrate.c:71-73, batch_integrate.c:111-113) */
+typedef struct SBMLReader { int unused; } SBMLReader_t;
+SBMLReader_t *SBMLReader_create(void);
+SBMLDocument_t *SBMLReader_readSBML(SBMLReader_t *, const char *filename);
+SBMLDocument_t *SBMLReader_readSBMLFromString(SBMLReader_t *, const char *xml);
+void SBMLReader_free(SBMLReader_t *);
 Model_t *SBMLDocument_getModel(SBMLDocument_t *);
 unsigned int SBMLDocument_getLevel(const SBMLDocument_t *);
 

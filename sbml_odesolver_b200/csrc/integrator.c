@@ -312,6 +312,14 @@ cvodeResults_t *IntegratorInstance_createResults(const integratorInstance_t *eng
   if (!results) return NULL;
   results->nout = iResults->nout;
   for (i = 0; i <= results->nout; i++) { results->time[i] = iResults->time[i]; for (j = 0; j < iResults->nvalues; j++) results->value[j][i] = iResults->value[j][i]; }
+  if (iResults->sensitivity != NULL) {         /* src/integratorInstance.c:920-931 */
+    int k;
+    CvodeResults_allocateSens(results, iResults->neq, iResults->nsens, engine->opt->PrintStep);
+    for (j = 0; j < iResults->nsens; j++) {
+      results->index_sens[j] = iResults->index_sens[j];
+      for (i = 0; i < iResults->neq; i++) for (k = 0; k <= results->nout; k++) results->sensitivity[i][j][k] = iResults->sensitivity[i][j][k];
+    }
+  }
   return results;
 }
 void IntegratorInstance_printResults(const integratorInstance_t *ii, FILE *fp)

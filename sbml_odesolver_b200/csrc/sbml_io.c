@@ -876,3 +876,9 @@ int writeSBML(const SBMLDocument_t *d, const char *filename)
   fputs(s, f); fclose(f); free(s);
   return 1;
 }
+
+/* libSBML's reader object (callers create one, read, free it) */
+SBMLReader_t *SBMLReader_create(void) { return (SBMLReader_t *)calloc(1, sizeof(SBMLReader_t)); }
+SBMLDocument_t *SBMLReader_readSBML(SBMLReader_t *sr, const char *filename) { (void)sr; return readSBML(filename); }
+SBMLDocument_t *SBMLReader_readSBMLFromString(SBMLReader_t *sr, const char *xml) { (void)sr; return readSBMLFromString(xml); }
+void SBMLReader_free(SBMLReader_t *sr) { free(sr); }

@@ -69,3 +69,17 @@ for name in ("MAPK_10pt.dat", "MAPK_100pt.dat"):
     rows = [l.strip() for l in open(os.path.join(REF, "examples", name)) if re.match(r"^[0-9]", l)]
     open(os.path.join(OUT, name.lower() + ".txt"), "w").write(f"# rows of examples/{name}: t + 8 species\n" + "\n".join(rows) + "\n")
     print(name, len(rows))
+
+# 5. further sections of examples/testrun.out: the printed output of the reference's own example programs
+#    (examples/testrun runs them in sequence).  Kept verbatim: they are what the same programs, compiled unmodified
+#    against this library (oracle/Makefile: refex), have to print.
+def section(first, last, name, what):
+    body = lines[first - 1:last]
+    open(os.path.join(OUT, name), "w").write(f"# examples/testrun.out:{first}-{last} -- {what}\n" + "\n".join(body) + "\n")
+    print(name, len(body))
+
+section(6, 21, "testrun_printODEs.txt", "./printODEs (examples/printODEModel.c on basic-model1-forward-l2.xml)")
+section(23, 234, "testrun_integrate.txt", "./integrate MAPK.xml 1000 100 (examples/integrate.c)")
+section(235, 243, "testrun_defSeries.txt", "./defSeries MAPK.xml (examples/definedTimeSeries.c)")
+section(498, 550, "testrun_sensitivity.txt", "./sensitivity (examples/sensitivity.c: forward sensitivities of MAPK.xml, all constants)")
+section(585, 1197, "testrun_ParameterScanner.txt", "./ParameterScanner MAPK.xml 200 50 Ki 0 15 5 MAPK_PP (examples/ParameterScanner.c)")

@@ -1,0 +1,133 @@
+"""DROP-IN CHECK with the reference's own programs and the reference's own golden output.
+
+oracle/Makefile (target refex, part of build() where /root/reference exists) compiles the reference's example sources
+UNMODIFIED, from where they lie under /root/reference/examples, against this repository's headers (include/sbmlsolver, the
+libSBML-named shims include/sbml/*.h, and a stand-in for the out-of-scope graph drawing header) and links them with
+libodes_b200.so.  The binaries travel to the GPU box in oracle/_ref/examples (git-ignored like the vendored CVODE build);
+nothing here reads /root/reference at run time.  examples/testrun.out is the printed output of these programs
+(examples/testrun runs them in sequence); the sections are committed verbatim under tests/golden/testrun_*.txt
+(tests/golden/make_fixtures.py).  A program run through this library on the GPU has to print the reference's text."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+import sbml_odesolver_b200 as so
+
+REFEX = os.path.join(H.ROOT, "oracle", "_ref", "examples")
+GOLD = os.path.join(H.ROOT, "tests", "golden")
+PROGRAMS = ["integrate", "batch_integrate", "ParameterScanner", "definedTimeSeries", "sensitivity", "senstest", "Sense", "simpleIntegratorInstance",
+            "ChangingIntegratorInstance", "ChangingParameterIntegrator", "SharingIntegratorInstance", "TwinIntegratorInstance", "integrateODEs",
+            "analyzeJacobian", "analyzeSensitivity", "printODEModel", "bistability", "testCompiler"]
+# the reference's model file names -> this repository's re-serialised copies (tests/golden/models)
+MODELS = {"MAPK.xml": "mapk_cascade.xml", "basic-model1-forward-l2.xml": "basic_forward.xml", "basic.xml": "basic_reversible.xml",
+          "events-2-events-1-assignment-l2.xml": "two_events_one_assignment.xml", "events-1-event-1-assignment-l2.xml": "one_event_one_assignment.xml",
+          "repressilator.xml": "repressilator_ring.xml", "huang96.xml": "huang_ferrell_cascade.xml"}
+have = pytest.mark.skipif(not os.path.exists(os.path.join(REFEX, "integrate")), reason="oracle/_ref/examples not built (needs the reference tree at build time)")
+
+
+def _gold(name):
+    return [l.rstrip() for l in open(os.path.join(GOLD, name)).read().split("\n")[1:]]
+
+
+def _run(tmp_path, prog, *args):
+    for ref_name, ours in MODELS.items():
+        dst = tmp_path / ref_name
+        if not dst.exists():
+            os.symlink(H.model_path(ours), dst)
+    r = subprocess.run([os.path.join(REFEX, prog), *args], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    return r, [l.rstrip() for l in r.stdout.split("\n")]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="needs the reference tree (build container only)")
+def test_reference_example_sources_compile_unmodified_against_this_library():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(H.ROOT, "oracle"), "refex"])
+    assert all(os.path.exists(os.path.join(REFEX, p)) for p in PROGRAMS)
+
+
+@have
+def test_printODEModel_prints_the_reference_text(tmp_path):
+    """No device needed: model construction only (examples/testrun.out:6-21)."""
+    r, out = _run(tmp_path, "printODEModel")
+    assert r.returncode == 0, r.stderr
+    gold = _gold("testrun_printODEs.txt")
+    body = [l for l in out if l.strip()]
+    assert body == [l for l in gold if l.strip()]
+
+
+@have
+@pytest.mark.gpu
+def test_integrate_prints_the_reference_text(tmp_path):
+    """./integrate MAPK.xml 1000 100: all species and flux time courses, every printed character (testrun.out:23-234)."""
+    r, out = _run(tmp_path, "integrate", "MAPK.xml", "1000", "100")
+    assert r.returncode == 0, r.stderr
+    gold = _gold("testrun_integrate.txt")
+    assert [l for l in out if l.strip()] == [l for l in gold if l.strip()]
+
+
+@have
+@pytest.mark.gpu
+def test_definedTimeSeries_prints_the_reference_text(tmp_path):
+    r, out = _run(tmp_path, "definedTimeSeries", "MAPK.xml")
+    assert r.returncode == 0, r.stderr
+    gold = [l for l in _gold("testrun_defSeries.txt") if l.strip()]
+    body = [l for l in out if l.strip()]
+    assert body[-len(gold):] == gold
+
+
+@have
+@pytest.mark.gpu
+def test_sensitivity_prints_the_reference_text(tmp_path):
+    """./sensitivity: forward sensitivities of MAPK.xml to all constants through IntegratorInstance_integrateOneStep,
+    IntegratorInstance_dumpPSensitivities and CvodeResults_getSensitivity, then the re-run with V1 + 1
+    (testrun.out:498-550) -- every printed digit."""
+    r, out = _run(tmp_path, "sensitivity")
+    assert r.returncode == 0, r.stderr
+    gold = [l for l in _gold("testrun_sensitivity.txt") if l.strip()]
+    assert [l for l in out if l.strip()] == gold
+
+
+def _golden_sensitivity_rows():
+    gold = _gold("testrun_sensitivity.txt")
+    on_the_fly = [l.split() for l in gold[2:13]]                       # t + d y_i / d K1, i = 0..7
+    i0 = gold.index("#time  MAPK_P  uVol V1 Ki K1")
+    per_variable = [l.split() for l in gold[i0 + 1:i0 + 12]]           # t, MAPK_P, d MAPK_P / d (uVol V1 Ki K1)
+    return on_the_fly, per_variable
+
+
+def _check_against_golden(out, sens, tp):
+    on_the_fly, per_variable = _golden_sensitivity_rows()
+    for k in range(11):
+        assert ["%g" % tp[k]] + ["%g" % v for v in sens[k, 3, :]] == on_the_fly[k]
+        assert ["%g" % tp[k], "%g" % out[k, 6]] + ["%g" % sens[k, j, 6] for j in range(4)] == per_variable[k]
+
+
+@pytest.mark.skipif(not H.have_sens_ref(), reason="oracle/_ref/libcvodes_ref.so not built")
+def test_sensitivity_oracle_and_emulated_kernel_reproduce_the_golden_digits():
+    """PIN of the sensitivity oracle: the vendored CVODES 2.3.0 driven like src/sensSolver.c:197-346 prints the digits of
+    examples/testrun.out:499-526, and so does the kernel's per-trajectory program (host emulation)."""
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    opt = so.settings(300.0, 10, 1e-9, 1e-4, mxstep=10 ** 9, sensitivity=1)       # examples/sensitivity.c:62-69
+    b = so.Batch(m, opt, [], store=list(range(m.neq)))
+    tp = H.tpoints(opt, 10)
+    none = np.zeros((1, 0))
+    ref = H.sens_ref_run(m, opt, b, [], none, tp, 10 ** 9, 1e-4, 1e-9, tag="mapk_nominal_sens")
+    _check_against_golden(ref["out"][0], ref["sens"][0], tp)
+    base, trig = b.base_values()
+    emu = H.Emu(b, "mapk_nominal_sens").run(base, trig, none, tp, 10 ** 9, 1e-4, 1e-9)
+    b.close()
+    _check_against_golden(np.transpose(emu["out"], (2, 0, 1))[0], emu["sens"][0], tp)
+
+
+@pytest.mark.gpu
+def test_sensitivity_kernel_reproduces_the_golden_digits():
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    opt = so.settings(300.0, 10, 1e-9, 1e-4, mxstep=10 ** 9, sensitivity=1)
+    b = so.Batch(m, opt, [], store=list(range(m.neq)))
+    b.reserve(1)
+    b.integrate(1)
+    out, sens = np.transpose(b.results(1), (2, 0, 1))[0], b.sensitivities(1)[0]
+    b.close()
+    _check_against_golden(out, sens, H.tpoints(opt, 10))
