@@ -27,6 +27,7 @@ int ODESBatch_setTimeGrid(odesBatch_t *, int nout, const double *tpoints);
 int ODESBatch_setInitialTriggers(odesBatch_t *, const int *trigger);
 int ODESBatch_setInitialSensitivities(odesBatch_t *, const double *s0);
 
+#define ODES_LOOKAHEAD 256        /* output steps computed ahead by one device run of an indefinite integration */
 static void drop_course(cvodeSolver_t *s)
 {
   free(s->course); free(s->courseFired); free(s->courseSens);
@@ -80,6 +81,7 @@ integratorInstance_t *IntegratorInstance_create(odeModel_t *om, cvodeSettings_t 
 int IntegratorInstance_set(integratorInstance_t *engine, cvodeSettings_t *opt)
 {
   if (opt != engine->opt && engine->solver->plan) { ODESBatch_free(engine->solver->plan); engine->solver->plan = NULL; }
+  if (opt != engine->opt && engine->solver->planOpt) { CvodeSettings_free(engine->solver->planOpt); engine->solver->planOpt = NULL; }
   CvodeData_initialize(engine->data, opt, engine->om, 0);
   return initialize_solver(engine, engine->data, opt, engine->om);
 }
@@ -93,7 +95,7 @@ int IntegratorInstance_resetTime(integratorInstance_t *engine, cvodeSettings_t *
 void IntegratorInstance_free(integratorInstance_t *engine)
 {
   if (!engine) return;
-  if (engine->solver) { drop_course(engine->solver); if (engine->solver->plan) ODESBatch_free(engine->solver->plan); free(engine->solver); }
+  if (engine->solver) { drop_course(engine->solver); if (engine->solver->plan) ODESBatch_free(engine->solver->plan); CvodeSettings_free(engine->solver->planOpt); free(engine->solver); }
   CvodeData_free(engine->data);
   ODESense_free(engine->os);
   free(engine);
@@ -167,26 +169,37 @@ static int compute_course(integratorInstance_t *engine)
   odeModel_t *om = engine->om; cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data;
   int nvalues = data->nvalues, nin = om->neq + om->nconst, i, j, nrem, st = 0;
   double *grid, *values, *rows; unsigned int *fired; int stats[ODES_NUM_STATS];
-  if (engine->opt->Indefinitely) {
-    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "indefinite integration is not supported by the device integrator; use a finite output grid");
-    return 0;
+  /* indefinite integration (opt->Indefinitely: one step of length opt->Time per call, no end; examples/ParameterScanner.c):
+     the device computes ODES_LOOKAHEAD output steps ahead from the current state, on the grid the reference walks
+     (tout += Time, src/integratorInstance.c:1228-1231); a run longer than that continues with a freshly initialised
+     solver at the look-ahead boundary */
+  const int indefinite = engine->opt->Indefinitely;
+  cvodeSettings_t *planOpt = engine->opt;
+  if (indefinite) {
+    if (!solver->planOpt) {
+      solver->planOpt = CvodeSettings_clone(engine->opt);
+      solver->planOpt->Indefinitely = 0;
+      CvodeSettings_setTime(solver->planOpt, engine->opt->Time * ODES_LOOKAHEAD, ODES_LOOKAHEAD);
+      solver->planOpt->StoreResults = 0;
+    }
+    planOpt = solver->planOpt;
   }
   if (!solver->plan) {
     int *idx = (int *)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(int));
     for (i = 0, j = 0; i < nvalues; i++) if (i < om->neq || i >= om->neq + om->nass) idx[j++] = i;
-    solver->plan = ODESBatch_create(om, engine->opt, nin, idx, 0, NULL, 0);
+    solver->plan = ODESBatch_create(om, planOpt, nin, idx, 0, NULL, 0);
     free(idx);
     if (!solver->plan) return 0;
   }
-  nrem = solver->nout - solver->iout + 1;
+  nrem = indefinite ? ODES_LOOKAHEAD : solver->nout - solver->iout + 1;
   grid = (double *)malloc((size_t)(nrem + 1) * sizeof(double));
   grid[0] = solver->t;
   grid[1] = solver->tout;
-  for (i = 2; i <= nrem; i++) grid[i] = engine->opt->TimePoints[solver->iout + i - 1];
+  for (i = 2; i <= nrem; i++) grid[i] = indefinite ? grid[i - 1] + engine->opt->Time : engine->opt->TimePoints[solver->iout + i - 1];
   values = (double *)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(double));
   for (i = 0, j = 0; i < nvalues; i++) if (i < om->neq || i >= om->neq + om->nass) values[j++] = data->value[i];
   rows = (double *)malloc((size_t)(nrem + 1) * (size_t)nvalues * sizeof(double));
-  fired = (unsigned int *)malloc((size_t)(solver->nout + 2) * sizeof(unsigned int));
+  fired = (unsigned int *)malloc((size_t)((indefinite ? ODES_LOOKAHEAD : solver->nout) + 2) * sizeof(unsigned int));
   if (solver->nsens > 0) {                     /* the course continues from the current sensitivities (src/sensSolver.c:268-277) */
     double *s0 = (double *)malloc((size_t)solver->nsens * (size_t)om->neq * sizeof(double));
     int ok;
@@ -204,7 +217,7 @@ static int compute_course(integratorInstance_t *engine)
   }
   drop_course(solver);
   if (solver->nsens > 0) {
-    solver->courseSens = (double *)malloc((size_t)(engine->opt->PrintStep + 1) * (size_t)solver->nsens * (size_t)om->neq * sizeof(double));
+    solver->courseSens = (double *)malloc((size_t)(planOpt->PrintStep + 1) * (size_t)solver->nsens * (size_t)om->neq * sizeof(double));
     if (!ODESBatch_getSensitivities(solver->plan, 1, solver->courseSens)) { free(grid); free(values); free(rows); free(fired); return 0; }
   }
   solver->course = rows; solver->courseFirst = solver->iout; solver->courseLen = nrem; solver->courseStatus = st;
@@ -272,7 +285,8 @@ static const char *cvode_message(int flag)
 int IntegratorInstance_cvodeOneStep(integratorInstance_t *engine)
 {
   cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data; int i, row;
-  if (!engine->isValid || !solver->course) {
+  if (!engine->isValid || !solver->course ||
+      (engine->opt->Indefinitely && solver->iout - solver->courseFirst + 1 > solver->courseLen)) {       /* look-ahead used up */
     solver->t0 = solver->t;
     if (!compute_course(engine)) return 0;
     engine->isValid = 1;
@@ -477,19 +491,25 @@ char *IntegratorInstance_getSensVariableName(integratorInstance_t *engine, int i
 { return (engine->os && i >= 0 && i < engine->os->nsens) ? engine->om->names[engine->os->index_sens[i]] : NULL; }
 void IntegratorInstance_dumpYSensitivities(integratorInstance_t *engine, variableIndex_t *y)
 {
-  int j;
-  if (!engine->os || !engine->data->sensitivity || y->index >= engine->om->neq) { printf("WARNING: no sensitivities for %s\n", engine->om->names[y->index]); return; }
-  printf("%g ", engine->solver->t);
-  for (j = 0; j < engine->os->nsens; j++) printf("%g ", engine->data->sensitivity[y->index][j]);
+  int j; cvodeData_t *data = engine->data;
+  if (!data->sensitivity) return;
+  if (y->index >= engine->om->neq) {
+    printf("Warning: ID is not a variable, no sensitivities ");
+    printf("can be calculated for %s \n", engine->om->names[y->index]);
+    return;
+  }
+  printf("%g  ", data->currenttime);
+  printf("%g  ", data->value[y->index]);
+  for (j = 0; j < data->nsens; j++) printf("%g ", data->sensitivity[y->index][j]);
   printf("\n");
 }
 void IntegratorInstance_dumpPSensitivities(integratorInstance_t *engine, variableIndex_t *p)
 {
-  int i, j;
-  if (!engine->os || !engine->data->sensitivity) return;
+  int i, j; cvodeData_t *data = engine->data;
+  if (!engine->os || !data->sensitivity) return;
   for (j = 0; j < engine->os->nsens && engine->os->index_sens[j] != p->index; j++) ;
-  if (j == engine->os->nsens) { printf("WARNING: no sensitivities for %s\n", engine->om->names[p->index]); return; }
-  printf("%g ", engine->solver->t);
-  for (i = 0; i < engine->om->neq; i++) printf("%g ", engine->data->sensitivity[i][j]);
+  if (j == engine->os->nsens) { printf("Warning: no sensitivity requested for ID %s\n", engine->om->names[p->index]); return; }
+  printf("%g  ", data->currenttime);
+  for (i = 0; i < engine->om->neq; i++) printf("%g ", data->sensitivity[i][j]);
   printf("\n");
 }

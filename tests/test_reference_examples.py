@@ -131,3 +131,19 @@ def test_sensitivity_kernel_reproduces_the_golden_digits():
     out, sens = np.transpose(b.results(1), (2, 0, 1))[0], b.sensitivities(1)[0]
     b.close()
     _check_against_golden(out, sens, H.tpoints(opt, 10))
+
+
+@have
+@pytest.mark.gpu
+def test_ParameterScanner_prints_the_reference_text(tmp_path):
+    """./ParameterScanner MAPK.xml 200 50 Ki 0 15 5 MAPK_PP (testrun.out:585-1197): INDEFINITE integration, one step of
+    length 50 per IntegratorInstance_integrateOneStep, 200 steps per value of Ki, reset + setVariableValue in between; Ki = 0
+    makes the first step fail ("Parameter = 0") and the scan goes on.  Every printed digit of the 3 x 201 rows."""
+    r, out = _run(tmp_path, "ParameterScanner", "MAPK.xml", "200", "50", "Ki", "0", "15", "5", "MAPK_PP")
+    assert r.returncode == 0, r.stderr
+    gold = _gold("testrun_ParameterScanner.txt")
+    while gold and not gold[-1].strip():
+        gold.pop()
+    while out and not out[-1].strip():
+        out.pop()
+    assert out == gold
