@@ -24,6 +24,7 @@ struct cvodeSolver {
   double reltol, atol1;
   /* device-side integration of the remaining time course (batch of one) */
   struct odesBatch *plan;
+  unsigned long planSignature; /* of the settings the plan was specialised for */
   cvodeSettings_t *planOpt;   /* indefinite integration: the finite look-ahead grid the plan was created with */
   double *course;      /* [nsteps][nvalues] rows computed ahead by the device */
   int *courseFired;    /* [nsteps] event bitmask per row                       */

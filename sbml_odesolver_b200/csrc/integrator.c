@@ -34,10 +34,28 @@ static void drop_course(cvodeSolver_t *s)
   s->course = NULL; s->courseFired = NULL; s->courseSens = NULL; s->courseLen = 0; s->courseFirst = 0; s->courseStatus = 0;
 }
 
+/* the settings a compiled plan depends on (kernel specialisation and buffer sizes); callers change cvodeSettings_t objects
+   in place between runs (examples/sensitivity.c switches the sensitivities off and resets), so the plan is keyed on the
+   values, not on the pointer */
+static unsigned long plan_signature(const cvodeSettings_t *opt)
+{
+  unsigned long h = 1469598103UL; int i; const char *c;
+  const long v[] = { opt->PrintStep, opt->Indefinitely, opt->CvodeMethod, opt->IterMethod, opt->MaxOrder, opt->ResetCvodeOnEvent, opt->SetTStop,
+                     opt->Sensitivity, opt->nsens, opt->SensMethod, opt->HaltOnEvent, opt->SteadyState, opt->UseJacobian, opt->sensIDs != NULL };
+  for (i = 0; i < (int)(sizeof v / sizeof v[0]); i++) h = (h ^ (unsigned long)v[i]) * 1099511UL;
+  for (i = 0; opt->sensIDs && i < opt->nsens; i++) for (c = opt->sensIDs[i]; *c; c++) h = (h ^ (unsigned long)*c) * 1099511UL;
+  { double d = opt->ssThreshold + (opt->Indefinitely ? opt->Time : 0.0); unsigned char b[sizeof d]; memcpy(b, &d, sizeof d); for (i = 0; i < (int)sizeof d; i++) h = (h ^ b[i]) * 1099511UL; }
+  return h;
+}
 static int initialize_solver(integratorInstance_t *engine, cvodeData_t *data, cvodeSettings_t *opt, odeModel_t *om)
 {
   int i; cvodeSolver_t *solver = engine->solver; cvodeResults_t *results = data->results;
   engine->om = om; engine->opt = opt; engine->data = data; engine->results = data->results;
+  if (solver->plan && solver->planSignature != plan_signature(opt)) {
+    ODESBatch_free(solver->plan); solver->plan = NULL;
+    if (solver->planOpt) { CvodeSettings_free(solver->planOpt); solver->planOpt = NULL; }
+  }
+  solver->planSignature = plan_signature(opt);
   /* IntegratorInstance_initializeJacobian (integratorInstance.c:291-311) */
   if (om->jacobianFailed > 0 || !opt->UseJacobian) engine->UseJacobian = 0;
   else if (om->jacob != NULL) engine->UseJacobian = 1;

@@ -83,3 +83,7 @@ section(23, 234, "testrun_integrate.txt", "./integrate MAPK.xml 1000 100 (exampl
 section(235, 243, "testrun_defSeries.txt", "./defSeries MAPK.xml (examples/definedTimeSeries.c)")
 section(498, 550, "testrun_sensitivity.txt", "./sensitivity (examples/sensitivity.c: forward sensitivities of MAPK.xml, all constants)")
 section(585, 1197, "testrun_ParameterScanner.txt", "./ParameterScanner MAPK.xml 200 50 Ki 0 15 5 MAPK_PP (examples/ParameterScanner.c)")
+section(353, 410, "testrun_analyzeJacobian.txt", "./analyzeJacobian (examples/analyzeJacobian.c: symbolic Jacobian of MAPK.xml, its signs at t = 0 and t = 1000)")
+section(411, 497, "testrun_analyzeSens.txt", "./analyzeSens (examples/analyzeSensitivity.c: the parametric matrix of MAPK.xml as printed expressions)")
+section(1198, 1608, "testrun_Sense.txt", "./Sense MAPK.xml 200 7.5 p Ki MKKK_P MAPK_PP (examples/Sense.c)")
+section(320, 350, "testrun_changeIntInst.txt", "./changeIntInst (examples/ChangingIntegratorInstance.c on basic-model1-forward-l2.xml: two instances, the second one with values changed on the way)")

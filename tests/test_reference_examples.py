@@ -147,3 +147,48 @@ def test_ParameterScanner_prints_the_reference_text(tmp_path):
     while out and not out[-1].strip():
         out.pop()
     assert out == gold
+
+
+def _same_text(out, gold_name, skip_head=0):
+    gold = [l for l in _gold(gold_name) if l.strip()]
+    body = [l for l in out if l.strip()]
+    assert body[skip_head:] == gold[skip_head:], "\n".join(f"{a!r} != {b!r}" for a, b in zip(body, gold) if a != b)[:2000]
+
+
+@have
+def test_analyzeSensitivity_prints_the_reference_text(tmp_path):
+    """No device needed: ODESense_constructMatrix and the printed expressions of every d f_i / d p_j of MAPK.xml
+    (examples/testrun.out:411-497) -- a known-answer test of the parametric matrix from the reference's own output."""
+    r, out = _run(tmp_path, "analyzeSensitivity")
+    assert r.returncode == 0, r.stderr
+    _same_text(out, "testrun_analyzeSens.txt")
+
+
+@have
+@pytest.mark.gpu
+def test_analyzeJacobian_prints_the_reference_text(tmp_path):
+    """The symbolic Jacobian, its signs at the initial conditions and after integrating to t = 1000 (testrun.out:356-410)."""
+    r, out = _run(tmp_path, "analyzeJacobian")
+    assert r.returncode == 0, r.stderr
+    _same_text(out, "testrun_analyzeJacobian.txt")
+
+
+@have
+@pytest.mark.gpu
+def test_Sense_prints_the_reference_text(tmp_path):
+    """./Sense MAPK.xml 200 7.5 p Ki MKKK_P MAPK_PP: sensitivity time courses as gnuplot data (testrun.out:1198-1620)."""
+    r, out = _run(tmp_path, "Sense", "MAPK.xml", "200", "7.5", "p", "Ki", "MKKK_P", "MAPK_PP")
+    assert r.returncode == 0, r.stderr
+    _same_text(out, "testrun_Sense.txt")
+
+
+@have
+@pytest.mark.gpu
+def test_ChangingIntegratorInstance_prints_the_reference_text(tmp_path):
+    """Two instances of one model stepped side by side, values of the second one changed on the way (setVariableValue
+    during a run re-initialises the solver at that time; testrun.out:320-350)."""
+    r, out = _run(tmp_path, "ChangingIntegratorInstance")
+    assert r.returncode == 0, r.stderr
+    gold = [l for l in _gold("testrun_changeIntInst.txt") if l.strip()]
+    body = [l for l in out if l.strip()]
+    assert body[-len(gold):] == gold
