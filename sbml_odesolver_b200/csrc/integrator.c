@@ -176,9 +176,10 @@ void IntegratorInstance_copyVariableState(integratorInstance_t *target, integrat
 }
 void IntegratorInstance_dumpData(const integratorInstance_t *engine)
 {
-  int i; cvodeData_t *data = engine->data;
-  printf("t = %g\n", engine->solver->t);
-  for (i = 0; i < data->nvalues; i++) printf("%s = %g\n", engine->om->names[i], data->value[i]);
+  int i; cvodeData_t *data = engine->data;                  /* one row: time, then all values (src/integratorInstance.c:737-746) */
+  printf("%g  ", data->currenttime);
+  for (i = 0; i < data->nvalues; i++) printf("%g ", data->value[i]);
+  printf("\n");
 }
 
 /* device look-ahead: integrates outputs iout..nout from the current state as a batch of one */

@@ -192,3 +192,16 @@ def test_ChangingIntegratorInstance_prints_the_reference_text(tmp_path):
     gold = [l for l in _gold("testrun_changeIntInst.txt") if l.strip()]
     body = [l for l in out if l.strip()]
     assert body[-len(gold):] == gold
+
+
+@have
+@pytest.mark.gpu
+def test_senstest_prints_the_reference_text_for_the_analytic_cases(tmp_path):
+    """./senstest up to the point where it frees the Jacobian and asks for CVODES' internal difference quotients (not
+    built: the plan creation fails loudly there): repeated integrate / reset, sensitivities switched on in place, the
+    default selection and a selection of parameters AND variables (initial-condition sensitivities), rtol 1e-10
+    (testrun.out:1826-1863)."""
+    r, out = _run(tmp_path, "senstest")
+    gold = [l for l in _gold("testrun_senstest_analytic.txt") if l.strip()]
+    body = [l for l in out if l.strip()]
+    assert body[:len(gold)] == gold, "\n".join(f"{a!r} != {b!r}" for a, b in zip(body, gold) if a != b)[:2000]
