@@ -69,7 +69,7 @@ void IntegratorInstance_printResults(const integratorInstance_t *, FILE *);
 int IntegratorInstance_checkSteadyState(integratorInstance_t *);
 int IntegratorInstance_handleError(integratorInstance_t *);
 void IntegratorInstance_printStatistics(const integratorInstance_t *, FILE *);
-void IntegratorInstance_printCVODEStatistics(const integratorInstance_t *, FILE *);
+int IntegratorInstance_printCVODEStatistics(const integratorInstance_t *, FILE *);   /* 1, like the reference (cvodeSolver.h:55) */
 double IntegratorInstance_getIntegrationTime(const integratorInstance_t *);
 int IntegratorInstance_setInitialTime(integratorInstance_t *, double);
 const char *IntegratorInstance_getVariableName(integratorInstance_t *, variableIndex_t *);

@@ -21,6 +21,12 @@ struct cvodeSettings {
   int observation_data_type; int DoAdjoint;
 };
 
+/* reference integratorSettings.h:150-169 ("not used currently"): start and end time, step, number of steps */
+typedef struct timeSettings { double t0; double tmult; double tend; int nout; } timeSettings_t;
+timeSettings_t *TimeSettings_create(double t0, double tend, int nout);
+void TimeSettings_free(timeSettings_t *);
+cvodeSettings_t *CvodeSettings_createFromTimeSettings(timeSettings_t *);
+
 cvodeSettings_t *CvodeSettings_create(void);
 cvodeSettings_t *CvodeSettings_createWithTime(double Time, int PrintStep);
 cvodeSettings_t *CvodeSettings_createWith(double EndTime, int PrintStep, double Error, double RError,

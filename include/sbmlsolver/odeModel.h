@@ -132,6 +132,7 @@ const ASTNode_t *ODEModel_getAssignment(const odeModel_t *, const variableIndex_
 /* Jacobian */
 int ODEModel_constructJacobian(odeModel_t *);
 void ODEModel_freeJacobian(odeModel_t *);
+ASTNode_t *ODEModel_constructDeterminant(const odeModel_t *);   /* Laplace expansion of the symbolic Jacobian; caller frees */
 const ASTNode_t *ODEModel_getJacobianIJEntry(const odeModel_t *, int i, int j);
 const ASTNode_t *ODEModel_getJacobianEntry(const odeModel_t *, const variableIndex_t *, const variableIndex_t *);
 

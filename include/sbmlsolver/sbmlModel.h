@@ -35,7 +35,7 @@ typedef struct SpeciesReference {
   char *species; double stoichiometry; ASTNode_t *stoichiometryMath;
 } SpeciesReference_t;
 
-typedef struct KineticLaw { ASTNode_t *math; ListOf_t parameters; } KineticLaw_t;
+typedef struct KineticLaw { ASTNode_t *math; ListOf_t parameters; char *formula; /* text of math, made on request */ } KineticLaw_t;
 
 typedef struct Reaction {
   char *id; int reversible; int fast;
@@ -43,7 +43,7 @@ typedef struct Reaction {
   KineticLaw_t *kineticLaw;
 } Reaction_t;
 
-typedef struct Rule { SBMLTypeCode_t type; char *variable; ASTNode_t *math; } Rule_t;
+typedef struct Rule { SBMLTypeCode_t type; char *variable; ASTNode_t *math; char *formula; /* text of math, made on request */ } Rule_t;
 typedef struct FunctionDefinition { char *id; ASTNode_t *math; } FunctionDefinition_t;
 typedef struct InitialAssignment { char *symbol; ASTNode_t *math; } InitialAssignment_t;
 typedef struct EventAssignment { char *variable; ASTNode_t *math; } EventAssignment_t;
@@ -130,6 +130,34 @@ Species_t *Species_clone(const Species_t *);
 Parameter_t *Parameter_clone(const Parameter_t *);
 Event_t *Event_clone(const Event_t *);
 void Parameter_setId(Parameter_t *, const char *);
+
+/* further libSBML-named accessors the reference's own unit tests and examples call on these structures */
+typedef void SBase_t;
+const char *Compartment_getId(const Compartment_t *);
+const char *Species_getId(const Species_t *);
+const char *Parameter_getId(const Parameter_t *);
+double Parameter_getValue(const Parameter_t *);
+void Parameter_setValue(Parameter_t *, double);
+void Parameter_setName(Parameter_t *, const char *);
+void Parameter_setConstant(Parameter_t *, int);
+void Compartment_setConstant(Compartment_t *, int);
+Parameter_t *Parameter_create(void);
+Parameter_t *Parameter_createWith(const char *id, const char *name);
+void Parameter_free(Parameter_t *);
+const char *Reaction_getId(const Reaction_t *);
+KineticLaw_t *Reaction_getKineticLaw(const Reaction_t *);
+const char *KineticLaw_getFormula(const KineticLaw_t *);       /* infix text of the math; owned by the kinetic law */
+const ASTNode_t *KineticLaw_getMath(const KineticLaw_t *);
+const char *Rule_getFormula(const Rule_t *);
+const char *Rule_getVariable(const Rule_t *);
+unsigned int Model_getNumUnitDefinitions(const Model_t *);                 /* not kept by this front end: 0 */
+unsigned int Model_getNumSpeciesWithBoundaryCondition(const Model_t *);
+unsigned int Model_getNumSpeciesTypes(const Model_t *);
+unsigned int Model_getNumCompartmentTypes(const Model_t *);
+unsigned int Model_getNumConstraints(const Model_t *);
+ListOf_t *ListOf_create(void);
+void ListOf_appendAndOwn(ListOf_t *, SBase_t *);
+void ListOf_free(ListOf_t *);                                              /* the list, not its items */
 
 #ifdef __cplusplus
 }

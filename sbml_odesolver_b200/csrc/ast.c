@@ -313,8 +313,11 @@ static void canonicalize_function(ASTNode_t *n)
       ASTNode_prependChild(n, ten);
     }
     if (t == AST_FUNCTION_ROOT && n->nchildren == 1) {
+      /* root(x): the degree 2 is made explicit for evaluation and differentiation; libSBML keeps the single argument, and
+         the text generator of the reference prints it that way -- the unused rational denominator of the node remembers it */
       ASTNode_t *two = ASTNode_create(); ASTNode_setInteger(two, 2);
       ASTNode_prependChild(n, two);
+      n->denom = -2;
     }
     ASTNode_setType(n, t);
   }

@@ -37,7 +37,10 @@ void CharBuffer_append(charBuffer_t *c, const char *s)
   memcpy(c->b + c->len, s, n + 1); c->len += n;
 }
 void CharBuffer_appendInt(charBuffer_t *c, long v) { char t[32]; snprintf(t, sizeof t, "%ld", v); CharBuffer_append(c, t); }
-void CharBuffer_appendDouble(charBuffer_t *c, double v)
+/* the public entry prints like the reference (src/charBuffer.c:103-112, "%g"); the emitters below use cb_double17 */
+void CharBuffer_appendDouble(charBuffer_t *c, double v) { char t[64]; snprintf(t, sizeof t, "%g", v); CharBuffer_append(c, t); }
+/* full precision for generated code: the value is reproduced exactly */
+static void cb_double17(charBuffer_t *c, double v)
 {
   char t[64];
   if (isnan(v)) strcpy(t, "(0.0/0.0)");
@@ -162,7 +165,7 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
      (same IEEE operations the interpreter would perform at run time) */
   if (c->cuda && n->nchildren > 0 && is_const_tree(n) && !ASTNode_isLogical(n) && !ASTNode_isRelational(n) && n->type != AST_FUNCTION_PIECEWISE) {
     if (c->leaf) leaf_number(s, c, evaluateAST((ASTNode_t *)n, NULL));
-    else CharBuffer_appendDouble(s, evaluateAST((ASTNode_t *)n, NULL));
+    else cb_double17(s, evaluateAST((ASTNode_t *)n, NULL));
     return;
   }
   switch (n->type) {
@@ -181,8 +184,8 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
       if (e == 2.0 && !c->interp) { CharBuffer_append(s, "odes_sqr("); gen(s, n->children[0], c); CharBuffer_append(s, ")"); break; }
     }
     gen_call(s, n, c->cuda ? "odes_pow" : "pow", c); break;
-  case AST_INTEGER: if (c->leaf) leaf_number(s, c, (double)n->ival); else CharBuffer_appendDouble(s, (double)n->ival); break;
-  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: if (c->leaf) leaf_number(s, c, ASTNode_getReal(n)); else CharBuffer_appendDouble(s, ASTNode_getReal(n)); break;
+  case AST_INTEGER: if (c->leaf) leaf_number(s, c, (double)n->ival); else cb_double17(s, (double)n->ival); break;
+  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: if (c->leaf) leaf_number(s, c, ASTNode_getReal(n)); else cb_double17(s, ASTNode_getReal(n)); break;
   case AST_NAME:
     if (ASTNode_isSetIndex(n)) c->name(s, (int)ASTNode_getIndex(n), c);
     else {
@@ -192,9 +195,9 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
     }
     break;
   case AST_NAME_TIME: CharBuffer_append(s, c->time); break;
-  case AST_CONSTANT_E: CharBuffer_appendDouble(s, exp(1.)); break;
+  case AST_CONSTANT_E: cb_double17(s, exp(1.)); break;
   case AST_CONSTANT_FALSE: CharBuffer_append(s, "0.0"); break;
-  case AST_CONSTANT_PI: CharBuffer_appendDouble(s, 4. * atan(1.)); break;
+  case AST_CONSTANT_PI: cb_double17(s, 4. * atan(1.)); break;
   case AST_CONSTANT_TRUE: CharBuffer_append(s, "1.0"); break;
   case AST_FUNCTION_ABS: gen_call(s, n, "fabs", c); break;
   case AST_FUNCTION_ARCCOS: gen_call(s, n, "acos", c); break;
@@ -258,13 +261,125 @@ static void gen(charBuffer_t *s, const ASTNode_t *n, const emit_ctx_t *c)
   }
 }
 
-/* the reference's public entry: value[] naming, C flavour */
+/* value[] naming of the C flavour */
 static void name_value(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "value[%d]", idx); }
-void generateAST(charBuffer_t *s, const ASTNode_t *node)
+
+/* The reference's public entry (src/processAST.c:2117-2311): an indexed AST as the C expression text the reference
+   writes into its generated sources -- numbers as ((realtype)%g), indexed names as value[i], time as
+   data->currenttime, the macro names of generateMacros (acot, sec ...), operator children in parentheses.  This is the
+   text API callers and the reference's unit tests see (unittest/test_processAST.c:190-247); the code THIS library
+   compiles comes from gen() above (full-precision constants, exact-case strength reduction). */
+static void genref(charBuffer_t *s, const ASTNode_t *n);
+static int ref_is_operator(const ASTNode_t *n)
 {
-  emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = REF_TIME; c.info = NULL; c.leaf = NULL;
-  gen(s, node, &c);
+  switch (n->type) {
+  case AST_PLUS: case AST_MINUS: case AST_TIMES: case AST_DIVIDE: case AST_POWER:
+  case AST_LOGICAL_AND: case AST_LOGICAL_OR: case AST_LOGICAL_XOR: case AST_LOGICAL_NOT:
+  case AST_RELATIONAL_EQ: case AST_RELATIONAL_GEQ: case AST_RELATIONAL_GT: case AST_RELATIONAL_LEQ: case AST_RELATIONAL_LT: case AST_RELATIONAL_NEQ:
+    return 1;
+  default: return 0;
+  }
 }
+static void genref_nested(charBuffer_t *s, const ASTNode_t *n)
+{
+  if (ref_is_operator(n)) { CharBuffer_append(s, "("); genref(s, n); CharBuffer_append(s, ")"); }
+  else genref(s, n);
+}
+static void genref_join(charBuffer_t *s, const ASTNode_t *n, const char *op)
+{
+  unsigned int i;
+  for (i = 0; i < n->nchildren; i++) { if (i) CharBuffer_append(s, op); genref_nested(s, n->children[i]); }
+}
+static void genref_call(charBuffer_t *s, const ASTNode_t *n, const char *fn)
+{
+  unsigned int i;
+  CharBuffer_append(s, fn); CharBuffer_append(s, "(");
+  for (i = 0; i < n->nchildren; i++) { if (i) CharBuffer_append(s, ", "); genref(s, n->children[i]); }
+  CharBuffer_append(s, ")");
+}
+static void genref_number(charBuffer_t *s, double v) { CharBuffer_append(s, "((realtype)"); CharBuffer_appendDouble(s, v); CharBuffer_append(s, ")"); }
+static void genref(charBuffer_t *s, const ASTNode_t *n)
+{
+  unsigned int i;
+  switch (n->type) {
+  case AST_PLUS: genref_join(s, n, " + "); break;
+  case AST_TIMES: genref_join(s, n, " * "); break;
+  case AST_DIVIDE: genref_join(s, n, " / "); break;
+  case AST_MINUS:
+    if (n->nchildren == 1) { CharBuffer_append(s, "-"); genref_nested(s, n->children[0]); }
+    else genref_join(s, n, " - ");
+    break;
+  case AST_POWER: case AST_FUNCTION_POWER: genref_call(s, n, "pow"); break;
+  case AST_INTEGER: genref_number(s, (double)n->ival); break;
+  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: genref_number(s, ASTNode_getReal(n)); break;
+  case AST_NAME:
+    if (ASTNode_isSetIndex(n)) cbprintf(s, "value[%d]", (int)ASTNode_getIndex(n));
+    else {
+      SolverError_error(FATAL_ERROR_TYPE, SOLVER_ERROR_AST_COMPILATION_FAILED_MISSING_VALUE,
+                        "generateAST: No value found for AST_NAME %s. Defaults to Zero to avoid program crash", ASTNode_getName(n));
+      CharBuffer_append(s, "0.0");
+    }
+    break;
+  case AST_NAME_TIME: CharBuffer_append(s, "data->currenttime"); break;
+  case AST_CONSTANT_E: CharBuffer_appendDouble(s, exp(1.)); break;
+  case AST_CONSTANT_FALSE: CharBuffer_append(s, "0"); break;
+  case AST_CONSTANT_PI: CharBuffer_appendDouble(s, 4. * atan(1.)); break;
+  case AST_CONSTANT_TRUE: CharBuffer_append(s, "1"); break;
+  case AST_FUNCTION_ABS: genref_call(s, n, "fabs"); break;
+  case AST_FUNCTION_ARCCOS: genref_call(s, n, "acos"); break;
+  case AST_FUNCTION_ARCCOSH: genref_call(s, n, "acosh"); break;
+  case AST_FUNCTION_ARCCOT: genref_call(s, n, "acot"); break;
+  case AST_FUNCTION_ARCCOTH: genref_call(s, n, "acoth"); break;
+  case AST_FUNCTION_ARCCSC: genref_call(s, n, "acsc"); break;
+  case AST_FUNCTION_ARCCSCH: genref_call(s, n, "acsch"); break;
+  case AST_FUNCTION_ARCSEC: genref_call(s, n, "asec"); break;
+  case AST_FUNCTION_ARCSECH: genref_call(s, n, "asech"); break;
+  case AST_FUNCTION_ARCSIN: genref_call(s, n, "asin"); break;
+  case AST_FUNCTION_ARCSINH: genref_call(s, n, "asinh"); break;
+  case AST_FUNCTION_ARCTAN: genref_call(s, n, "atan"); break;
+  case AST_FUNCTION_ARCTANH: genref_call(s, n, "atanh"); break;
+  case AST_FUNCTION_CEILING: genref_call(s, n, "ceil"); break;
+  case AST_FUNCTION_COS: genref_call(s, n, "cos"); break;
+  case AST_FUNCTION_COSH: genref_call(s, n, "cosh"); break;
+  case AST_FUNCTION_COT: genref_call(s, n, "cot"); break;
+  case AST_FUNCTION_COTH: genref_call(s, n, "coth"); break;
+  case AST_FUNCTION_CSC: genref_call(s, n, "csc"); break;
+  case AST_FUNCTION_CSCH: genref_call(s, n, "csch"); break;
+  case AST_FUNCTION_EXP: genref_call(s, n, "exp"); break;
+  case AST_FUNCTION_FACTORIAL: genref_call(s, n, "factorial"); break;
+  case AST_FUNCTION_FLOOR: genref_call(s, n, "floor"); break;
+  case AST_FUNCTION_LN: case AST_FUNCTION_LOG: genref_call(s, n, "log"); break;
+  case AST_FUNCTION_ROOT:
+    if (n->nchildren == 2 && n->denom == -2) { CharBuffer_append(s, "root("); genref(s, n->children[1]); CharBuffer_append(s, ")"); }   /* written as root(x) */
+    else genref_call(s, n, "root");
+    break;
+  case AST_FUNCTION_SEC: genref_call(s, n, "sec"); break;
+  case AST_FUNCTION_SECH: genref_call(s, n, "sech"); break;
+  case AST_FUNCTION_SIN: genref_call(s, n, "sin"); break;
+  case AST_FUNCTION_SINH: genref_call(s, n, "sinh"); break;
+  case AST_FUNCTION_TAN: genref_call(s, n, "tan"); break;
+  case AST_FUNCTION_TANH: genref_call(s, n, "tanh"); break;
+  case AST_LOGICAL_AND: genref_join(s, n, " && "); break;
+  case AST_LOGICAL_OR: genref_join(s, n, " || "); break;
+  case AST_LOGICAL_NOT: CharBuffer_append(s, "!"); genref_nested(s, n->children[0]); break;
+  case AST_LOGICAL_XOR:
+    CharBuffer_append(s, "((");
+    for (i = 0; i < n->nchildren; i++) { if (i) CharBuffer_append(s, " + "); CharBuffer_append(s, "("); genref_nested(s, n->children[i]); CharBuffer_append(s, " ? 1 : 0)"); }
+    CharBuffer_append(s, ") % 2) != 0");
+    break;
+  case AST_RELATIONAL_EQ: genref_join(s, n, " == "); break;
+  case AST_RELATIONAL_GEQ: genref_join(s, n, " >= "); break;
+  case AST_RELATIONAL_GT: genref_join(s, n, " > "); break;
+  case AST_RELATIONAL_LEQ: genref_join(s, n, " <= "); break;
+  case AST_RELATIONAL_LT: genref_join(s, n, " < "); break;
+  case AST_RELATIONAL_NEQ: genref_join(s, n, " != "); break;
+  default: {                                   /* piecewise, delay ...: the text this library compiles */
+      emit_ctx_t c; c.cuda = 0; c.interp = 0; c.name = name_value; c.time = "data->currenttime"; c.info = NULL; c.leaf = NULL;
+      gen(s, n, &c);
+    }
+  }
+}
+void generateAST(charBuffer_t *s, const ASTNode_t *node) { genref(s, node); }
 
 /* helper library shared by both flavours; DEV expands to __device__ __forceinline__ or static inline */
 void generateMacros(charBuffer_t *b)
@@ -365,7 +480,7 @@ static void name_cuda(charBuffer_t *s, int idx, const emit_ctx_t *c)
   default:
     /* a constant that no trajectory changes: its value is known now, so x / 1.0, x * 1.0 ... fold at compile time
        (exactly: these identities hold in IEEE arithmetic) */
-    if (k->base) { CharBuffer_append(s, "("); CharBuffer_appendDouble(s, k->base[idx]); CharBuffer_append(s, ")"); }
+    if (k->base) { CharBuffer_append(s, "("); cb_double17(s, k->base[idx]); CharBuffer_append(s, ")"); }
     else cbprintf(s, "c_base[%d]", idx);
   }
 }
@@ -526,7 +641,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
               "#define W_ODE_NTERMS %d\n#define W_ODE_DIVIDE %d\n#define W_ODE_FALLBACK %d\n#define W_NEGZERO_OFF %d\n",
            nlev, w_as_off(&w), w_pv_off(&w), w_lit_off(&w), w.nlit, ngroups, odeterms, odedivide, odefallback, w_lit_off(&w) + negzero);
   CharBuffer_append(b, "DEV double w_literal(int n)\n{\n  switch (n) {\n");
-  for (i = 0; i < w.nlit; i++) { cbprintf(b, "  case %d: return ", i); if (i == negzero) CharBuffer_append(b, "-0.0"); else CharBuffer_appendDouble(b, w.lit[i]); CharBuffer_append(b, ";\n"); }
+  for (i = 0; i < w.nlit; i++) { cbprintf(b, "  case %d: return ", i); if (i == negzero) CharBuffer_append(b, "-0.0"); else cb_double17(b, w.lit[i]); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "  default: return 0.0;\n  }\n}\n");
   /* packed operand words: bit 63 valid, bits 50..59 destination, 10 bits per operand from bit 0 */
   CharBuffer_append(b, "DEV unsigned long long w_group_task(int g, int lane)\n{\n  (void)g; (void)lane;\n  switch (g * 32 + lane) {\n");
@@ -597,7 +712,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
     }
   }
   CharBuffer_append(b, "  default: return 0ull;\n  }\n}\nDEV double w_ode_divisor(int lane)\n{\n  switch (lane) {\n");
-  for (i = 0; i < om->neq; i++) if (odecnt[i] && odediv[i] != 1.0) { cbprintf(b, "  case %d: return ", i); CharBuffer_appendDouble(b, odediv[i]); CharBuffer_append(b, ";\n"); }
+  for (i = 0; i < om->neq; i++) if (odecnt[i] && odediv[i] != 1.0) { cbprintf(b, "  case %d: return ", i); cb_double17(b, odediv[i]); CharBuffer_append(b, ";\n"); }
   CharBuffer_append(b, "  default: return 1.0;\n  }\n}\n");
   CharBuffer_append(b, "DEV double w_ode_case(int i, double t, const double *y, const double *a, const PvRef pv)\n{\n  (void)t; (void)y; (void)a; (void)pv;\n  switch (i) {\n");
   for (i = 0; i < om->neq; i++) { if (odecnt[i]) continue; cbprintf(b, "  case %d: return ", i); gen(b, om->ode[i], c); CharBuffer_append(b, ";\n"); }
@@ -793,7 +908,7 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
      interpreter does on the refreshed values; non-zero when mean + std is below the threshold */
   cbprintf(b, "#define HALT_ON_STEADY %d\n", (opt->SteadyState == 1 && om->neq > 0) ? 1 : 0);
   if (opt->SteadyState == 1 && om->neq > 0) {
-    CharBuffer_append(b, "#define SS_THRESHOLD "); CharBuffer_appendDouble(b, opt->ssThreshold); CharBuffer_append(b, "\n");
+    CharBuffer_append(b, "#define SS_THRESHOLD "); cb_double17(b, opt->ssThreshold); CharBuffer_append(b, "\n");
     CharBuffer_append(b, "DEV int steady_f(double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  double a[A1(NASS)], dy[A1(NEQ)], mean = 0.0, var = 0.0; (void)t; (void)a; (void)pv;\n");
     k.local = all_local; c.interp = 1;
     emit_refresh_all(b, om, &c, "  ");

@@ -395,12 +395,20 @@ int IntegratorInstance_handleError(integratorInstance_t *engine)
   (void)engine;
   return errorCode;
 }
-void IntegratorInstance_printCVODEStatistics(const integratorInstance_t *engine, FILE *f)
+int IntegratorInstance_printCVODEStatistics(const integratorInstance_t *engine, FILE *f)
 {
   const cvodeSolver_t *s = engine->solver;
   fprintf(f, "## CVode Statistics:\n");
   fprintf(f, "## nst = %-6ld nfe  = %-6ld nsetups = %-6ld nje = %ld\n", s->nst, s->nfe, s->nsetups, s->nje);
   fprintf(f, "## nni = %-6ld ncfn = %-6ld netf = %ld\n", s->nni, s->ncfn, s->netf);
+  return 1;
+}
+/* src/sensSolver.c:680-720: the state's counters and, with sensitivities, a note on what the device counted */
+int IntegratorInstance_printCVODESStatistics(const integratorInstance_t *engine, FILE *f)
+{
+  IntegratorInstance_printCVODEStatistics(engine, f);
+  if (engine->os) fprintf(f, "##\n## CVode Sensitivity: %d sensitivity vectors iterated with the state (simultaneous or staggered corrector)\n", engine->os->nsens);
+  return 1;
 }
 void IntegratorInstance_printStatistics(const integratorInstance_t *engine, FILE *f)
 {

@@ -740,6 +740,52 @@ const ASTNode_t *ODESense_getSensEntry(const odeSense_t *os, const variableIndex
   return NULL;
 }
 
+/* ------------------------------------------------------------ determinant of the Jacobian
+   Reference: ODEModel_constructDeterminant -> determinantNAST (src/odeModel.c:1950-1956).  Laplace expansion along the
+   first row of the symbolic Jacobian, structurally zero entries skipped; the result is a well-formed expression tree
+   (the reference's printout of its own tree has empty operands, unittest/test_odeModel.c:734-800: that text is not
+   reproduced). */
+static int entry_is_zero(const ASTNode_t *e)
+{
+  if (ASTNode_isInteger(e)) return ASTNode_getInteger(e) == 0;
+  if (ASTNode_isReal(e)) return ASTNode_getReal(e) == 0.0;
+  return 0;
+}
+static ASTNode_t *minor_det(ASTNode_t ***jac, const int *rows, const int *cols, int n)
+{
+  ASTNode_t *sum = NULL; int j, k, sign = 1;
+  if (n == 1) return copyAST(jac[rows[0]][cols[0]]);
+  for (j = 0; j < n; j++, sign = -sign) {
+    int *sub; ASTNode_t *m, *term;
+    if (entry_is_zero(jac[rows[0]][cols[j]])) continue;
+    sub = (int *)malloc((size_t)(n - 1) * sizeof(int));
+    for (k = 0; k < n - 1; k++) sub[k] = cols[k < j ? k : k + 1];
+    m = minor_det(jac, rows + 1, sub, n - 1);
+    free(sub);
+    if (!m) continue;
+    term = ASTNode_createWithType(AST_TIMES);
+    ASTNode_addChild(term, copyAST(jac[rows[0]][cols[j]])); ASTNode_addChild(term, m);
+    if (!sum) {
+      if (sign < 0) { ASTNode_t *neg = ASTNode_createWithType(AST_MINUS); ASTNode_addChild(neg, term); sum = neg; } else sum = term;
+    } else {
+      ASTNode_t *op = ASTNode_createWithType(sign < 0 ? AST_MINUS : AST_PLUS);
+      ASTNode_addChild(op, sum); ASTNode_addChild(op, term); sum = op;
+    }
+  }
+  return sum;                                     /* NULL: the minor vanishes structurally */
+}
+ASTNode_t *ODEModel_constructDeterminant(const odeModel_t *om)
+{
+  int i, *idx; ASTNode_t *det;
+  if (!om || !om->jacob || om->jacobian != 1 || om->neq < 1) return NULL;
+  idx = (int *)malloc((size_t)om->neq * sizeof(int));
+  for (i = 0; i < om->neq; i++) idx[i] = i;
+  det = minor_det(om->jacob, idx, idx, om->neq);
+  free(idx);
+  if (!det) { det = ASTNode_create(); ASTNode_setInteger(det, 0); }
+  return det;
+}
+
 void ODEModel_freeJacobian(odeModel_t *om)
 {
   int i, j;

@@ -534,7 +534,7 @@ void Model_free(Model_t *m)
   for (i = 0; i < m->species.size; i++) { Species_t *s = Model_getSpecies(m, i); free(s->id); free(s->compartment); free(s); }
   for (i = 0; i < m->parameters.size; i++) param_free(Model_getParameter(m, i));
   for (i = 0; i < m->initialAssignments.size; i++) { InitialAssignment_t *a = Model_getInitialAssignment(m, i); free(a->symbol); ASTNode_free(a->math); free(a); }
-  for (i = 0; i < m->rules.size; i++) { Rule_t *r = Model_getRule(m, i); free(r->variable); ASTNode_free(r->math); free(r); }
+  for (i = 0; i < m->rules.size; i++) { Rule_t *r = Model_getRule(m, i); free(r->variable); ASTNode_free(r->math); free(r->formula); free(r); }
   for (i = 0; i < m->reactions.size; i++) {
     Reaction_t *r = Model_getReaction(m, i);
     for (j = 0; j < r->reactants.size; j++) sref_free((SpeciesReference_t *)r->reactants.items[j]);
@@ -544,7 +544,7 @@ void Model_free(Model_t *m)
     if (r->kineticLaw) {
       ASTNode_free(r->kineticLaw->math);
       for (j = 0; j < r->kineticLaw->parameters.size; j++) param_free((Parameter_t *)r->kineticLaw->parameters.items[j]);
-      free(r->kineticLaw->parameters.items); free(r->kineticLaw);
+      free(r->kineticLaw->parameters.items); free(r->kineticLaw->formula); free(r->kineticLaw);
     }
     free(r->id); free(r);
   }
@@ -882,3 +882,47 @@ SBMLReader_t *SBMLReader_create(void) { return (SBMLReader_t *)calloc(1, sizeof(
 SBMLDocument_t *SBMLReader_readSBML(SBMLReader_t *sr, const char *filename) { (void)sr; return readSBML(filename); }
 SBMLDocument_t *SBMLReader_readSBMLFromString(SBMLReader_t *sr, const char *xml) { (void)sr; return readSBMLFromString(xml); }
 void SBMLReader_free(SBMLReader_t *sr) { free(sr); }
+
+/* ------------------------------------------------------ libSBML-named accessors */
+const char *Compartment_getId(const Compartment_t *c) { return c->id; }
+const char *Species_getId(const Species_t *s) { return s->id; }
+const char *Parameter_getId(const Parameter_t *p) { return p->id; }
+double Parameter_getValue(const Parameter_t *p) { return p->value; }
+void Parameter_setValue(Parameter_t *p, double v) { p->value = v; p->isSetValue = 1; }
+void Parameter_setName(Parameter_t *p, const char *name) { (void)p; (void)name; }       /* names are not kept */
+void Parameter_setConstant(Parameter_t *p, int c) { p->constant = c; }
+void Compartment_setConstant(Compartment_t *c, int v) { c->constant = v; }
+Parameter_t *Parameter_create(void) { Parameter_t *p = (Parameter_t *)calloc(1, sizeof *p); p->constant = 1; return p; }
+Parameter_t *Parameter_createWith(const char *id, const char *name) { Parameter_t *p = Parameter_create(); (void)name; Parameter_setId(p, id); return p; }
+void Parameter_free(Parameter_t *p) { param_free(p); }
+const char *Reaction_getId(const Reaction_t *r) { return r->id; }
+KineticLaw_t *Reaction_getKineticLaw(const Reaction_t *r) { return r->kineticLaw; }
+const ASTNode_t *KineticLaw_getMath(const KineticLaw_t *k) { return k->math; }
+const char *KineticLaw_getFormula(const KineticLaw_t *ck)
+{
+  KineticLaw_t *k = (KineticLaw_t *)ck;
+  free(k->formula);
+  k->formula = k->math ? SBML_formulaToString(k->math) : NULL;
+  return k->formula;
+}
+const char *Rule_getFormula(const Rule_t *cr)
+{
+  Rule_t *r = (Rule_t *)cr;
+  free(r->formula);
+  r->formula = r->math ? SBML_formulaToString(r->math) : NULL;
+  return r->formula;
+}
+const char *Rule_getVariable(const Rule_t *r) { return r->variable; }
+unsigned int Model_getNumUnitDefinitions(const Model_t *m) { (void)m; return 0; }
+unsigned int Model_getNumSpeciesTypes(const Model_t *m) { (void)m; return 0; }
+unsigned int Model_getNumCompartmentTypes(const Model_t *m) { (void)m; return 0; }
+unsigned int Model_getNumConstraints(const Model_t *m) { (void)m; return 0; }
+unsigned int Model_getNumSpeciesWithBoundaryCondition(const Model_t *m)
+{
+  unsigned int i, n = 0;
+  for (i = 0; i < m->species.size; i++) if (Model_getSpecies(m, i)->boundaryCondition) n++;
+  return n;
+}
+ListOf_t *ListOf_create(void) { return (ListOf_t *)calloc(1, sizeof(ListOf_t)); }
+void ListOf_appendAndOwn(ListOf_t *l, SBase_t *item) { ListOf_append(l, item); }
+void ListOf_free(ListOf_t *l) { if (l) { free(l->items); free(l); } }

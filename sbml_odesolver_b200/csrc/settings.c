@@ -147,7 +147,7 @@ int CvodeSettings_getHaltOnSteadyState(cvodeSettings_t *s) { return s->SteadySta
 double CvodeSettings_getSteadyStateThreshold(cvodeSettings_t *s) { return s->ssThreshold; }
 int CvodeSettings_getStoreResults(cvodeSettings_t *s) { return s->StoreResults; }
 int CvodeSettings_getSensitivity(cvodeSettings_t *s) { return s->Sensitivity; }
-const char *CvodeSettings_getSensMethod(const cvodeSettings_t *s) { static const char *m[] = { "SIMULTANEOUS", "STAGGERED", "STAGGERED1" }; return m[s->SensMethod]; }
+const char *CvodeSettings_getSensMethod(const cvodeSettings_t *s) { static const char *m[] = { "simultaneous", "staggered", "staggered1" }; return m[s->SensMethod]; }
 void CvodeSettings_dump(cvodeSettings_t *set)
 {
   printf("\nSOSlib INTEGRATION SETTINGS\n1) CVODE SPECIFIC SETTINGS:\n");
@@ -164,3 +164,15 @@ void CvodeSettings_dump(cvodeSettings_t *set)
   if (set->Indefinitely) printf("Infinite integration with time step %g\n", set->Time);
   else printf("endtime: %g\nsteps:   %d\n", set->TimePoints[set->PrintStep], set->PrintStep);
 }
+
+/* src/integratorSettings.c:1153-1183; tmult keeps the reference's sign, (t0 - tend) / nout (unittest/test_integratorSettings.c:7-15) */
+timeSettings_t *TimeSettings_create(double t0, double tend, int nout)
+{
+  timeSettings_t *ts;
+  assert(nout > 0);
+  ts = (timeSettings_t *)calloc(1, sizeof *ts);
+  ts->t0 = t0; ts->tend = tend; ts->nout = nout; ts->tmult = (t0 - tend) / nout;
+  return ts;
+}
+void TimeSettings_free(timeSettings_t *ts) { free(ts); }
+cvodeSettings_t *CvodeSettings_createFromTimeSettings(timeSettings_t *ts) { return CvodeSettings_createWithTime(ts->tend, ts->nout); }

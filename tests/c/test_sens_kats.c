@@ -64,7 +64,7 @@ int main(int argc, char **argv)
   CvodeSettings_setSensMethod(cs, 0);
   CvodeSettings_setSensParams(cs, (char **)params, 4);
   CK(CvodeSettings_getSensitivity(cs) == 1 && cs->nsens == 4 && strcmp(cs->sensIDs[2], "K1") == 0);
-  CK(strcmp(CvodeSettings_getSensMethod(cs), "SIMULTANEOUS") == 0);
+  CK(strcmp(CvodeSettings_getSensMethod(cs), "simultaneous") == 0);
   if (argc > 2 && strcmp(argv[2], "cpu") == 0) goto done;
 
   /* the fixture of unittest/test_sensSolver.c */
