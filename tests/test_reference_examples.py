@@ -205,3 +205,19 @@ def test_senstest_prints_the_reference_text_for_the_analytic_cases(tmp_path):
     gold = [l for l in _gold("testrun_senstest_analytic.txt") if l.strip()]
     body = [l for l in out if l.strip()]
     assert body[:len(gold)] == gold, "\n".join(f"{a!r} != {b!r}" for a, b in zip(body, gold) if a != b)[:2000]
+
+
+@have
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog,args", [("TwinIntegratorInstance", []), ("SharingIntegratorInstance", []), ("ChangingParameterIntegrator", []),
+                                       ("integrateODEs", []),
+                                       ("batch_integrate", ["MAPK.xml", "1000", "2", "1", "10", "5", "V1", "1", "10", "10", "k4", "J3"]),
+                                       ("bistability", ["MAPK.xml", "MAPK_PP", "Ki", "5", "15", "5", "K1", "5", "15", "5", "100"])])
+def test_further_reference_programs_run_to_completion(tmp_path, prog, args):
+    """Programs without a golden section in examples/testrun.out: they have to run through this library and exit cleanly
+    (two and shared integrator instances on the events models, parameters changed during a run, ODEs given as formulas
+    without an SBML file, the reference's batch driver on a 5 x 10 grid with a kinetic-law parameter, a 2-D scan to steady
+    states)."""
+    r, out = _run(tmp_path, prog, *args)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert len([l for l in out if l.strip()]) > 3
