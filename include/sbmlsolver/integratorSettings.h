@@ -1,7 +1,8 @@
 /*
  * integratorSettings.h -- cvodeSettings_t, field-for-field the reference's
  * src/sbmlsolver/integratorSettings.h:56-148 for the forward path (forward
- * sensitivities, simultaneous corrector, are honoured by the batched kernel; the adjoint switches are inert fields).
+ * sensitivities with the simultaneous or the staggered corrector are honoured by the batched kernel; the adjoint switches are
+ * inert fields).
  * Functions: reference integratorSettings.h:172-245.
  */
 #ifndef ODES_B200_INTEGRATORSETTINGS_H
