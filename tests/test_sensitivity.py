@@ -269,3 +269,22 @@ def test_model_odesolverbatch_maps_sensitivities_per_design_point():
         assert np.array_equal(got, sens[k, :, :, 1].T)
     L.SBMLResultsArray_free(res)
     L.VarySettings_free(vs)
+
+
+@needs_ref
+def test_failed_trajectories_leave_not_a_number_rows_in_states_and_sensitivities():
+    """mxstep too small: CV_TOO_MUCH_WORK at the same output interval as the reference, the rows before it identical, the rows
+    after it not-a-number in the states AND the sensitivities."""
+    w = _case("mapk", nout=6)
+    m = w["model"]
+    vals = H.workload_values(w, 5, seed=8)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    tp = H.tpoints(w["opt"], 6)
+    base, trig = b.base_values()
+    got = H.Emu(b, "mapk_sens0").run(base, trig, vals, tp, 15, w["rtol"], w["atol"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 15, w["rtol"], w["atol"], tag="mapk_sens")
+    b.close()
+    assert (ref["status"] == -4).all() and np.array_equal(got["status"], ref["status"])
+    assert np.isnan(ref["sens"]).any() and not np.isnan(ref["sens"][:, 0]).any()
+    assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"], equal_nan=True)
+    assert np.array_equal(got["sens"], ref["sens"], equal_nan=True)
