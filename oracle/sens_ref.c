@@ -37,7 +37,7 @@ typedef void (*c_ode_fn)(double t, const double *y, double *ydot, double *value)
 typedef void (*c_jac_fn)(double t, const double *y, double *J, double *value);
 typedef void (*c_sens_fn)(int iS, double t, const double *y, const double *yS, double *ySdot, double *value);
 
-/* SensMethod of the next batch calls (0 simultaneous, 1 staggered); set by the test helper before a run */
+/* SensMethod of the next batch calls (0 simultaneous, 1 staggered, 2 staggered1); set by the test helper before a run */
 int refcvs_sens_method = 0;
 
 typedef struct { int neq; double *value; c_ode_fn f; c_jac_fn j; c_sens_fn s; } ctx_t;
@@ -229,7 +229,7 @@ int refcvs_integrate_batch_events(const char *compiled_so, int neq, int nvalues,
     jb->rtol = rtol; jb->atol = atol; jb->out = out; jb->sens = sens; jb->status = status; jb->stats = stats;
     jb->f = f; jb->j = j; jb->s = s;
     jb->om = om; jb->resetOnEvent = resetOnEvent; jb->haltOnEvent = haltOnEvent; jb->trigger0 = trigger0; jb->fired = fired;
-    jb->ism = refcvs_sens_method == 1 ? CV_STAGGERED : CV_SIMULTANEOUS;
+    jb->ism = refcvs_sens_method == 1 ? CV_STAGGERED : refcvs_sens_method == 2 ? CV_STAGGERED1 : CV_SIMULTANEOUS;
     if (nthreads == 1) run_range(jb); else pthread_create(&th[k], NULL, run_range, jb);
   }
   for (k = 0; k < nthreads; k++) { if (nthreads > 1) pthread_join(th[k], NULL); failed += jobs[k].failed; }

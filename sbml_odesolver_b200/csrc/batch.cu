@@ -444,7 +444,7 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
   if (opt->Sensitivity) {
     const char *why = NULL;
     if (!(opt->UseJacobian && om->jacobian)) why = "forward sensitivities need the analytic Jacobian";
-    else if (opt->SensMethod != 0 && opt->SensMethod != 1) why = "the batched kernel implements the simultaneous and the staggered corrector (SensMethod 0, 1), not staggered1";
+    else if (opt->SensMethod < 0 || opt->SensMethod > 2) why = "SensMethod must be 0 (simultaneous), 1 (staggered) or 2 (staggered1)";
     else if (om->neq < 1 || om->neq > 32) why = "forward sensitivities are implemented for 1..32 equations (one trajectory per warp)";
     if (!why) {
       b->os = ODESense_create(om, opt);

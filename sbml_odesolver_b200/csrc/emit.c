@@ -799,7 +799,7 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
   cbprintf(b, "#define NEQ %d\n#define NASS %d\n#define NVAL %d\n#define NEVENTS %d\n#define NPV %d\n#define NVARY %d\n#define NSTORE %d\n#define NNZ %d\n#define HAS_JAC %d\n#define USE_TSTOP %d\n",
            om->neq, om->nass, nvalues, om->nevents, npv, nvary, nstore, usejac ? om->sparsesize : 0, usejac, (opt->SetTStop || om->npiecewise) ? 1 : 0);
   cbprintf(b, "#define RESET_ON_EVENT %d\n#define HALT_ON_EVENT %d\n", opt->ResetCvodeOnEvent ? 1 : 0, opt->HaltOnEvent ? 1 : 0);
-  cbprintf(b, "#define NSENS %d\n#define SENS_STAGGERED %d\n", (os && usejac) ? os->nsens : 0, (os && usejac && opt->SensMethod == 1) ? 1 : 0);
+  cbprintf(b, "#define NSENS %d\n#define SENS_STAGGERED %d\n", (os && usejac) ? os->nsens : 0, (os && usejac) ? opt->SensMethod : 0);
   CharBuffer_append(b, "#define A1(n) ((n) > 0 ? (n) : 1)\n#define DEV __device__ __forceinline__\n");
   /* per-trajectory constants live in strided shared memory (word k of this thread at p[k*s]) */
   CharBuffer_append(b, "#ifndef ODES_BLOCK\n#define ODES_BLOCK 64\n#endif\n#ifndef ODES_MAT_LOCAL\n#define ODES_MAT_LOCAL 0\n#endif\n"
