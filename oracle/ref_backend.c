@@ -14,6 +14,10 @@
 #include "nvector_serial.h"
 #include "oracle.h"
 
+/* linear multistep method of solvers created from now on: 0 BDF (the default), 1 Adams-Moulton (cvodeSettings_t.CvodeMethod);
+   set by the test helper before a run */
+int refcv_adams = 0;
+
 typedef struct {
   int n; oracle_rhs_fn f; oracle_jac_fn jac; void *user;
   void *mem; N_Vector y, abstol; int created; long tot[7];
@@ -49,7 +53,7 @@ int refcv_init(void *h, double t0, const double *y0, double reltol, double absto
   ref_t *r = (ref_t *)h; int i, flag;
   for (i = 0; i < r->n; i++) { NV_Ith_S(r->y, i) = y0[i]; NV_Ith_S(r->abstol, i) = abstol; }
   if (!r->created) {
-    r->mem = CVodeCreate(CV_BDF, CV_NEWTON);
+    r->mem = CVodeCreate(refcv_adams ? CV_ADAMS : CV_BDF, CV_NEWTON);
     if (!r->mem) return -1;
     CVodeSetErrFile(r->mem, NULL);
     flag = CVodeMalloc(r->mem, f_cb, t0, r->y, CV_SV, reltol, r->abstol);

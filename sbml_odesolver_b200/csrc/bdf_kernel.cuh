@@ -134,8 +134,16 @@ __device__ __forceinline__ unsigned long long odes_take_sets(unsigned long long 
 #define FW_NEWTON 1     /* f(tn, y) inside the Newton iteration */
 #define FW_RESTART 2    /* f(tn, zn[0]) to reload zn[1] at order 1 after repeated error-test failures */
 
+#ifndef ODES_ADAMS
+#define ODES_ADAMS 0          /* 1: Adams-Moulton (orders 1..12) instead of BDF (1..5); warp-per-trajectory kernel only */
+#endif
+#if ODES_ADAMS
+#define QMAX 12
+#define LMAX 13
+#else
 #define QMAX 5
 #define LMAX 6
+#endif
 #define UROUND 2.2204460492503131e-16
 
 /* CVODE control constants (cvode.c:40-143, cvdense.h:43-44) */

@@ -148,6 +148,7 @@ double CvodeSettings_getSteadyStateThreshold(cvodeSettings_t *s) { return s->ssT
 int CvodeSettings_getStoreResults(cvodeSettings_t *s) { return s->StoreResults; }
 int CvodeSettings_getSensitivity(cvodeSettings_t *s) { return s->Sensitivity; }
 const char *CvodeSettings_getSensMethod(const cvodeSettings_t *s) { static const char *m[] = { "simultaneous", "staggered", "staggered1" }; return m[s->SensMethod]; }
+/* the reference's printout, line for line (src/integratorSettings.c:83-127; examples/testrun.out:246-266) */
 void CvodeSettings_dump(cvodeSettings_t *set)
 {
   printf("\nSOSlib INTEGRATION SETTINGS\n1) CVODE SPECIFIC SETTINGS:\n");
@@ -157,12 +158,18 @@ void CvodeSettings_dump(cvodeSettings_t *set)
   printf("Nonlinear solver method:                         %d: %s\n          Maximum Order:                         %d\n",
          set->CvodeMethod, CvodeSettings_getMethod(set), set->MaxOrder);
   printf("Iteration method:                                %d: %s\n", set->IterMethod, CvodeSettings_getIterMethod(set));
+  printf("Sensitivity:                                     %s\n", set->Sensitivity ? "1: yes " : "0: no");
+  printf("     method:                                     %d: %s\n", set->SensMethod, CvodeSettings_getSensMethod(set));
   printf("2) SOSlib SPECIFIC SETTINGS:\nJacobian matrix: %s\n", set->UseJacobian ? "1: generate Jacobian" : "0: CVODE's internal approximation");
+  printf("Indefinitely:    %s\n", set->Indefinitely ? "1: infinite integration" : "0: finite integration");
   printf("Event Handling:  %s\n", set->HaltOnEvent ? "1: stop integration" : "0: keep integrating");
+  printf("Steady States:   %s\n", set->SteadyState ? "1: stop integrating" : "0: keep integrating");
+  printf("Steady state threshold: %g\n", set->ssThreshold);
   printf("Store Results:   %s\n", set->StoreResults ? "1: store results (only for finite integration)" : "0: don't store results");
   printf("3) TIME SETTINGS:\n");
-  if (set->Indefinitely) printf("Infinite integration with time step %g\n", set->Time);
-  else printf("endtime: %g\nsteps:   %d\n", set->TimePoints[set->PrintStep], set->PrintStep);
+  if (set->Indefinitely) printf("Infinite integration with time step %g", set->Time);
+  else printf("endtime: %g\nsteps:   %d", set->TimePoints[set->PrintStep], set->PrintStep);
+  printf("\n\n");
 }
 
 /* src/integratorSettings.c:1153-1183; tmult keeps the reference's sign, (t0 - tend) / nout (unittest/test_integratorSettings.c:7-15) */

@@ -88,3 +88,4 @@ section(411, 497, "testrun_analyzeSens.txt", "./analyzeSens (examples/analyzeSen
 section(1198, 1608, "testrun_Sense.txt", "./Sense MAPK.xml 200 7.5 p Ki MKKK_P MAPK_PP (examples/Sense.c)")
 section(320, 350, "testrun_changeIntInst.txt", "./changeIntInst (examples/ChangingIntegratorInstance.c on basic-model1-forward-l2.xml: two instances, the second one with values changed on the way)")
 section(1826, 1863, "testrun_senstest_analytic.txt", "./senstest, first part (examples/senstest.c:45-150: repeated runs, default and selected sensitivities with analytic matrices; the rest uses CVODES' internal difference quotients)")
+section(244, 318, "testrun_simpleIntInst.txt", "./simpleIntInst (examples/simpleIntegratorInstance.c on basic-model1-forward-l2.xml: indefinite Adams-Moulton run from t = 0.05, then a finite BDF run with other settings)")

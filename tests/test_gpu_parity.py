@@ -368,3 +368,17 @@ def test_time_dependent_model_on_gpu(tmp_path):
     assert np.array_equal(b.stats(500).T, ref["stats"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))
     b.close()
+
+
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 512, None), ("goodwin", 128, None), ("events", 256, None), ("huang", 64, None)])
+def test_adams_moulton_on_gpu(name, nsets, nout):
+    """CvodeMethod 1 (Adams-Moulton, orders 1..12) in the warp kernel: bit-identical to the vendored CVODE with CV_ADAMS."""
+    w = H.workload(name, nout=nout, method=1)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=2028)
+    got = _gpu_run(w, vals)
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF, compiled_so=H.compile_c_model(m, name), threads=8, adams=True)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"], ref["stats"])
+    assert np.array_equal(got["fired"], ref["fired"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)

@@ -221,3 +221,14 @@ def test_further_reference_programs_run_to_completion(tmp_path, prog, args):
     r, out = _run(tmp_path, prog, *args)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
     assert len([l for l in out if l.strip()]) > 3
+
+
+@have
+@pytest.mark.gpu
+def test_simpleIntegratorInstance_prints_the_reference_text(tmp_path):
+    """Settings dumps, an INDEFINITE ADAMS-MOULTON run (orders up to 12, atol 1e-20, rtol 1e-14) started at t = 0.05 with
+    IntegratorInstance_setInitialTime, then IntegratorInstance_set with new settings and a finite BDF run
+    (testrun.out:244-318) -- every printed digit."""
+    r, out = _run(tmp_path, "simpleIntegratorInstance")
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    _same_text(out, "testrun_simpleIntInst.txt")
