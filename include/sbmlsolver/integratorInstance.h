@@ -25,6 +25,7 @@ struct cvodeSolver {
   /* device-side integration of the remaining time course (batch of one) */
   struct odesBatch *plan;
   unsigned long planSignature; /* of the settings the plan was specialised for */
+  int lmmCreated;              /* 0: no solver yet, else 1 + CvodeMethod of the first run (kept for the life of the instance) */
   cvodeSettings_t *planOpt;   /* indefinite integration: the finite look-ahead grid the plan was created with */
   double *course;      /* [nsteps][nvalues] rows computed ahead by the device */
   int *courseFired;    /* [nsteps] event bitmask per row                       */

@@ -389,8 +389,8 @@ DEV double inv_int(int j) { return c_inv_int[j]; }
 ODES_NOINLINE double root_pow(double x, int n)
 {
   if (x <= 0.0) return 0.0;
-  if (n > 7 || !(x > 1e-300 && x < 1e300)) return pow(x, 1.0 / n);
-  return odes_glibc_pow(x, inv_int(n));
+  if (!(x > 1e-300 && x < 1e300)) return pow(x, 1.0 / n);
+  return odes_glibc_pow(x, n <= 7 ? inv_int(n) : 1.0 / n);     /* n up to 13 with Adams-Moulton (orders 1..12) */
 }
 ODES_NOINLINE double rsqrt_(double x) { return x <= 0.0 ? 0.0 : sqrt(x); }
 #if !ODES_WARP

@@ -194,12 +194,20 @@ static int compute_course(integratorInstance_t *engine)
      solver at the look-ahead boundary */
   const int indefinite = engine->opt->Indefinitely;
   cvodeSettings_t *planOpt = engine->opt;
-  if (indefinite) {
+  /* an instance keeps the linear multistep method its solver memory was first created with: the reference re-initialises
+     that memory for later runs and cannot change the method then ("problem with ReInit: can't use new method",
+     src/cvodeSolver.c:541-547) -- examples/simpleIntegratorInstance.c's second run announces BDF and integrates with
+     Adams-Moulton (examples/testrun.out:281-310) */
+  if (solver->lmmCreated == 0) solver->lmmCreated = 1 + engine->opt->CvodeMethod;
+  if (indefinite || engine->opt->CvodeMethod != solver->lmmCreated - 1) {
     if (!solver->planOpt) {
       solver->planOpt = CvodeSettings_clone(engine->opt);
-      solver->planOpt->Indefinitely = 0;
-      CvodeSettings_setTime(solver->planOpt, engine->opt->Time * ODES_LOOKAHEAD, ODES_LOOKAHEAD);
-      solver->planOpt->StoreResults = 0;
+      solver->planOpt->CvodeMethod = solver->lmmCreated - 1;
+      if (indefinite) {
+        solver->planOpt->Indefinitely = 0;
+        CvodeSettings_setTime(solver->planOpt, engine->opt->Time * ODES_LOOKAHEAD, ODES_LOOKAHEAD);
+        solver->planOpt->StoreResults = 0;
+      }
     }
     planOpt = solver->planOpt;
   }
