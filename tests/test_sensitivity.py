@@ -24,13 +24,14 @@ CASES = {
     "huang": dict(ids=["r_r1a_a1", "KKK", "r_r10b_k10"], nout=None),
     "goodwin": dict(ids=None, nout=20),                        # default: every constant of the model
     "events": dict(ids=["S1", "compartment", "S2"], nout=None),  # events re-initialise the solver from the current sensitivities
+    "huang_all": dict(ids=None, nout=20, workload="huang"),    # 22 equations, all 31 constants: one vector per slab, 32 slabs
 }
 needs_ref = pytest.mark.skipif(not H.have_sens_ref(), reason="oracle/_ref/libcvodes_ref.so not built")
 
 
 def _case(name, nout=None, method=0):
     c = CASES[name]
-    w = H.workload(name, nout=nout if nout is not None else c["nout"], sensitivity=1, sens_ids=c["ids"], sens_method=method)
+    w = H.workload(c.get("workload", name), nout=nout if nout is not None else c["nout"], sensitivity=1, sens_ids=c["ids"], sens_method=method)
     return w
 
 
@@ -78,7 +79,7 @@ def test_emitted_sense_function_follows_the_reference_generator():
 
 @needs_ref
 @pytest.mark.parametrize("method", [0, 1, 2])
-@pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6), ("events", 24)])
+@pytest.mark.parametrize("name,nsets", [("mapk", 24), ("repressilator", 6), ("huang", 6), ("goodwin", 6), ("events", 24), ("huang_all", 2)])
 def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets, method):
     """method 0: CV_SIMULTANEOUS (the reference's default), 1: CV_STAGGERED, 2: CV_STAGGERED1 (src/sensSolver.c:286-290)."""
     w = _case(name, method=method)
@@ -167,7 +168,7 @@ def test_unsupported_sensitivity_configurations_fail_loudly():
 @pytest.mark.gpu
 @needs_ref
 @pytest.mark.parametrize("method", [0, 1, 2])
-@pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64), ("events", 512)])
+@pytest.mark.parametrize("name,nsets", [("mapk", 512), ("repressilator", 64), ("huang", 96), ("goodwin", 64), ("events", 512), ("huang_all", 32)])
 def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets, method):
     w = _case(name, method=method)
     m = w["model"]
