@@ -208,11 +208,11 @@ class Model:
 
 
 def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1, steady_state=0, ss_threshold=None,
-             sensitivity=0, sens_ids=None, sens_method=0, method=0):
+             sensitivity=0, sens_ids=None, sens_method=0, method=0, iter_method=0):
     """CvodeSettings_createWith(Time, PrintStep, Error, RError, Mxstep, Method (0 BDF, 1 Adams-Moulton), Iter=Newton, ...).
     sensitivity=1 switches forward sensitivity analysis on (sens_method 0: simultaneous corrector, 1: staggered); sens_ids: ids of the parameters /
     variables (CvodeSettings_setSensParams), None = all constants of the model."""
-    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, method, 0, use_jacobian, 0, halt_on_event, steady_state, store_results, sensitivity, sens_method)
+    opt = lib().CvodeSettings_createWith(end_time, print_step, atol, rtol, mxstep, method, iter_method, use_jacobian, 0, halt_on_event, steady_state, store_results, sensitivity, sens_method)
     _check(opt, "CvodeSettings_createWith")
     if sens_ids is not None:
         arr = (c_s * len(sens_ids))(*[x.encode() for x in sens_ids])

@@ -372,7 +372,7 @@ static std::string build_source(odesBatch_t *b)
      n = 20 0.51 M vs 0.56 M, n = 24 0.26 M vs 0.48 M, n = 32 0.11 M vs 0.38 M trajectories/s; huang96 (n = 22) 82 k vs 174 k */
   if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
   if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
-  if (b->opt->CvodeMethod == 1) warp = 1;       /* and so does Adams-Moulton */
+  if (b->opt->CvodeMethod == 1 || b->opt->IterMethod == 1) warp = 1;       /* and so do Adams-Moulton and functional iteration */
   if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
   b->warpMode = warp;
   if (warp) {
@@ -385,8 +385,8 @@ static std::string build_source(odesBatch_t *b)
     if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[512];
-    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_ADAMS=%d -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->opt->CvodeMethod == 1 ? 1 : 0, wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
@@ -426,9 +426,9 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
   if (!om || !opt) return NULL;
   if (om->hasCycle) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_ODE_MODEL_CYCLIC_DEPENDENCY_IN_RULES, "model rules contain a cycle"); return NULL; }
   if (opt->Indefinitely || !opt->TimePoints) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "batched integration needs a finite output grid"); return NULL; }
-  if ((opt->CvodeMethod != 0 && opt->CvodeMethod != 1) || opt->IterMethod != 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the batched kernel implements BDF and Adams-Moulton with Newton iteration only"); return NULL; }
-  if (opt->CvodeMethod == 1 && (opt->Sensitivity || om->neq < 1 || om->neq > 32 || !opt->UseJacobian)) {
-    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "Adams-Moulton runs in the warp-per-trajectory kernel: 1..32 equations, analytic Jacobian, no sensitivities");
+  if ((opt->CvodeMethod != 0 && opt->CvodeMethod != 1) || (opt->IterMethod != 0 && opt->IterMethod != 1)) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "CvodeMethod must be 0 (BDF) or 1 (Adams-Moulton), IterMethod 0 (Newton) or 1 (functional)"); return NULL; }
+  if ((opt->CvodeMethod == 1 || opt->IterMethod == 1) && (opt->Sensitivity || om->neq < 1 || om->neq > 32 || !opt->UseJacobian)) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "Adams-Moulton and functional iteration run in the warp-per-trajectory kernel: 1..32 equations, analytic Jacobian available, no sensitivities");
     return NULL;
   }
   if (om->nevents > 32) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "at most 32 events are supported"); return NULL; }

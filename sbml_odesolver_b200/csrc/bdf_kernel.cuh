@@ -137,6 +137,9 @@ __device__ __forceinline__ unsigned long long odes_take_sets(unsigned long long 
 #ifndef ODES_ADAMS
 #define ODES_ADAMS 0          /* 1: Adams-Moulton (orders 1..12) instead of BDF (1..5); warp-per-trajectory kernel only */
 #endif
+#ifndef ODES_FUNCTIONAL
+#define ODES_FUNCTIONAL 0      /* 1: functional (fixed-point) iteration instead of Newton; warp-per-trajectory kernel only */
+#endif
 #if ODES_ADAMS
 #define QMAX 12
 #define LMAX 13

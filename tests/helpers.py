@@ -39,16 +39,18 @@ def model_path(name):
     return os.path.join(MODELS, name)
 
 
-def oracle_run(model, opt, vary, values, nout, backend=PORT, threads=1, compiled_so=None, want_margin=False, adams=False):
+def oracle_run(model, opt, vary, values, nout, backend=PORT, threads=1, compiled_so=None, want_margin=False, adams=False, functional=False):
     """Returns dict(out[nsets][nout+1][nvalues], status, stats[nsets][7], fired[nsets][nout+1]).
     adams: Adams-Moulton instead of BDF -- only the vendored CVODE (backend=REF) has it."""
-    if adams:
-        assert backend == REF, "the restated port holds BDF only"
-        C.c_int.in_dll(C.CDLL(REF_LIB), "refcv_adams").value = 1
+    if adams or functional:
+        assert backend == REF, "the restated port holds BDF with Newton iteration only"
+        C.c_int.in_dll(C.CDLL(REF_LIB), "refcv_adams").value = int(adams)
+        C.c_int.in_dll(C.CDLL(REF_LIB), "refcv_functional").value = int(functional)
         try:
             return oracle_run(model, opt, vary, values, nout, backend=backend, threads=threads, compiled_so=compiled_so, want_margin=want_margin)
         finally:
             C.c_int.in_dll(C.CDLL(REF_LIB), "refcv_adams").value = 0
+            C.c_int.in_dll(C.CDLL(REF_LIB), "refcv_functional").value = 0
     values = np.ascontiguousarray(values, dtype=np.float64)
     nsets = values.shape[0]
     vary = np.ascontiguousarray(vary, dtype=np.int32)
@@ -154,7 +156,7 @@ class Emu:
         if not os.path.exists(lib):
             open(cu, "w").write(src)
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
-                                  ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W") or t.startswith("-DODES_ADAMS")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
+                                  ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W") or t.startswith("-DODES_ADAMS") or t.startswith("-DODES_FUNCTIONAL")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
                                    f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
         self.lib = C.CDLL(lib)
         self.batch = batch

@@ -162,3 +162,23 @@ def test_emulated_adams_moulton_is_bit_identical_to_vendored_cvode(name, nsets, 
     # Adams and BDF are different methods: the step counts differ from the BDF run of the same sets
     bdf = H.oracle_run(m, H.workload(name, nout=nout)["opt"], w["vary"], vals, w["nout"], backend=H.REF, compiled_so=H.compile_c_model(m, name))
     assert not np.array_equal(bdf["stats"], ref["stats"])
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref/libcvode_ref.so not built")
+@pytest.mark.parametrize("name,method,nsets,nout", [("goodwin", 1, 8, None), ("goodwin", 0, 8, None), ("mapk", 1, 8, 30), ("repressilator", 1, 4, 60), ("events", 1, 16, None)])
+def test_emulated_functional_iteration_is_bit_identical_to_vendored_cvode(name, method, nsets, nout):
+    """cvodeSettings_t.IterMethod = 1: CVnlsFunctional (cvode.c:2180-2225), the fixed-point corrector without matrix, with BDF or
+    (the classic non-stiff pairing) Adams-Moulton.  Checker: the vendored CVODE with CV_FUNCTIONAL."""
+    w = H.workload(name, nout=nout, method=method, iter_method=1)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=22)
+    b = so.Batch(m, w["opt"], w["vary"])
+    assert "-DODES_FUNCTIONAL=1" in b.source().split("\n")[0]
+    base, trig = b.base_values()
+    got = H.Emu(b, name + "_func%d" % method).run(base, trig, vals, H.tpoints(w["opt"], w["nout"]), 10000, w["rtol"], w["atol"])
+    b.close()
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF, compiled_so=H.compile_c_model(m, name), adams=bool(method), functional=True)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"].T, ref["stats"]) and (ref["stats"][:, 2:5] == 0).all()      # no set-ups, Jacobians, Newton iterations
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)

@@ -382,3 +382,17 @@ def test_adams_moulton_on_gpu(name, nsets, nout):
     assert np.array_equal(got["stats"], ref["stats"])
     assert np.array_equal(got["fired"], ref["fired"])
     assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+
+
+@pytest.mark.parametrize("name,method,nsets", [("goodwin", 1, 128), ("goodwin", 0, 128), ("events", 1, 256)])
+def test_functional_iteration_on_gpu(name, method, nsets):
+    """IterMethod 1 (CVnlsFunctional) with BDF or Adams-Moulton in the warp kernel: bit-identical to the vendored CVODE."""
+    w = H.workload(name, method=method, iter_method=1)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=2029)
+    got = _gpu_run(w, vals)
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF, compiled_so=H.compile_c_model(m, name), threads=8, adams=bool(method), functional=True)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["stats"], ref["stats"])
+    assert np.array_equal(got["fired"], ref["fired"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
