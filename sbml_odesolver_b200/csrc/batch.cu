@@ -384,9 +384,9 @@ static std::string build_source(odesBatch_t *b)
     int slabs = 1;                            /* register slabs of the packed layout (bdf_warp_kernel.cuh: W_S) */
     if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
-    char headw[512];
-    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
+    char headw[640];
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
