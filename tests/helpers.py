@@ -35,6 +35,12 @@ def have_ref():
     return os.path.exists(REF_LIB)
 
 
+def gpu_tier_backend():
+    """Checker of the GPU tier: the reference's own vendored CVODE (oracle/_ref, travels to the GPU box) when it was built,
+    else the restated port (bit-identical to it in the CPU tier, tests/test_oracle_golden.py)."""
+    return REF if have_ref() else PORT
+
+
 def model_path(name):
     return os.path.join(MODELS, name)
 

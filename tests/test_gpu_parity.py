@@ -26,12 +26,26 @@ def _gpu_run(w, vals, store=None):
     return r
 
 
-def _oracle(w, vals):
+# The checker of the GPU tier is the reference's OWN arithmetic: the vendored cvode.c / cvdense.c / smalldense.c compiled
+# unmodified into oracle/_ref/libcvode_ref.so (backend REF).  The restated port (equal to it bit for bit in the CPU tier,
+# tests/test_oracle_golden.py) is only the fallback where oracle/_ref was not built.
+BACKEND = H.gpu_tier_backend()
+
+
+def _oracle(w, vals, **kw):
     m = w["model"]
-    return H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, w["name"]), threads=8)
+    return H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=BACKEND,
+                        compiled_so=H.compile_c_model(m, w["name"]), threads=8, **kw)
 
 
-@pytest.mark.parametrize("name,nsets,nout", [("mapk", 1024, None), ("repressilator", 96, 200), ("goodwin", 256, None), ("huang", 128, None)])
+def test_checker_is_the_vendored_cvode():
+    """The GPU box gets oracle/_ref from the snapshot: every BDF parity test below runs against the reference's CVODE."""
+    assert H.have_ref() and BACKEND == H.REF
+
+
+# repressilator at the BASELINE shape (configs[2]): t = 0..1000, 1000 output points
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 1024, None), ("repressilator", 96, 200), ("repressilator", 64, 1000),
+                                             ("goodwin", 256, None), ("huang", 128, None)])
 def test_parity_with_oracle(name, nsets, nout):
     w = H.workload(name, nout=nout)
     vals = H.workload_values(w, nsets, seed=2026)
@@ -53,7 +67,7 @@ def test_event_order_identical():
     vals = H.workload_values(w, 2048, seed=9)
     got = _gpu_run(w, vals)
     m = w["model"]
-    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, "events"), threads=8, want_margin=True)
+    ref = _oracle(w, vals, want_margin=True)
     # sets whose trigger expression comes within 100*max(rtol |x|, atol) of its threshold at an output point are
     # ill-conditioned and reported separately
     safe = (ref["margin"] > 100 * np.maximum(w["rtol"] * 1.0, w["atol"])).all(axis=1)
@@ -109,7 +123,7 @@ def test_failure_flags_and_nan_rows():
     b.set_values(vals)
     b.integrate(40)
     st, out = b.status(40), b.results(40)
-    ref = H.oracle_run(w["model"], opt, w["vary"], vals, 4)
+    ref = H.oracle_run(w["model"], opt, w["vary"], vals, 4, backend=H.gpu_tier_backend())
     assert np.array_equal(st, ref["status"]) and (st == -4).all()
     assert np.array_equal(np.isnan(out), np.isnan(np.transpose(ref["out"], (1, 2, 0))))
     b.close()
@@ -146,7 +160,7 @@ def test_run_host_pipeline_and_one_shot_entry():
     failed = L.IntegratorInstance_integrateBatch(ii, 64, len(w["vary"]), vis, vals[:64].ctypes.data, out.ctypes.data, st.ctypes.data)
     assert failed == 0 and (st == 0).all()
     assert np.array_equal(out[:, :, :8], np.transpose(direct[:, :, :64], (2, 0, 1)))
-    ref = H.oracle_run(m, w["opt"], w["vary"], vals[:64], 20)
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals[:64], 20, backend=H.gpu_tier_backend())
     assert H.parity(np.transpose(out, (1, 2, 0)), np.transpose(ref["out"], (1, 2, 0)), w["rtol"], w["atol"]) <= 1.0
     L.IntegratorInstance_free(ii)
 
@@ -195,7 +209,7 @@ def test_feature_model_on_gpu(tmp_path):
     b.set_values(vals)
     b.integrate(n)
     out, st, stats, fired = b.results(n), b.status(n), b.stats(n).T, b.event_log(n).T
-    ref = H.oracle_run(m, opt, vary, vals, 80, compiled_so=H.compile_c_model(m, "features"), threads=8)
+    ref = H.oracle_run(m, opt, vary, vals, 80, compiled_so=H.compile_c_model(m, "features"), threads=8, backend=H.gpu_tier_backend())
     assert np.array_equal(st, ref["status"]) and np.array_equal(stats, ref["stats"])
     assert np.array_equal(fired, ref["fired"]) and ref["fired"].any()
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
@@ -220,7 +234,7 @@ def test_chain_models_on_gpu(tmp_path, n):
     b.set_values(vals)
     b.integrate(ns)
     out, st, stats = b.results(ns), b.status(ns), b.stats(ns).T
-    ref = H.oracle_run(m, opt, vary, vals, 30, compiled_so=H.compile_c_model(m, f"chain{n}"), threads=8)
+    ref = H.oracle_run(m, opt, vary, vals, 30, compiled_so=H.compile_c_model(m, f"chain{n}"), threads=8, backend=H.gpu_tier_backend())
     print(n, b.kernel_info())
     assert (st == 0).all() and np.array_equal(stats, ref["stats"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))
@@ -254,7 +268,7 @@ def test_warp_layout_failure_flags(monkeypatch):
     b.set_values(vals)
     b.integrate(40)
     out, st = b.results(40), b.status(40)
-    ref = H.oracle_run(m, opt, w["vary"], vals, 4, compiled_so=H.compile_c_model(m, "mapk"))
+    ref = H.oracle_run(m, opt, w["vary"], vals, 4, compiled_so=H.compile_c_model(m, "mapk"), backend=H.gpu_tier_backend())
     assert (st == -4).all() and np.array_equal(st, ref["status"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
     b.close()
@@ -293,7 +307,7 @@ def test_steady_state_halt_on_gpu(monkeypatch, warp):
     b.integrate(300)
     out, st = b.results(300), b.status(300)
     b.close()
-    ref = H.oracle_run(m, opt, w["vary"], vals, 40, compiled_so=H.compile_c_model(m, "huang"), threads=8)
+    ref = H.oracle_run(m, opt, w["vary"], vals, 40, compiled_so=H.compile_c_model(m, "huang"), threads=8, backend=H.gpu_tier_backend())
     want = np.transpose(ref["out"], (1, 2, 0))
     assert (st == 0).all() and np.isnan(want[-1, 0, :]).mean() > 0.5        # most sets settle inside the grid
     assert np.array_equal(out, want, equal_nan=True)
@@ -363,7 +377,7 @@ def test_time_dependent_model_on_gpu(tmp_path):
     b.set_values(vals)
     b.integrate(500)
     out, st, fired = b.results(500), b.status(500), b.event_log(500).T
-    ref = H.oracle_run(m, opt, vary, vals, 70, compiled_so=H.compile_c_model(m, "forced"), threads=8)
+    ref = H.oracle_run(m, opt, vary, vals, 70, compiled_so=H.compile_c_model(m, "forced"), threads=8, backend=H.gpu_tier_backend())
     assert (st == 0).all() and np.array_equal(fired, ref["fired"])
     assert np.array_equal(b.stats(500).T, ref["stats"])
     assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))

@@ -52,7 +52,7 @@ def test_mapk_results_match_the_reference_printout():
     L = so.lib()
     m = so.Model(H.model_path("mapk_cascade.xml"))
     opt = so.settings(1000.0, 100, 1e-9, 1e-4, mxstep=1000)
-    r = H.oracle_run(m, opt, [], np.zeros((1, 0)), 100)
+    r = H.oracle_run(m, opt, [], np.zeros((1, 0)), 100, backend=H.gpu_tier_backend())
     flat = _flat(r["out"], r["status"], np.arange(101) * 10.0)
     arr = L.SBMLResultsArray_fromBatch(m.sbml, m.om, C.byref(flat))
     assert arr and L.SBMLResultsArray_getNumResults(arr) == 1
@@ -79,7 +79,7 @@ def test_scan_fluxes_use_the_models_constants_like_the_reference():
     m, vary, nominal = H.mapk_scan_model()
     opt = so.settings(1000.0, 20, 1e-9, 1e-6)
     vals = H.log_uniform_sets(nominal, 3, seed=11)
-    r = H.oracle_run(m, opt, vary, vals, 20)
+    r = H.oracle_run(m, opt, vary, vals, 20, backend=H.gpu_tier_backend())
     flat = _flat(r["out"], r["status"], np.arange(21) * 50.0)
     arr = L.SBMLResultsArray_fromBatch(m.sbml, m.om, C.byref(flat))
     assert L.SBMLResultsArray_getNumResults(arr) == 3
@@ -135,7 +135,7 @@ def test_variable_compartments_and_parameters_get_courses(tmp_path):
     L = so.lib()
     m = so.Model(str(p))
     opt = so.settings(4.0, 8, 1e-12, 1e-10)
-    r = H.oracle_run(m, opt, [], np.zeros((1, 0)), 8)
+    r = H.oracle_run(m, opt, [], np.zeros((1, 0)), 8, backend=H.gpu_tier_backend())
     flat = _flat(r["out"], r["status"], np.arange(9) * 0.5)
     arr = L.SBMLResultsArray_fromBatch(m.sbml, m.om, C.byref(flat))
     res = L.SBMLResultsArray_getResults(arr, 0)
@@ -184,7 +184,7 @@ def test_model_odesolverbatch_on_gpu_returns_results_per_design_point():
     assert L.SBMLResultsArray_getNumResults(arr) == 5
     mg = so.Model(H.model_path("mapk_cascade.xml"), globalize=[("J1", "V2")])
     vary = [mg.index(k) for k in ("V1", "Ki", "K1", "r_J1_V2")]
-    ref = H.oracle_run(mg, opt, vary, pts, 50, compiled_so=H.compile_c_model(mg, "mapk_g1"))
+    ref = H.oracle_run(mg, opt, vary, pts, 50, compiled_so=H.compile_c_model(mg, "mapk_g1"), backend=H.gpu_tier_backend())
     for s in range(5):
         res = L.SBMLResultsArray_getResults(arr, s)
         assert L.SBMLResults_getNout(res) == 51
