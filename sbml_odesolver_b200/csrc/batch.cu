@@ -414,6 +414,8 @@ static std::string build_source(odesBatch_t *b)
            env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
+  /* development knob: further -D options for the kernel text (tools/gpu_sweep.py), e.g. ODES_EXTRA_DEFS="-DODES_LU_FORM=1" */
+  if (getenv("ODES_EXTRA_DEFS") && *getenv("ODES_EXTRA_DEFS")) { src.erase(src.size() - 1); src += " "; src += getenv("ODES_EXTRA_DEFS"); src += "\n"; }
   src += model;
   src += odes_bdf_kernel_source;
   free(model);

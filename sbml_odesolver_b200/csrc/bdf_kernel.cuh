@@ -275,6 +275,38 @@ static inline void odes_signal_done(const OdesArgs &, size_t) {}
 #undef ODES_LA
 #define ODES_LA 0
 #endif
+/* Form of the dense linear algebra (gefa / gesl):
+     0  element-wise on shared-memory words (run-time row indices are plain addresses)
+     1  right-looking, one matrix column at a time in registers, rolled loops (run-time pivot rows picked with selects)
+     2  LEFT-LOOKING with compile-time indices: column j is built from the saved Jacobian in registers, receives the
+        eliminations of the columns before it (each skipped when its multiplier row entry is zero in every lane of the
+        warp -- the structural zeros of a reaction network), is searched for its pivot, scaled and stored ONCE; row
+        exchanges are applied to the stored multipliers as well (LAPACK's layout instead of LINPACK's), so that the
+        solves permute the right-hand side up front and then run without any run-time row index.  Every matrix
+        element still receives the reference's operations in the reference's order (smalldense.c:58-160).
+   Form 2 needs the analytic Jacobian (the column build is fused into it) and is meant for small systems. */
+#ifndef ODES_LU2_MAXN
+#define ODES_LU2_MAXN 10
+#endif
+#ifndef ODES_LU_FORM
+#if ODES_LA == 2 && HAS_JAC && NEQ >= 2 && NEQ <= ODES_LU2_MAXN
+#define ODES_LU_FORM 2
+#elif ODES_LA != 0
+#define ODES_LU_FORM 1
+#else
+#define ODES_LU_FORM 0
+#endif
+#endif
+#if ODES_LU_FORM == 2 && !(HAS_JAC && NEQ >= 2 && NEQ <= 32)
+#undef ODES_LU_FORM
+#define ODES_LU_FORM 0
+#endif
+#if defined(ODES_HOST_EMULATION) && defined(ODES_EMU_COUNT_SWAPS)
+extern "C" { long odes_emu_swaps = 0; }
+#define ODES_EMU_NOTE_SWAP (odes_emu_swaps++)
+#else
+#define ODES_EMU_NOTE_SWAP ((void)0)
+#endif
 #define ZOFF 0                                    /* zn[0..5][NEQ]                         */
 #define EWOFF (ZOFF + LMAX * NEQ)                 /* error weights                         */
 #define ACOFF (EWOFF + NEQ)                       /* acor: accumulated Newton correction   */
@@ -436,6 +468,7 @@ struct Solver {
   int st, fwhy, callSetup, convfail, waited;
   int pend, ydone;             /* pending history transforms fused into the next predictor (1 restore, 2 rescale); y already interpolated */
   double saved_t, nl_delp, dsm, resc_eta;
+  unsigned int swapmask;       /* LU form 2: bit k set when step k of the factorisation exchanged rows */
   int c_nst, c_nfe, c_nsetups, c_nje, c_nni, c_ncfn, c_netf;      /* totals over re-inits */
 #if NEQ <= 16
   unsigned long long pivpack;                                      /* LU pivot rows, 4 bits each */
@@ -646,7 +679,133 @@ struct Solver {
   DEV void mcol_load(int j, double (&c)[A1(NP)]) const { la_load<NCH>(la, LAM + j * NP, c); }
   DEV void mcol_store(int j, const double (&c)[A1(NP)]) const { la_store<NCH>(la, LAM + j * NP, c); }
 
-#if ODES_LA != 0
+#if ODES_LU_FORM == 2
+  /* rows j and lp of the multiplier columns 0..j-1 change places (the exchange of step j applied to the stored L) */
+  DEV void swap_stored_rows(const int j, const int lp, const bool doit) const
+  {
+    _Pragma("unroll 1") for (int k = 0; k < j; k++) {
+      double m[A1(NP)];
+      mcol_load(k, m);
+      if (doit) {
+        double mj = 0.0, ml = 0.0;
+        FORI { if (i == j) mj = m[i]; if (i == lp) ml = m[i]; }
+        FORI { if (i == j) m[i] = ml; if (i == lp) m[i] = mj; }
+      }
+      mcol_store(k, m);
+    }
+    la_fence(la);
+  }
+  /* M = I - gamma*J built column by column from the saved Jacobian and factored on the way (left-looking gefa);
+     returns 0, or j+1 when column j has no pivot.  Warp-converged; lanes without act keep their stored matrix. */
+  DEV int factor_columns(const bool act0, const double (&jnz)[A1(NSJP)], const double mg)
+  {
+    bool act = act0;
+    int ier = 0;
+    unsigned int swm = 0u;
+    bool scratched = false;
+    if (act) piv_clear();
+    _Pragma("unroll") for (int j = 0; j < NEQ; j++) {
+      double c[A1(NP)];
+      {
+        const double z = 0.0 * mg;
+        _Pragma("unroll") for (int i = 0; i < NP; i++) c[i] = z;
+        scatter_col(j, c, jnz, mg);
+        c[j] = c[j] + 1.0;
+      }
+      /* the row exchanges of the steps before (rare: through this lane's acor words, which are zero during a setup) */
+      if (j > 0 && ODES_WARP_ANY(act && swm != 0u)) {
+        if (act && swm != 0u) {
+          FORI ACOR(i) = c[i];
+          _Pragma("unroll 1") for (int k = 0; k < j; k++) {
+            const int lp = piv_get(k);
+            if (lp != k) { const double t = ACOR(lp); ACOR(lp) = ACOR(k); ACOR(k) = t; }
+          }
+          FORI c[i] = ACOR(i);
+          scratched = true;
+        }
+        ODES_WARP_SYNC();
+      }
+      /* eliminations of the steps before, each with its stored multipliers */
+      _Pragma("unroll") for (int k = 0; k < NEQ - 1; k++) {
+        if (k < j) {
+          const double a_kj = c[k];
+          if (ODES_WARP_ANY(act && a_kj != 0.0)) {
+            double m[A1(NP)];
+            mcol_load(k, m);
+            if (a_kj != 0.0) { _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > k) c[i] = c[i] + a_kj * m[i]; }
+          }
+        }
+      }
+      if (j < NEQ - 1) {
+        /* pivot: the first row of maximal magnitude at or below the diagonal */
+        int lp = j;
+        double pval = c[j], big = fabs(c[j]);
+        _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j) { const double v = fabs(c[i]); if (v > big) { big = v; lp = i; pval = c[i]; } }
+        if (act) {
+          piv_set(j, lp);
+          if (pval == 0.0) { ier = j + 1; act = false; }
+        }
+        const bool sw = act && (lp != j);
+        if (ODES_WARP_ANY(sw)) {
+          if (sw) {
+            ODES_EMU_NOTE_SWAP;
+            const double cj = c[j];
+            _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j && i == lp) c[i] = cj;
+            c[j] = pval;
+            swm |= 1u << j;
+          }
+          if (j > 0) swap_stored_rows(j, lp, sw);
+        }
+        const double mult = -1.0 / c[j];
+        _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j) c[i] = c[i] * mult;
+      } else if (act) {
+        piv_set(NEQ - 1, NEQ - 1);
+        if (c[NEQ - 1] == 0.0) ier = NEQ;
+      }
+      /* the finished column replaces the stored one in the lanes that factor */
+      {
+        double o[A1(NP)];
+        mcol_load(j, o);
+        _Pragma("unroll") for (int i = 0; i < NP; i++) if (act0) o[i] = c[i];
+        mcol_store(j, o);
+        la_fence(la);
+      }
+    }
+    if (act0) { swapmask = swm; if (scratched) { FORC ACOR(i) = 0.0; } }
+    return ier;
+  }
+  /* solves M x = b in place, b = FT, for the lanes with act: b is permuted up front, then both triangular solves run on
+     registers with compile-time indices, one stored column per step */
+  DEV void gesl(bool act)
+  {
+    if (ODES_WARP_ANY(act && swapmask != 0u)) {
+      if (act && swapmask != 0u) {
+        _Pragma("unroll 1") for (int k = 0; k < NEQ - 1; k++) {
+          const int lp = piv_get(k);
+          if (lp != k) { const double t = FT(lp); FT(lp) = FT(k); FT(k) = t; }
+        }
+      }
+      ODES_WARP_SYNC();
+    }
+    double b[A1(NEQ)];
+    FORI b[i] = FT(i);
+    _Pragma("unroll") for (int k = 0; k < NEQ - 1; k++) {
+      double c[A1(NP)];
+      mcol_load(k, c);
+      const double mult = b[k];
+      _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > k) b[i] = b[i] + mult * c[i];
+    }
+    _Pragma("unroll") for (int k = NEQ - 1; k >= 0; k--) {
+      double c[A1(NP)];
+      mcol_load(k, c);
+      const double bk = b[k] / c[k];
+      b[k] = bk;
+      const double mult = -bk;
+      _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i < k) b[i] = b[i] + mult * c[i];
+    }
+    if (act) { FORI FT(i) = b[i]; }
+  }
+#elif ODES_LU_FORM == 1
   /* LU with partial pivoting of the lanes with act; returns 0, or k+1 when column k has no pivot.  Column-at-a-time
      form: for tensor memory (whole columns are what tcgen05.ld moves) and for the global scratch (a column is 8
      independent loads in flight; the element-wise form below measured 51 k vs 82 k trajectories/s on huang96) */
@@ -791,6 +950,10 @@ struct Solver {
       ODES_WARP_SYNC();
       la_store<NSJCH>(la, LAJ, jnz);
     }
+#if ODES_LU_FORM == 2
+    la_fence(la);
+    return factor_columns(act, jnz, mg) > 0 ? 1 : 0;
+#else
     /* M = I - gamma*J column by column: zero pattern, the stored non-zeros (DenseScale order), +1 on the diagonal */
     _Pragma("unroll 1") for (int j = 0; j < NEQ; j++) {
       double c[A1(NP)];
@@ -803,6 +966,7 @@ struct Solver {
       }
       mcol_store(j, c);
     }
+#endif
 #else
     /* difference-quotient Jacobian, cvdense.c:479-537: y is z0 here; ACOR holds f(tn, z0) during the sweep.
        The saved Jacobian is dense: column j at LAJ + j*NP */
@@ -837,8 +1001,10 @@ struct Solver {
     }
     if (jbad) { FORC { FT(i) = ACOR(i); ACOR(i) = 0.0; } }
 #endif
+#if ODES_LU_FORM != 2
     la_fence(la);
     return gefa(act) > 0 ? 1 : 0;
+#endif
   }
 
   /* ---- CVHin (cvode.c:1514-1636), warp-converged: lanes with act compute their initial step; the at most
@@ -1169,7 +1335,7 @@ struct Solver {
     fwhy = FW_ATTEMPT; callSetup = 0; convfail = CV_NO_FAILURES; waited = 0; pend = 0; ydone = 0; resc_eta = 1.0;
     h = 0.0; hprime = 0.0; hscale = 0.0; hu = 0.0; eta = 1.0; tn = 0.0; q = 1; L = 2; qprime = 1; qwait = 2;
     etamax = K_ETAMX1; rl1 = 1.0; gamma = 0.0; tstop = 0.0; nstlp = 0; nstlj = 0;
-    piv_clear();
+    piv_clear(); swapmask = 0u;
     clear_history();
   }
 

@@ -154,14 +154,18 @@ class Emu:
 
     def __init__(self, batch, tag):
         src = batch.source()
-        h = hashlib.sha1(src.encode()).hexdigest()[:12]
+        # extra defines for the host build (e.g. ODES_EMU_DEFS="-DODES_LU_FORM=2": the left-looking linear algebra the
+        # GPU build selects with tensor memory, run here on the shared-memory word space)
+        extra = (tag if isinstance(tag, (list, tuple)) else []) or os.environ.get("ODES_EMU_DEFS", "").split()
+        tag = tag if isinstance(tag, str) else "emu"
+        h = hashlib.sha1((src + " ".join(extra)).encode()).hexdigest()[:12]
         d = os.path.join(ROOT, "tests", "emu", "_build")
         os.makedirs(d, exist_ok=True)
         cu = os.path.join(d, f"{tag}_{h}.cu")
         lib = os.path.join(d, f"{tag}_{h}.so")
         if not os.path.exists(lib):
             open(cu, "w").write(src)
-            subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
+            subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + extra + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
                                   ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W") or t.startswith("-DODES_ADAMS") or t.startswith("-DODES_FUNCTIONAL")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
                                    f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
         self.lib = C.CDLL(lib)

@@ -126,6 +126,55 @@ def chain_model_xml(n):
             f'<listOfParameters>{pars}</listOfParameters><listOfReactions>{"".join(rx)}</listOfReactions></model></sbml>')
 
 
+def amplifier_model_xml(n):
+    """A cascade S1 -> 3 S2 -> 9 S3 ... with product stoichiometry 3 and first-order decay of every species: below the
+    diagonal the Newton matrix I - gamma J holds -3 gamma k against 1 + gamma (k + d) on it, so as soon as the step size
+    is large the partial pivoting of gefa exchanges rows (smalldense.c:74-96) -- the case the reaction networks of the
+    benchmark never meet."""
+    sp = "".join(f'<species id="S{i}" compartment="c" initialConcentration="{2.0 if i == 1 else 0.05}"/>' for i in range(1, n + 1))
+    rx = []
+    for i in range(1, n):
+        rx.append(f'<reaction id="r{i}" reversible="false"><listOfReactants><speciesReference species="S{i}"/></listOfReactants>'
+                  f'<listOfProducts><speciesReference species="S{i + 1}" stoichiometry="3"/></listOfProducts><kineticLaw><math {M}>'
+                  f'<apply><times/><ci>k{i}</ci><ci>S{i}</ci></apply></math></kineticLaw></reaction>')
+    for i in range(1, n + 1):
+        rx.append(f'<reaction id="d{i}" reversible="false"><listOfReactants><speciesReference species="S{i}"/></listOfReactants>'
+                  f'<kineticLaw><math {M}><apply><times/><ci>dec</ci><ci>S{i}</ci></apply></math></kineticLaw></reaction>')
+    rx.append(f'<reaction id="src" reversible="false"><listOfProducts><speciesReference species="S1"/></listOfProducts>'
+              f'<kineticLaw><math {M}><apply><divide/><ci>vin</ci><apply><plus/><cn>1</cn><ci>S{n}</ci></apply></apply></math></kineticLaw></reaction>')
+    pars = "".join(f'<parameter id="k{i}" value="{4.0 + i}"/>' for i in range(1, n)) + '<parameter id="dec" value="0.8"/><parameter id="vin" value="1.5"/>'
+    return (f'<?xml version="1.0" encoding="UTF-8"?><sbml xmlns="http://www.sbml.org/sbml/level2" level="2" version="1"><model id="amp{n}">'
+            f'<listOfCompartments><compartment id="c" size="1"/></listOfCompartments><listOfSpecies>{sp}</listOfSpecies>'
+            f'<listOfParameters>{pars}</listOfParameters><listOfReactions>{"".join(rx)}</listOfReactions></model></sbml>')
+
+
+def amplifier_case(tmp_path, n, nsets):
+    p = tmp_path / f"amp{n}.xml"
+    p.write_text(amplifier_model_xml(n))
+    m = so.Model(str(p))
+    vary = [m.index(f"k{i}") for i in range(1, n)] + [m.index("dec")]
+    rng = np.random.default_rng(100 + n)
+    vals = m.base_values()[vary][None, :] * np.exp2(rng.uniform(-1, 1, size=(nsets, len(vary))))
+    return m, vary, vals, so.settings(20.0, 20, 1e-9, 1e-6)
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_left_looking_lu_with_row_exchanges_emulated(tmp_path, n):
+    """LU form 2 of bdf_kernel.cuh (left-looking, LAPACK row layout, what the GPU build uses with tensor memory) on a model
+    whose factorisations exchange rows: bit-identical to the vendored CVODE; the exchanges are counted."""
+    import ctypes as C
+    m, vary, vals, opt = amplifier_case(tmp_path, n, 12)
+    b = so.Batch(m, opt, vary)
+    base, trig = b.base_values()
+    emu = H.Emu(b, ["-DODES_LU_FORM=2", "-DODES_EMU_COUNT_SWAPS"])
+    got = emu.run(base, trig, vals, H.tpoints(opt, 20), 10000, 1e-6, 1e-9)
+    ref = H.oracle_run(m, opt, vary, vals, 20, backend=H.gpu_tier_backend(), compiled_so=H.compile_c_model(m, f"amp{n}"))
+    assert C.c_long.in_dll(emu.lib, "odes_emu_swaps").value > 100
+    assert np.array_equal(got["stats"].T, ref["stats"]) and (got["status"] == 0).all()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)))
+    b.close()
+
+
 @pytest.mark.parametrize("n", [3, 12, 17, 20, 32])
 def test_chain_models_emulated_kernel_vs_oracle(tmp_path, n):
     """State dimensions around the storage thresholds: one and two 8-row chunks per matrix column, packed and

@@ -241,6 +241,23 @@ def test_chain_models_on_gpu(tmp_path, n):
     b.close()
 
 
+@pytest.mark.parametrize("n", [4, 8, 10])
+def test_row_exchanges_in_the_tensor_memory_lu(tmp_path, n):
+    """Models whose Newton matrices need partial pivoting (product stoichiometry 3): the left-looking LU of the lane kernel
+    exchanges rows of the multiplier columns it keeps in tensor memory; bit-identical to the vendored CVODE."""
+    from test_frontend_models import amplifier_case
+    m, vary, vals, opt = amplifier_case(tmp_path, n, 1500)
+    b = so.Batch(m, opt, vary)
+    b.set_values(vals)
+    b.integrate(len(vals))
+    out, st, stats = b.results(len(vals)), b.status(len(vals)), b.stats(len(vals)).T
+    ref = H.oracle_run(m, opt, vary, vals, 20, compiled_so=H.compile_c_model(m, f"amp{n}"), threads=8, backend=H.gpu_tier_backend())
+    print(n, b.kernel_info())
+    assert (st == 0).all() and np.array_equal(stats, ref["stats"])
+    assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)))
+    b.close()
+
+
 @pytest.mark.parametrize("name,nsets,nout", [("mapk", 300, None), ("goodwin", 200, None), ("events", 400, None), ("repressilator", 64, 200)])
 def test_warp_layout_forced_on_small_models(monkeypatch, name, nsets, nout):
     """bdf_warp_kernel.cuh (one trajectory per warp; automatic for n > 12) on the small models: solver restarts after

@@ -20,6 +20,6 @@ else:
     for cfg in sys.argv[2:] or [""]:
         env = dict(os.environ); env["ODES_CFG"] = cfg
         for kv in cfg.split():
-            k, v = kv.split("="); env[k] = v
+            k, v = kv.split("=", 1); env[k] = v
         r = subprocess.run([sys.executable, __file__, "--one", n], env=env, capture_output=True, text=True)
         print(r.stdout.strip().split("\n")[-1] if r.returncode == 0 else f"FAILED {cfg}: {r.stderr[-400:]}")
