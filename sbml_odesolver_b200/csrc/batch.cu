@@ -411,7 +411,7 @@ static std::string build_source(odesBatch_t *b)
   char head[640];
   snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 8), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
+           env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   /* development knob: further -D options for the kernel text (tools/gpu_sweep.py), e.g. ODES_EXTRA_DEFS="-DODES_LU_FORM=1" */

@@ -65,7 +65,7 @@
 #define ODES_COL_UNROLL 2
 #endif
 #ifndef ODES_SETUP_MIN
-#define ODES_SETUP_MIN 8
+#define ODES_SETUP_MIN 10           /* measured on MAPK (B200, left-looking LU): 4 245 ms, 6 233, 8 227, 10 224, 12 225, 16 229 */
 #endif
 #ifndef ODES_SETUP_WAIT
 #define ODES_SETUP_WAIT 3
@@ -245,6 +245,12 @@ static inline void odes_signal_done(const OdesArgs &, size_t) {}
 #define ODES_STR(x) ODES_STR_(x)
 /* loop over the state dimension (columns of the Nordsieck array) */
 #define FORC _Pragma(ODES_STR(unroll ODES_COL_UNROLL)) for (int i = 0; i < NEQ; i++)
+/* the same loop in the blocks every step runs (predictor, Newton update, step completion): these are chains of dependent
+   FP64 operations per column (6-9 cycles each, profiles/r02_ncu_v14), so more columns in flight hide more latency */
+#ifndef ODES_HOT_UNROLL
+#define ODES_HOT_UNROLL ODES_COL_UNROLL
+#endif
+#define FORH _Pragma(ODES_STR(unroll ODES_HOT_UNROLL)) for (int i = 0; i < NEQ; i++)
 /* fully unrolled loop, only where model code needs compile-time indices */
 #define FORI _Pragma("unroll") for (int i = 0; i < NEQ; i++)
 #define NMAT (NEQ * NEQ)
@@ -428,7 +434,51 @@ ODES_NOINLINE double root_pow(double x, int n)
   return odes_glibc_pow(x, n <= 7 ? inv_int(n) : 1.0 / n);     /* n up to 13 with Adams-Moulton (orders 1..12) */
 }
 ODES_NOINLINE double rsqrt_(double x) { return x <= 0.0 ? 0.0 : sqrt(x); }
+/* The step-size factors are eta = 1 / (RPowerR(x, 1/n) + ADDON) and are only looked at above THRESH = 1.5 (CVSetEta,
+   cvode.c:2689-2700; the order selection compares the largest of three, :2640-2660).  For x >= c_eta_small[n] =
+   (2/3 + 1e-6)^n (1 + 1e-9) the root is above 2/3 + 1e-6 whatever the last bit of pow, so eta < 1.5 for certain and the
+   pow call is skipped -- the decisions (eta = 1, or "not the largest") are the reference's. */
+#ifdef ODES_HOST_EMULATION
+static const double c_eta_small[8] =
+#else
+__constant__ double c_eta_small[8] =
+#endif
+  {1e300, 1e300, 0.44444577822322356, 0.2962976299279273, 0.1975320495829148, 0.1316882305873261, 0.08779228541311465, 0.05852827806769518};
+DEV bool eta_below_thresh(double x, int n) { return n >= 2 && n <= 7 && x >= c_eta_small[n]; }
 #if !ODES_WARP
+#ifndef ODES_POW_SHARE
+#define ODES_POW_SHARE 1
+#endif
+/* RPowerR for up to three (x, n) requests per lane, warp-converged.  pow is a pure function, so it does not matter WHICH
+   lane evaluates a request: the requests of the warp (about one per completing lane plus two for the few lanes that
+   select a new order) are compacted into a per-warp staging array and evaluated by all 32 lanes together -- one pass
+   through the 300 instructions of pow per warp instead of three passes with 20, 9 and 3 lanes. */
+#if defined(ODES_HOST_EMULATION) || !ODES_POW_SHARE
+DEV void pow_service(const int nreq, double (&x)[3], const int (&n)[3])
+{
+  _Pragma("unroll") for (int r = 0; r < 3; r++) if (r < nreq) x[r] = root_pow(x[r], n[r]);
+}
+#else
+DEV void pow_service(const int nreq, double (&x)[3], const int (&n)[3])
+{
+  __shared__ double stage_x[ODES_BLOCK / 32][96];
+  __shared__ int stage_n[ODES_BLOCK / 32][96];
+  const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned int b0 = __ballot_sync(0xffffffffu, (nreq & 1) != 0), b1 = __ballot_sync(0xffffffffu, (nreq & 2) != 0);
+  const unsigned int below = (1u << lane) - 1u;
+  const int off = __popc(b0 & below) + 2 * __popc(b1 & below), total = __popc(b0) + 2 * __popc(b1);
+  if (total == 0) return;
+  _Pragma("unroll") for (int r = 0; r < 3; r++) if (r < nreq) { stage_x[w][off + r] = x[r]; stage_n[w][off + r] = n[r]; }
+  __syncwarp();
+  _Pragma("unroll 1") for (int base = 0; base < total; base += 32) {
+    const int idx = base + (int)lane;
+    if (idx < total) stage_x[w][idx] = root_pow(stage_x[w][idx], stage_n[w][idx]);
+  }
+  __syncwarp();
+  _Pragma("unroll") for (int r = 0; r < 3; r++) if (r < nreq) x[r] = stage_x[w][off + r];
+  __syncwarp();
+}
+#endif
 /* N_VWrmsNorm(x, ewt) with x the vector at word offset off (nvector_serial.c:591) */
 ODES_NOINLINE double wrms_vec(const double *sm, int off)
 {
@@ -491,7 +541,7 @@ struct Solver {
   DEV bool ewt_set()
   {
     double mn = 1.0;
-    FORC { COLPTR; const double w = reltol * fabs(CZ(0)) + abstol; if (i == 0 || w < mn) mn = w; C(EWOFF) = 1.0 / w; }
+    FORH { COLPTR; const double w = reltol * fabs(CZ(0)) + abstol; if (i == 0 || w < mn) mn = w; C(EWOFF) = 1.0 / w; }
     return mn > 0.0;
   }
 
@@ -567,7 +617,7 @@ struct Solver {
     const int qq = q;
     const bool pr = (pend & 1) != 0, ps = (pend & 2) != 0;
     const double f1 = resc_eta, f2 = f1 * resc_eta, f3 = f2 * resc_eta, f4 = f3 * resc_eta, f5 = f4 * resc_eta;
-    FORC { COLPTR; history_column(c, qq, pr, ps, true, f1, f2, f3, f4, f5); }
+    FORH { COLPTR; history_column(c, qq, pr, ps, true, f1, f2, f3, f4, f5); }
     pend = 0;
   }
 
@@ -704,13 +754,23 @@ struct Solver {
     unsigned int swm = 0u;
     bool scratched = false;
     if (act) piv_clear();
+#ifndef ODES_LU2_ROLLJ
+#define ODES_LU2_ROLLJ 1
+#endif
+#if ODES_LU2_ROLLJ
+    /* the column loop stays rolled (j is a run-time value, the eliminations inside are unrolled over k and predicated on
+       k < j): a third of the instructions of the fully unrolled form -- the kernel is bound by instruction delivery, and
+       measured on MAPK the smaller text wins although it executes more */
+    _Pragma("unroll 1") for (int j = 0; j < NEQ; j++) {
+#else
     _Pragma("unroll") for (int j = 0; j < NEQ; j++) {
+#endif
       double c[A1(NP)];
       {
         const double z = 0.0 * mg;
         _Pragma("unroll") for (int i = 0; i < NP; i++) c[i] = z;
         scatter_col(j, c, jnz, mg);
-        c[j] = c[j] + 1.0;
+        FORI if (i == j) c[i] = c[i] + 1.0;
       }
       /* the row exchanges of the steps before (rare: through this lane's acor words, which are zero during a setup) */
       if (j > 0 && ODES_WARP_ANY(act && swm != 0u)) {
@@ -739,7 +799,9 @@ struct Solver {
       if (j < NEQ - 1) {
         /* pivot: the first row of maximal magnitude at or below the diagonal */
         int lp = j;
-        double pval = c[j], big = fabs(c[j]);
+        double cj = 0.0;
+        FORI if (i == j) cj = c[i];
+        double pval = cj, big = fabs(cj);
         _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j) { const double v = fabs(c[i]); if (v > big) { big = v; lp = i; pval = c[i]; } }
         if (act) {
           piv_set(j, lp);
@@ -749,14 +811,12 @@ struct Solver {
         if (ODES_WARP_ANY(sw)) {
           if (sw) {
             ODES_EMU_NOTE_SWAP;
-            const double cj = c[j];
-            _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j && i == lp) c[i] = cj;
-            c[j] = pval;
+            _Pragma("unroll") for (int i = 0; i < NEQ; i++) { if (i > j && i == lp) c[i] = cj; if (i == j) c[i] = pval; }
             swm |= 1u << j;
           }
           if (j > 0) swap_stored_rows(j, lp, sw);
         }
-        const double mult = -1.0 / c[j];
+        const double mult = -1.0 / pval;
         _Pragma("unroll") for (int i = 0; i < NEQ; i++) if (i > j) c[i] = c[i] * mult;
       } else if (act) {
         piv_set(NEQ - 1, NEQ - 1);
@@ -1048,7 +1108,7 @@ struct Solver {
       f(tn + hgs, looping);
       if (looping) {
         FORC FT(i) = FT(i) - ZN(1, i);
-        { const double c = 1.0 / hgs; FORC FT(i) = c * FT(i); }
+        { const double c = 1.0 / hgs; FORH FT(i) = c * FT(i); }
         const double yddnrm = wrms(FTOFF);
         hnew = (yddnrm * hub * hub > 2.0) ? rsqrt_(2.0 / yddnrm) : rsqrt_(hg * hub);
         count++;
@@ -1089,7 +1149,7 @@ struct Solver {
          mean square is not provably small (mean square < 1e30  =>  UROUND*sqrt(mean square) < 0.23) */
       {
         double sum = 0.0;
-        FORC { const double pz = ZN(0, i) * EW(i); sum += pz * pz; }
+        FORH { const double pz = ZN(0, i) * EW(i); sum += pz * pz; }
         if (!(sum / NEQ < 1e30) && UROUND * rsqrt_(sum / NEQ) > 1.0) return CV_TOO_MUCH_ACC;
       }
       /* CVStep prologue */
@@ -1103,7 +1163,7 @@ struct Solver {
     callSetup = (nflag == PREV_CONV_FAIL) || (nflag == PREV_ERR_FAIL) || (nst == 0) ||
                 (nst >= nstlp + K_MSBP) || (fabs(gamrat - 1.0) > K_DGMAX);
     /* start of the Newton iteration: acor = 0, y = predicted zn[0] */
-    FORC { COLPTR; C(YOFF) = CZ(0); C(ACOFF) = 0.0; }
+    FORH { COLPTR; C(YOFF) = CZ(0); C(ACOFF) = 0.0; }
     nl_m = 0; nl_delp = 0.0;
     st = ST_F; fwhy = FW_ATTEMPT;
     return 0;
@@ -1147,7 +1207,7 @@ struct Solver {
   DEV int blk_newton(bool act)
   {
     /* b = gamma*f(tn,y) - (rl1*zn[1] + acor)   (N_VLinearSum with a == 1 multiplies by 1.0: same value) */
-    if (act) { FORC { COLPTR; const double tv = rl1 * CZ(1) + C(ACOFF); C(FTOFF) = gamma * C(FTOFF) - tv; } }
+    if (act) { FORH { COLPTR; const double tv = rl1 * CZ(1) + C(ACOFF); C(FTOFF) = gamma * C(FTOFF) - tv; } }
     ODES_WARP_SYNC();
     gesl(act);                                     /* warp-converged: the matrix columns come through la_load */
     if (!act) return 0;
@@ -1156,7 +1216,7 @@ struct Solver {
     double del;
     {
       double sum = 0.0;
-      FORC {
+      FORH {
         COLPTR;
         const double bi = C(FTOFF), p = bi * C(EWOFF);
         sum += p * p;
@@ -1219,9 +1279,14 @@ struct Solver {
     st = ST_F; fwhy = FW_RESTART;
     return 0;
   }
-  /* COMPLETE: CVCompleteStep + CVPrepareNextStep (cvode.c:2540-2713) */
-  DEV void blk_complete(double tout)
+  /* COMPLETE: CVCompleteStep + CVPrepareNextStep (cvode.c:2540-2713), warp-converged for the lanes with act (the
+     pow calls of the step-size / order selection are shared by the warp, see pow_service) */
+  DEV void blk_complete(const bool act, double tout)
   {
+    double px[3] = {0.0, 0.0, 0.0};
+    int pn[3] = {1, 1, 1}, nreq = 0;
+    bool want_q = false, want_m = false, want_p = false, select = false;
+    if (act) {
     nst++; c_nst++;
     hu = h;
     _Pragma("unroll 1") for (int i = q; i >= 2; i--) TAU(i) = TAU(i - 1);
@@ -1242,7 +1307,7 @@ struct Solver {
 #endif
       const double sh = (tout - tn) / h;
       const bool p2 = qq >= 2, p3 = qq >= 3, p4 = qq >= 4, p5 = qq >= 5;
-      FORC {
+      FORH {
         COLPTR;
         const double ac = C(ACOFF);
         const double z0 = l0 * ac + CZ(0), z1 = l1 * ac + CZ(1), z2 = l2 * ac + CZ(2), z3 = l3 * ac + CZ(3),
@@ -1266,17 +1331,19 @@ struct Solver {
       ydone = outnow ? 1 : 0;
     }
     if (save5) saved_tq5 = TQ(5);
-    /* CVPrepareNextStep (cvode.c:2577-2713) */
+    /* CVPrepareNextStep (cvode.c:2577-2713): the arguments of the pow calls first */
     if (etamax == 1.0) { qwait = qwait > 2 ? qwait : 2; qprime = q; hprime = h; eta = 1.0; }
     else {
-      const double etaq = 1.0 / (root_pow(K_BIAS2 * dsm, L) + K_ADDON);
-      if (qwait != 0) { eta = etaq; qprime = q; }
-      else {
-        qwait = 2;
-        double etaqm1 = 0.0, etaqp1 = 0.0;
+      select = (qwait == 0);
+      px[0] = K_BIAS2 * dsm; pn[0] = L;
+      want_q = !eta_below_thresh(px[0], L);
+      nreq = want_q ? 1 : 0;
+      if (select) {
         if (q > 1) {
           const double ddn = wrms(ZOFF + q * NEQ) / TQ(1);
-          etaqm1 = 1.0 / (root_pow(K_BIAS1 * ddn, q) + K_ADDON);
+          const double xm = K_BIAS1 * ddn;
+          want_m = !eta_below_thresh(xm, q);
+          if (want_m) { px[nreq] = xm; pn[nreq] = q; nreq++; }
         }
         if (q != QMAX) {
           double hr = h / TAU(2), pw = 1.0;
@@ -1285,8 +1352,25 @@ struct Solver {
           double sum = 0.0;
           FORC { COLPTR; const double tv = (-cquot) * CZ(QMAX) + C(ACOFF), p = tv * C(EWOFF); sum += p * p; }
           const double dup = rsqrt_(sum / NEQ) / TQ(3);
-          etaqp1 = 1.0 / (root_pow(K_BIAS3 * dup, L + 1) + K_ADDON);
+          const double xp = K_BIAS3 * dup;
+          want_p = !eta_below_thresh(xp, L + 1);
+          if (want_p) { px[nreq] = xp; pn[nreq] = L + 1; nreq++; }
         }
+      }
+    }
+    }
+    ODES_WARP_SYNC();
+    pow_service(nreq, px, pn);
+    if (!act) return;
+    if (etamax != 1.0) {
+      /* a factor known to be below THRESH is represented by 0: it is neither taken nor the largest of the three */
+      int r = 0;
+      const double etaq = want_q ? 1.0 / (px[r++] + K_ADDON) : 0.0;
+      if (!select) { eta = etaq; qprime = q; }
+      else {
+        qwait = 2;
+        const double etaqm1 = want_m ? 1.0 / (px[r++] + K_ADDON) : 0.0;
+        const double etaqp1 = want_p ? 1.0 / (px[r++] + K_ADDON) : 0.0;
         const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
         if (etam < K_THRESH) { eta = 1.0; qprime = q; }
         else if (etam == etaq) { eta = etaq; qprime = q; }
@@ -1564,11 +1648,12 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     }
     /* ---- COMPLETE ---- */
     ODES_BLOCK_ALIGN(8);
-    if (s.st == ST_COMPLETE) {
-      s.blk_complete(tout);
-      if (s.after_step(tout, t)) s.st = ST_OUTPUT;
+    if (ODES_WARP_ANY(s.st == ST_COMPLETE)) {
+      const bool act = (s.st == ST_COMPLETE);
+      s.blk_complete(act, tout);
+      if (act && s.after_step(tout, t)) s.st = ST_OUTPUT;
+      ODES_WARP_SYNC();
     }
-    ODES_WARP_SYNC();
 #else
     if (s.st != ST_DONE && s.st != ST_FINISH) { t = a.tpoints[iout]; s.st = ST_OUTPUT; }
 #endif
