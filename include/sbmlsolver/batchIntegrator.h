@@ -20,6 +20,7 @@
  */
 #ifndef ODES_B200_BATCHINTEGRATOR_H
 #define ODES_B200_BATCHINTEGRATOR_H
+#include <stddef.h>
 #include "sbmlsolver/integratorInstance.h"
 #ifdef __cplusplus
 extern "C" {
@@ -95,6 +96,15 @@ int ODESBatch_getSensIndex(const odesBatch_t *, int is);     /* value[] index of
 int ODESBatch_getSensitivities(odesBatch_t *, int nsets, double *sens /* [nsets][nout+1][nsens][neq] */);
 double *ODESBatch_deviceSensitivities(odesBatch_t *);
 
+/* reaction fluxes of the stored rows (the reference: src/odeSolver.c:463-471, :519-531), evaluated by
+   odes_flux_kernel over the device-resident results.  Plans of models with reactions whose om->m is set carry the
+   emitted kinetic laws; the plan must store all model values (storeIndex == NULL). */
+int ODESBatch_getNflux(const odesBatch_t *);                 /* number of reactions, 0: no flux function in this plan */
+int ODESBatch_computeFluxes(odesBatch_t *, int nsets);       /* asynchronous, on the plan's stream, after ODESBatch_integrate */
+int ODESBatch_getFluxes(odesBatch_t *, int nsets, double *flux /* [nsets][nout+1][nflux] */);
+double *ODESBatch_deviceFluxes(odesBatch_t *);
+float ODESBatch_getLastFluxMs(const odesBatch_t *);          /* CUDA events around the last flux launch */
+
 /* end-to-end helper with host buffers (values [nsets][nvary] in, results [nsets][nout+1][nstore] and status out).
    chunk >= 0: launches of `chunk` sets (0: up to 2^22), the results of finished groups of sets are copied back while
    the kernel runs; chunk < 0: launches of -chunk sets, the copy of launch k-1 overlaps launch k */
@@ -103,6 +113,10 @@ int ODESBatch_runHost(odesBatch_t *, int nsets, const double *values, double *re
 /* ... with the forward sensitivities [nsets][nout+1][nsens][neq] streamed back as well (sens may be NULL) */
 int ODESBatch_runHostSens(odesBatch_t *, int nsets, const double *values, double *results, double *sens, int *status,
                           int chunk);
+
+/* ... and with the reaction fluxes [nsets][nout+1][nflux] (flux may be NULL) */
+int ODESBatch_runHostEx(odesBatch_t *, int nsets, const double *values, double *results, double *sens, double *flux,
+                        int *status, int chunk);
 
 /* the same over all GPUs of the box: device k integrates the index range [k n / G, (k+1) n / G) of the caller's arrays
    (no collective; one plan and one host thread per device).  ndevices <= 0: all devices when every one gets at least
@@ -115,9 +129,24 @@ int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt, int nvary,
 int ODESBatch_runHostAllDevicesSens(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore,
                                     const int *storeIndex, int nsets, const double *values, double *results,
                                     double *sens /* NULL or [nsets][nout+1][nsens][neq] */, int *status, int ndevices);
+int ODESBatch_runHostAllDevicesEx(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore,
+                                  const int *storeIndex, int nsets, const double *values, double *results,
+                                  double *sens, double *flux /* NULL or [nsets][nout+1][nreactions] */, int *status, int ndevices);
 /* one-shot entry with sensitivities: sens NULL or [nsets][nout+1][nsens][neq], nsens as IntegratorInstance_getNsens(ii) */
 int IntegratorInstance_integrateBatchSens(integratorInstance_t *ii, int nsets, int nvary, variableIndex_t *const *vi,
                                           const double *values, double *out, double *sens, int *status);
+
+/* The one-shot entries (IntegratorInstance_integrateBatch, Model_odeSolverBatch[Flat], ODESBatch_runHostAllDevices*) keep
+   their plans -- compiled module, loaded kernel, streams, device buffers of every GPU used -- on the odeModel_t, keyed by
+   the generated kernel text; tolerances, step limit, time grid and base values are refreshed per call.  The cache goes
+   with ODEModel_free; ODEModel_freeKernelCache releases it (and its device memory) earlier. */
+void ODEModel_freeKernelCache(odeModel_t *om);
+/* work counters: [0] NVRTC compilations, [1] cubin-cache loads, [2] module loads, [3] device / pinned allocations,
+   [4] plans created, [5] plan-cache hits, [6] kernel launches, [7] host registrations */
+void ODES_getCounters(long long *counters /* [8] */);
+/* pinned host buffers for callers that want full-speed host<->device copies */
+void *ODES_hostAlloc(size_t bytes);
+void ODES_hostFree(void *);
 
 /* device utilities */
 int ODES_deviceCount(void);

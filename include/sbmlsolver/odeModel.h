@@ -168,6 +168,8 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *, const cvodeSettings_t *, int
                                       int nstore, const int *store, const double *base, const odeSense_t *os);
 /* Host-C flavour of the same generated functions (the reference's compiled mode), used by
    tests and by the CPU baseline harness.  Caller frees. */
+/* text of flux_row: the indexed kinetic laws of SBMLResults_fluxASTs as one device function over a stored row */
+char *ODEModel_generateCUDAFluxSection(int nflux, ASTNode_t *const *kls);
 char *ODEModel_generateCSource(odeModel_t *);
 /* ... plus sense_f (reference src/odeModel.c:2994-3100) when os is given */
 char *ODEModel_generateCSourceSens(odeModel_t *, const odeSense_t *os);

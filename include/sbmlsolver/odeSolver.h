@@ -30,6 +30,9 @@ typedef struct batchResults {
   int *status;                   /* [nsets] */
   /* forward sensitivities when set->Sensitivity was on: sens[set][time][parameter][equation], else nsens == 0 */
   int nsens, neq; char **sensParam; double *sens;
+  /* reaction fluxes evaluated on the device from the stored rows: flux[set][time][reaction], names = reaction ids
+     (nflux == 0: not computed) */
+  int nflux; char **fluxNames; double *flux;
 } batchResults_t;
 
 varySettings_t *VarySettings_allocate(int nrparams, int nrdesignpoints);
@@ -54,6 +57,9 @@ batchResults_t *Model_odeSolverBatchFlat(Model_t *, cvodeSettings_t *, varySetti
 batchResults_t *SBML_odeSolverBatchFlat(SBMLDocument_t *, cvodeSettings_t *, varySettings_t *);
 SBMLResultsArray_t *SBMLResultsArray_fromBatch(Model_t *, odeModel_t *, const batchResults_t *);
 double BatchResults_getValue(const batchResults_t *, int set, const char *name, int timestep);
+double BatchResults_getFlux(const batchResults_t *, int set, const char *reaction, int timestep);
+/* the indexed kinetic laws the flux courses are evaluated from (src/odeSolver.c:463-471), one per reaction or NULL */
+int SBMLResults_fluxASTs(Model_t *m, const odeModel_t *om, ASTNode_t ***kls);
 void BatchResults_free(batchResults_t *);
 int Model_globalizeParameter(Model_t *m, const char *id, const char *rid);
 int Model_localizeParameter(Model_t *m, const char *id, const char *rid);

@@ -100,6 +100,10 @@ _SIGS = {
     "ODESBatch_getStatus": (c_i, [c_p, c_i, c_p]), "ODESBatch_getStats": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_getEventLog": (c_i, [c_p, c_i, c_p]), "ODESBatch_runHost": (c_i, [c_p, c_i, c_p, c_p, c_p, c_i]),
     "ODESBatch_runHostAllDevices": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_i]),
+    "ODESBatch_getNflux": (c_i, [c_p]), "ODESBatch_computeFluxes": (c_i, [c_p, c_i]), "ODESBatch_getFluxes": (c_i, [c_p, c_i, c_p]),
+    "ODESBatch_getLastFluxMs": (C.c_float, [c_p]), "ODESBatch_runHostEx": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i]),
+    "BatchResults_getFlux": (c_d, [c_p, c_i, c_s, c_i]),
+    "ODES_getCounters": (None, [c_p]), "ODEModel_freeKernelCache": (None, [c_p]),
     "ODES_deviceCount": (c_i, []), "ODES_deviceName": (c_i, [c_i, c_p, c_i]), "ODES_measureFP64Peak": (c_d, [c_i, c_i]),
     "ODES_hostAlloc": (c_p, [C.c_size_t]), "ODES_hostFree": (None, [c_p]),
     "SolverError_getNum": (c_i, [c_i]), "SolverError_getLastCode": (c_i, [c_i]), "SolverError_clear": (None, []),
@@ -122,6 +126,17 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype, fn.argtypes = res, args
     return _lib
+
+
+COUNTERS = ("nvrtc_compiles", "cubin_cache_loads", "module_loads", "device_allocations", "plans_created", "plan_cache_hits",
+            "kernel_launches", "host_registrations")
+
+
+def counters():
+    """The library's work counters (ODES_getCounters) as a dict."""
+    v = (C.c_longlong * 8)()
+    lib().ODES_getCounters(v)
+    return dict(zip(COUNTERS, list(v)))
 
 
 def take_string(ptr):
@@ -244,6 +259,17 @@ class Batch:
         _check(lib().ODESBatch_getSensitivities(self.h, nsets, out.ctypes.data), "ODESBatch_getSensitivities")
         return out
 
+    @property
+    def nflux(self):
+        return lib().ODESBatch_getNflux(self.h)
+
+    def fluxes(self, nsets):
+        """Reaction fluxes [set][row][reaction] of the stored rows, evaluated on the device (odes_flux_kernel)."""
+        _check(lib().ODESBatch_computeFluxes(self.h, nsets), "ODESBatch_computeFluxes")
+        out = np.empty((nsets, self.nrows, self.nflux))
+        _check(lib().ODESBatch_getFluxes(self.h, nsets, out.ctypes.data), "ODESBatch_getFluxes")
+        return out
+
     def source(self):
         return lib().ODESBatch_getSource(self.h).decode()
 
@@ -309,12 +335,12 @@ class Batch:
         _check(lib().ODESBatch_getKernelInfo(self.h, *[C.byref(x) for x in v]), "ODESBatch_getKernelInfo")
         return dict(zip(("regs", "smem_bytes_per_block", "local_bytes_per_thread", "threads_per_block", "blocks_per_sm"), (x.value for x in v)))
 
-    def run_host(self, values, results=None, status=None, chunk=0, sens=None):
+    def run_host(self, values, results=None, status=None, chunk=0, sens=None, flux=None):
         v = np.ascontiguousarray(values, dtype=np.float64)
         n = v.shape[0]
-        _check(lib().ODESBatch_runHostSens(self.h, n, v.ctypes.data, None if results is None else results.ctypes.data,
-                                           None if sens is None else sens.ctypes.data,
-                                           None if status is None else status.ctypes.data, chunk), "ODESBatch_runHost")
+        _check(lib().ODESBatch_runHostEx(self.h, n, v.ctypes.data, None if results is None else results.ctypes.data,
+                                         None if sens is None else sens.ctypes.data, None if flux is None else flux.ctypes.data,
+                                         None if status is None else status.ctypes.data, chunk), "ODESBatch_runHost")
 
     def close(self):
         if self.h:

@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 #include "sbmlsolver/batchIntegrator.h"
+#include "sbmlsolver/odeSolver.h"
 #include "sbmlsolver/processAST.h"
 #include "sbmlsolver/solverError.h"
 
@@ -123,6 +124,20 @@ static std::string cache_dir(void)
   return "/tmp/odes_b200_cache";
 }
 
+/* work counters of the library (ODES_getCounters): how often the expensive, once-per-plan operations ran.  The one-shot
+   entries keep their plans and device buffers on the odeModel_t, so a second call with the same model, settings
+   and varied set must not move any of the first four. */
+#include <atomic>
+#include <mutex>
+enum { CNT_NVRTC = 0, CNT_CUBIN_LOAD, CNT_MODULE_LOAD, CNT_DEVICE_ALLOC, CNT_PLAN_CREATE, CNT_PLAN_HIT, CNT_LAUNCH, CNT_HOST_REGISTER, CNT_NUM };
+static std::atomic<long long> g_counters[CNT_NUM];
+extern "C" void ODES_getCounters(long long *out /* [8]: NVRTC compilations, cubin-cache loads, module loads, device/pinned allocations,
+                                                  plans created, plan-cache hits, kernel launches, host registrations */)
+{ for (int i = 0; i < CNT_NUM; i++) out[i] = g_counters[i].load(); }
+static cudaError_t counted_malloc(void **p, size_t bytes) { g_counters[CNT_DEVICE_ALLOC]++; return cudaMalloc(p, bytes); }
+template <class T> static cudaError_t counted_malloc(T **p, size_t bytes) { return counted_malloc((void **)p, bytes); }
+#define cudaMalloc counted_malloc
+
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 
 /* Compiles a CUDA translation unit for sm_100a.  Same three-call shape as the reference
@@ -164,7 +179,7 @@ extern "C" compiled_code_t *Compiler_compile(const char *sourceCode)
       fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
       if (n > 0) {
         code->cubin = malloc((size_t)n);
-        if (fread(code->cubin, 1, (size_t)n, f) == (size_t)n) { code->cubinSize = (unsigned long)n; code->log = strdup("(loaded from cache)"); fclose(f); return code; }
+        if (fread(code->cubin, 1, (size_t)n, f) == (size_t)n) { g_counters[CNT_CUBIN_LOAD]++; code->cubinSize = (unsigned long)n; code->log = strdup("(loaded from cache)"); fclose(f); return code; }
         free(code->cubin); code->cubin = NULL;
       }
       fclose(f);
@@ -178,6 +193,7 @@ extern "C" compiled_code_t *Compiler_compile(const char *sourceCode)
   }
   std::vector<const char *> copts;
   for (size_t i = 0; i < opts.size(); i++) copts.push_back(opts[i].c_str());
+  g_counters[CNT_NVRTC]++;
   nvrtcResult res = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
   size_t logSize = 0; nvrtcGetProgramLogSize(prog, &logSize);
   code->log = (char *)calloc(logSize + 1, 1);
@@ -208,6 +224,7 @@ extern "C" void *CompiledCode_getFunction(compiled_code_t *code, const char *sym
   if (!load_driver()) return NULL;
   if (!code->module) {
     CUmodule m;
+    g_counters[CNT_MODULE_LOAD]++;
     CUresult r = drv.ModuleLoadData(&m, code->cubin);
     if (r != CUDA_SUCCESS) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_DLL_LOAD_FAILED, "cuModuleLoadData failed with CUresult %d", (int)r); return NULL; }
     code->module = m;
@@ -306,6 +323,7 @@ struct odesBatch {
   float lastMs; int launches;
   std::vector<double> base; std::vector<int> trigger0;
   int sensFromRow0;                               /* initial sensitivities supplied by the host (single-instance restarts) */
+  int nflux; CUfunction fluxKernel; double *d_flux; size_t fluxCap; float lastFluxMs; cudaEvent_t f0, f1;   /* reaction fluxes of the stored rows: [capacity][nout+1][nflux] */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
 };
 
@@ -331,7 +349,9 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
     cudaSetDevice(b->device);
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
     cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch); cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
-    cudaFree(b->d_sens);
+    cudaFree(b->d_sens); cudaFree(b->d_flux);
+    if (b->f0) cudaEventDestroy(b->f0);
+    if (b->f1) cudaEventDestroy(b->f1);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copyIn) cudaStreamDestroy(b->copyIn);
     if (b->copyOut) cudaStreamDestroy(b->copyOut);
@@ -344,6 +364,24 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
   CompiledCode_free(b->code);
   ODESense_free(b->os);
   delete b;
+}
+
+/* reaction fluxes: when the plan stores every model value and the ODE model still knows its SBML model,
+   the kinetic laws are emitted as flux_row next to the model functions; odes_flux_kernel (end of the kernel text) maps
+   the stored rows.  ODES_FLUX=0 leaves it out. */
+static std::string flux_section(odesBatch_t *b)
+{
+  b->nflux = 0;
+  if (!b->om->m || !env_int("ODES_FLUX", 1)) return "";
+  if (b->nstore != b->nvalues) return "";
+  for (int j = 0; j < b->nstore; j++) if (b->store[(size_t)j] != j) return "";
+  ASTNode_t **kls = NULL;
+  const int n = SBMLResults_fluxASTs(b->om->m, b->om, &kls);
+  std::string text;
+  if (n > 0) { char *t = ODEModel_generateCUDAFluxSection(n, kls); text = t; free(t); b->nflux = n; }
+  for (int r = 0; r < n; r++) if (kls[r]) ASTNode_free(kls[r]);
+  free(kls);
+  return text;
 }
 
 static std::string build_source(odesBatch_t *b)
@@ -390,6 +428,7 @@ static std::string build_source(odesBatch_t *b)
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
+    srcw += flux_section(b);
     srcw += odes_bdf_kernel_source;
     free(model);
     return srcw;
@@ -417,13 +456,28 @@ static std::string build_source(odesBatch_t *b)
   /* development knob: further -D options for the kernel text (tools/gpu_sweep.py), e.g. ODES_EXTRA_DEFS="-DODES_LU_FORM=1" */
   if (getenv("ODES_EXTRA_DEFS") && *getenv("ODES_EXTRA_DEFS")) { src.erase(src.size() - 1); src += " "; src += getenv("ODES_EXTRA_DEFS"); src += "\n"; }
   src += model;
+  src += flux_section(b);
   src += odes_bdf_kernel_source;
   free(model);
   return src;
 }
 
+static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex, int device, std::string &src);
 extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex,
                                           int nstore, const int *storeIndex, int device)
+{
+  /* code generation + compilation need no device (NVRTC targets sm_100a explicitly) */
+  std::string src;
+  odesBatch_t *b = batch_prepare(om, opt, nvary, varyIndex, nstore, storeIndex, device, src);
+  if (!b) return NULL;
+  b->code = Compiler_compile(src.c_str());
+  if (!b->code) { ODESBatch_free(b); return NULL; }
+  g_counters[CNT_PLAN_CREATE]++;
+  return b;
+}
+/* everything of a plan up to the generated kernel text (no compilation, no device) */
+static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex,
+                                  int nstore, const int *storeIndex, int device, std::string &src)
 {
   if (!om || !opt) return NULL;
   if (om->hasCycle) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_ODE_MODEL_CYCLIC_DEPENDENCY_IN_RULES, "model rules contain a cycle"); return NULL; }
@@ -462,10 +516,7 @@ extern "C" odesBatch_t *ODESBatch_create(odeModel_t *om, cvodeSettings_t *opt, i
     b->nsens = b->os->nsens;
   }
 
-  /* code generation + compilation need no device (NVRTC targets sm_100a explicitly) */
-  std::string src = build_source(b);
-  b->code = Compiler_compile(src.c_str());
-  if (!b->code) { delete b; return NULL; }
+  src = build_source(b);
   return b;
 }
 
@@ -583,6 +634,57 @@ extern "C" int ODESBatch_getSensitivities(odesBatch_t *b, int nsets, double *sen
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return 1;
 }
+extern "C" int ODESBatch_getNflux(const odesBatch_t *b) { return b->nflux; }
+extern "C" double *ODESBatch_deviceFluxes(odesBatch_t *b) { return b->d_flux; }
+extern "C" float ODESBatch_getLastFluxMs(const odesBatch_t *b) { return b->lastFluxMs; }
+/* fluxes of the sets [offset, offset + nsets) of the device-resident results, on `stream` */
+static int launch_fluxes(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream)
+{
+  if (b->nflux <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "this plan has no flux function (it must store all model values of a model with reactions)"); return 0; }
+  if (!ensure_loaded(b)) return 0;
+  if (!b->fluxKernel) {
+    b->fluxKernel = (CUfunction)CompiledCode_getFunction(b->code, "odes_flux_kernel");
+    if (!b->fluxKernel) return 0;
+    CUDA_OK(cudaEventCreate(&b->f0)); CUDA_OK(cudaEventCreate(&b->f1));
+  }
+  const size_t rowsPerSet = (size_t)(b->opt->PrintStep + 1);
+  const size_t need = (size_t)b->capacity * rowsPerSet * (size_t)b->nflux;
+  if (need > b->fluxCap) { cudaFree(b->d_flux); b->d_flux = NULL; b->fluxCap = 0; CUDA_OK(cudaMalloc(&b->d_flux, need * sizeof(double))); b->fluxCap = need; }
+  if (nsets == 0) return 1;
+  const int rowsPerBlock = 128;
+  const unsigned int smem = (unsigned int)(sizeof(double) * (size_t)rowsPerBlock * (size_t)((b->nvalues | 1) + (b->nflux | 1)));
+  if (smem > 48 * 1024) DRV_OK(drv.FuncSetAttribute(b->fluxKernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  const double *out = b->d_out + offset * rowsPerSet * (size_t)b->nstore;
+  double *flux = b->d_flux + offset * rowsPerSet * (size_t)b->nflux;
+  unsigned long long nrows = (unsigned long long)nsets * rowsPerSet;
+  int rps = (int)rowsPerSet;
+  const double *tp = b->d_tpoints;
+  void *params[] = { &out, &tp, &flux, &nrows, &rps };
+  unsigned long long blocks = (nrows + rowsPerBlock - 1) / rowsPerBlock;
+  const unsigned long long cap = (unsigned long long)b->numSMs * 16ull;          /* grid-stride beyond 16 resident blocks per SM */
+  if (blocks > cap) blocks = cap;
+  CUDA_OK(cudaEventRecord(b->f0, stream));
+  g_counters[CNT_LAUNCH]++;
+  DRV_OK(drv.LaunchKernel(b->fluxKernel, (unsigned)blocks, 1, 1, rowsPerBlock, 1, 1, smem, (CUstream)stream, params, NULL));
+  CUDA_OK(cudaEventRecord(b->f1, stream));
+  b->launches++;
+  return 1;
+}
+extern "C" int ODESBatch_computeFluxes(odesBatch_t *b, int nsets)
+{
+  if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  return launch_fluxes(b, nsets, 0, b->stream);
+}
+extern "C" int ODESBatch_getFluxes(odesBatch_t *b, int nsets, double *flux)
+{
+  if (b->nflux <= 0 || !b->d_flux) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "no fluxes have been computed on this plan"); return 0; }
+  if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaMemcpyAsync(flux, b->d_flux, sizeof(double) * (size_t)nsets * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nflux, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  { float ms = 0; if (b->f0 && cudaEventElapsedTime(&ms, b->f0, b->f1) == cudaSuccess) b->lastFluxMs = ms; else cudaGetLastError(); }
+  return 1;
+}
 extern "C" const char *ODESBatch_getSource(const odesBatch_t *b) { return b->code ? b->code->source : NULL; }
 extern "C" const char *ODESBatch_getCompileLog(const odesBatch_t *b) { return b->code ? b->code->log : NULL; }
 extern "C" double *ODESBatch_deviceValues(odesBatch_t *b) { return b->d_vary; }
@@ -668,6 +770,7 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   if (grid > resident) grid = resident;
   CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
   if (timed) CUDA_OK(cudaEventRecord(b->e0, stream));
+  g_counters[CNT_LAUNCH]++;
   DRV_OK(drv.LaunchKernel(b->kernel, grid, 1, 1, (unsigned)b->block, 1, 1, (unsigned)b->smemBytes, (CUstream)stream, params, NULL));
   if (timed) CUDA_OK(cudaEventRecord(b->e1, stream));
   b->launches++;
@@ -780,7 +883,11 @@ static int run_host_chunked(odesBatch_t *b, int nsets, const double *values, dou
 extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
 { return ODESBatch_runHostSens(b, nsets, values, results, NULL, status, chunk); }
 extern "C" int ODESBatch_runHostSens(odesBatch_t *b, int nsets, const double *values, double *results, double *sens, int *status, int chunk)
+{ return ODESBatch_runHostEx(b, nsets, values, results, sens, NULL, status, chunk); }
+extern "C" int ODESBatch_runHostEx(odesBatch_t *b, int nsets, const double *values, double *results, double *sens, double *flux, int *status, int chunk)
 {
+  if (flux && b->nflux <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "this plan has no flux function (it must store all model values of a model with reactions)"); return 0; }
+  if (flux && chunk < 0) chunk = -chunk;
   if (sens && b->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the plan was created without sensitivity analysis"); return 0; }
   if (sens && chunk < 0) chunk = -chunk;              /* sensitivities travel with the streamed pipeline only */
   if (!ODESBatch_reserve(b, nsets)) return 0;
@@ -798,6 +905,7 @@ extern "C" int ODESBatch_runHostSens(odesBatch_t *b, int nsets, const double *va
     cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
     b->d_groupDone = NULL; b->h_flags = NULL; b->groupCap = 0;
     CUDA_OK(cudaMalloc(&b->d_groupDone, sizeof(unsigned int) * (size_t)maxGroups));
+    g_counters[CNT_DEVICE_ALLOC]++;
     CUDA_OK(cudaHostAlloc((void **)&b->h_flags, sizeof(unsigned int) * (size_t)maxGroups, cudaHostAllocMapped));
     CUDA_OK(cudaHostGetDevicePointer((void **)&b->d_flags, b->h_flags, 0));
     b->groupCap = maxGroups;
@@ -831,8 +939,15 @@ extern "C" int ODESBatch_runHostSens(odesBatch_t *b, int nsets, const double *va
         next = upto;
       } else sched_yield();
     }
+    if (flux) {
+      /* the fluxes of this launch's rows: one pass over the results in HBM, then their copy */
+      const size_t frows = (size_t)(b->nout + 1) * (size_t)b->nflux;
+      if (!launch_fluxes(b, n, off, b->stream)) return 0;
+      CUDA_OK(cudaMemcpyAsync(flux + off * frows, b->d_flux + off * frows, sizeof(double) * (size_t)n * frows, cudaMemcpyDeviceToHost, b->stream));
+    }
     CUDA_OK(cudaStreamSynchronize(b->copyOut));
     CUDA_OK(cudaStreamSynchronize(b->stream));
+    if (flux) { float ms = 0; if (cudaEventElapsedTime(&ms, b->f0, b->f1) == cudaSuccess) b->lastFluxMs = ms; else cudaGetLastError(); }
   }
   return 1;
 }
@@ -851,6 +966,57 @@ extern "C" int ODESBatch_runHostAllDevices(odeModel_t *om, cvodeSettings_t *opt,
 { return ODESBatch_runHostAllDevicesSens(om, opt, nvary, varyIndex, nstore, storeIndex, nsets, values, results, NULL, status, ndevices); }
 extern "C" int ODESBatch_runHostAllDevicesSens(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex,
                                                int nsets, const double *values, double *results, double *sens, int *status, int ndevices)
+{ return ODESBatch_runHostAllDevicesEx(om, opt, nvary, varyIndex, nstore, storeIndex, nsets, values, results, sens, NULL, status, ndevices); }
+/* ---- the plan cache of a model ("library owns device buffers cached on ii/om") ----
+   The reference's batch loop reuses ONE integrator instance for all design points and all calls (src/odeSolver.c:313-330).
+   The one-shot entries here keep what is expensive to make -- the compiled module, the loaded kernel, streams, events and
+   the device buffers of every GPU -- in odeModel_t.kernelCache, keyed by the generated kernel text (which folds in the model,
+   the varied and stored index sets and every code-relevant setting).  Tolerances, step limit, time grid and the model's
+   current base values are refreshed on every call.  Freed by ODEModel_free / ODEModel_freeKernelCache.
+   ODES_PLAN_CACHE=0 builds and frees the plans per call as before. */
+struct PlanSet { std::string src; cvodeSettings_t *opt; std::vector<odesBatch_t *> plans; std::mutex run; unsigned long long lastUse; };
+struct KernelCache { std::mutex mu; std::vector<PlanSet *> sets; unsigned long long clock; };
+static std::mutex g_cacheCreate;
+static void planset_free(PlanSet *ps)
+{
+  for (size_t k = 0; k < ps->plans.size(); k++) if (ps->plans[k]) ODESBatch_free(ps->plans[k]);
+  if (ps->opt) CvodeSettings_free(ps->opt);
+  delete ps;
+}
+extern "C" void ODEModel_freeKernelCache(odeModel_t *om)
+{
+  if (!om || !om->kernelCache) return;
+  KernelCache *kc = (KernelCache *)om->kernelCache;
+  for (size_t i = 0; i < kc->sets.size(); i++) planset_free(kc->sets[i]);
+  delete kc;
+  om->kernelCache = NULL;
+}
+/* the caller's settings into the cached clone: everything a launch reads (the code-relevant fields are equal by key) */
+static void refresh_settings(cvodeSettings_t *dst, const cvodeSettings_t *src)
+{
+  dst->Time = src->Time; dst->Error = src->Error; dst->RError = src->RError; dst->Mxstep = src->Mxstep;
+  dst->StoreResults = src->StoreResults; dst->DetectNegState = src->DetectNegState;
+  if (src->TimePoints && dst->TimePoints) for (int i = 0; i <= src->PrintStep; i++) dst->TimePoints[i] = src->TimePoints[i];
+}
+/* a cached plan before its next run: the model's current base values and trigger flags, the time grid */
+static int refresh_plan(odesBatch_t *b)
+{
+  if (!compute_base(b->om, b->opt, b->base, b->trigger0)) return 0;
+  b->nout = b->opt->PrintStep;
+  if (!b->kernel) return 1;                               /* not loaded yet: ensure_loaded uploads everything */
+  CUDA_OK(cudaSetDevice(b->device));
+  CUdeviceptr sym; size_t bytes;
+  DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_base"));
+  if (b->nvalues > 0) DRV_OK(drv.MemcpyHtoD(sym, b->base.data(), sizeof(double) * (size_t)b->nvalues));
+  DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
+  if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
+  CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
+  return 1;
+}
+static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex, int device, std::string &src);
+
+extern "C" int ODESBatch_runHostAllDevicesEx(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex,
+                                             int nsets, const double *values, double *results, double *sens, double *flux, int *status, int ndevices)
 {
   int have = ODES_deviceCount();
   if (ndevices <= 0) {
@@ -859,26 +1025,67 @@ extern "C" int ODESBatch_runHostAllDevicesSens(odeModel_t *om, cvodeSettings_t *
   }
   if (ndevices > have) ndevices = have;
   if (ndevices < 1) ndevices = 1;                              /* no device: the single plan fails loudly below */
+  const bool cached = env_int("ODES_PLAN_CACHE", 1) != 0 && have > 0;
   std::vector<odesBatch_t *> plans((size_t)ndevices, (odesBatch_t *)NULL);
+  PlanSet *ps = NULL;
   int ok = 1;
-  for (int k = 0; k < ndevices && ok; k++) { plans[(size_t)k] = ODESBatch_create(om, opt, nvary, varyIndex, nstore, storeIndex, k); if (!plans[(size_t)k]) ok = 0; }
+  if (cached) {
+    /* look the plan set up by the kernel text this call would compile */
+    std::string src;
+    odesBatch_t *probe = batch_prepare(om, opt, nvary, varyIndex, nstore, storeIndex, 0, src);
+    if (!probe) return 0;
+    ODESBatch_free(probe);
+    std::lock_guard<std::mutex> g(g_cacheCreate);
+    if (!om->kernelCache) { KernelCache *n = new KernelCache(); n->clock = 0; om->kernelCache = n; }
+    KernelCache *kc = (KernelCache *)om->kernelCache;
+    for (size_t i = 0; i < kc->sets.size(); i++) if (kc->sets[i]->src == src) ps = kc->sets[i];
+    if (ps) g_counters[CNT_PLAN_HIT]++;
+    else {
+      /* at most four plan sets per model: the least recently used one makes room (its device buffers are freed) */
+      if (kc->sets.size() >= (size_t)env_int("ODES_PLAN_CACHE_SETS", 4)) {
+        size_t lru = 0;
+        for (size_t i = 1; i < kc->sets.size(); i++) if (kc->sets[i]->lastUse < kc->sets[lru]->lastUse) lru = i;
+        planset_free(kc->sets[lru]); kc->sets.erase(kc->sets.begin() + (long)lru);
+      }
+      ps = new PlanSet(); ps->src = src; ps->opt = CvodeSettings_clone(opt);
+      kc->sets.push_back(ps);
+    }
+    ps->lastUse = ++kc->clock;
+  }
+  std::unique_lock<std::mutex> running;
+  if (ps) {
+    running = std::unique_lock<std::mutex>(ps->run);          /* one run at a time on a plan set */
+    refresh_settings(ps->opt, opt);
+    if (ps->plans.size() < (size_t)ndevices) ps->plans.resize((size_t)ndevices, (odesBatch_t *)NULL);
+    for (int k = 0; k < ndevices && ok; k++) {
+      if (!ps->plans[(size_t)k]) ps->plans[(size_t)k] = ODESBatch_create(om, ps->opt, nvary, varyIndex, nstore, storeIndex, k);
+      else if (!refresh_plan(ps->plans[(size_t)k])) ok = 0;
+      plans[(size_t)k] = ps->plans[(size_t)k];
+      if (!plans[(size_t)k]) ok = 0;
+    }
+  } else {
+    for (int k = 0; k < ndevices && ok; k++) { plans[(size_t)k] = ODESBatch_create(om, opt, nvary, varyIndex, nstore, storeIndex, k); if (!plans[(size_t)k]) ok = 0; }
+  }
   if (ok) {
     const size_t rows = (size_t)(opt->PrintStep + 1) * (size_t)plans[0]->nstore;
     const size_t srows = (size_t)(opt->PrintStep + 1) * (size_t)(plans[0]->nsens > 0 ? plans[0]->nsens : 0) * (size_t)om->neq;
     if (sens && plans[0]->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "sensitivities requested but opt->Sensitivity is off"); ok = 0; }
+    if (flux && plans[0]->nflux <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "fluxes requested but the plan has no flux function"); ok = 0; }
+    const size_t frows = (size_t)(opt->PrintStep + 1) * (size_t)(plans[0]->nflux > 0 ? plans[0]->nflux : 0);
     std::vector<int> done((size_t)ndevices, 0);
     std::vector<std::thread> workers;
     for (int k = 0; k < ndevices && ok; k++) {
       size_t lo = ((size_t)nsets * (size_t)k / (size_t)ndevices) & ~(size_t)31, hi = (k + 1 == ndevices) ? (size_t)nsets : (((size_t)nsets * (size_t)(k + 1) / (size_t)ndevices) & ~(size_t)31);
       workers.emplace_back([&, k, lo, hi]() {
-        done[(size_t)k] = (hi <= lo) ? 1 : ODESBatch_runHostSens(plans[(size_t)k], (int)(hi - lo), values + lo * (size_t)(nvary > 0 ? nvary : 0),
-                                                                 results ? results + lo * rows : NULL, sens ? sens + lo * srows : NULL, status ? status + lo : NULL, 0);
+        done[(size_t)k] = (hi <= lo) ? 1 : ODESBatch_runHostEx(plans[(size_t)k], (int)(hi - lo), values + lo * (size_t)(nvary > 0 ? nvary : 0),
+                                                               results ? results + lo * rows : NULL, sens ? sens + lo * srows : NULL,
+                                                               flux ? flux + lo * frows : NULL, status ? status + lo : NULL, 0);
       });
     }
     for (auto &w : workers) w.join();
     for (int k = 0; k < ndevices; k++) if (!done[(size_t)k]) ok = 0;
   }
-  for (int k = 0; k < ndevices; k++) if (plans[(size_t)k]) ODESBatch_free(plans[(size_t)k]);
+  if (!ps) for (int k = 0; k < ndevices; k++) if (plans[(size_t)k]) ODESBatch_free(plans[(size_t)k]);
   return ok ? ndevices : 0;
 }
 
@@ -901,7 +1108,6 @@ extern "C" int IntegratorInstance_integrateBatchSens(integratorInstance_t *ii, i
   return failed;
 }
 
-extern "C" void ODEModel_freeKernelCache(odeModel_t *om) { (void)om; }
 extern "C" int ODEModel_compileCVODEFunctions(odeModel_t *om)
 {
   /* kept for API compatibility: compilation happens per (model, varied set) in ODESBatch_create */

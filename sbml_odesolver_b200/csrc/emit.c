@@ -760,6 +760,27 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
   free(text); free(leaves); free(group); free(depth); free(refs); free(odeoff); free(odeneg); free(odecnt); free(odediv); free(w.lit);
 }
 
+/* Reaction fluxes as a device function.  The reference maps results after every run by evaluating each
+   kinetic law -- local parameters and constants substituted -- with evaluateAST on the stored values of every time point
+   (src/odeSolver.c:463-471, :519-531).  Here the same indexed trees (SBMLResults_fluxASTs, sbml_results.c) are emitted
+   with the interpreter's arithmetic over one stored row v[0..NVAL) and run by odes_flux_kernel (bdf_kernel.cuh) over the
+   trajectories in HBM.  Reactions without a kinetic law keep the zero of their freshly created time course. */
+static void name_row(charBuffer_t *s, int idx, const emit_ctx_t *c) { (void)c; cbprintf(s, "v[%d]", idx); }
+char *ODEModel_generateCUDAFluxSection(int nflux, ASTNode_t *const *kls)
+{
+  charBuffer_t *b = CharBuffer_create(); emit_ctx_t c; char *out; int r;
+  c.cuda = 1; c.interp = 1; c.name = name_row; c.time = REF_TIME; c.info = NULL; c.leaf = NULL;
+  cbprintf(b, "#define NFLUX %d\nDEV void flux_row(double t, const double *v, double *flux)\n{\n  (void)t; (void)v;\n", nflux);
+  for (r = 0; r < nflux; r++) {
+    cbprintf(b, "  flux[%d] = ", r);
+    if (kls[r]) gen(b, kls[r], &c); else CharBuffer_append(b, "0.0");
+    CharBuffer_append(b, ";\n");
+  }
+  CharBuffer_append(b, "}\n");
+  out = b->b; b->b = NULL; CharBuffer_free(b);
+  return out;
+}
+
 char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
                                   int nstore, const int *store, const double *base)
 { return ODEModel_generateCUDASourceSens(om, opt, nvary, vary, nstore, store, base, NULL); }

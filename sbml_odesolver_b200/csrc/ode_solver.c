@@ -113,6 +113,8 @@ void BatchResults_free(batchResults_t *r)
   for (i = 0; i < r->nvalues; i++) free(r->names[i]);
   for (i = 0; i < r->nsens; i++) free(r->sensParam[i]);
   free(r->sensParam); free(r->sens);
+  for (i = 0; i < r->nflux; i++) free(r->fluxNames[i]);
+  free(r->fluxNames); free(r->flux);
   free(r->names); free(r->time); free(r->value); free(r->status); free(r);
 }
 double BatchResults_getValue(const batchResults_t *r, int set, const char *name, int timestep)
@@ -121,6 +123,15 @@ double BatchResults_getValue(const batchResults_t *r, int set, const char *name,
   for (i = 0; i < r->nvalues; i++)
     if (strcmp(r->names[i], name) == 0) return r->value[((size_t)set * (size_t)r->nout + (size_t)timestep) * (size_t)r->nvalues + (size_t)i];
   SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_SYMBOL_IS_NOT_IN_MODEL, "Symbol %s is not in the model", name);
+  return 0.0;
+}
+
+double BatchResults_getFlux(const batchResults_t *r, int set, const char *reaction, int timestep)
+{
+  int i;
+  for (i = 0; i < r->nflux; i++)
+    if (strcmp(r->fluxNames[i], reaction) == 0) return r->flux[((size_t)set * (size_t)r->nout + (size_t)timestep) * (size_t)r->nflux + (size_t)i];
+  SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_SYMBOL_IS_NOT_IN_MODEL, "Reaction %s has no flux course in these results", reaction);
   return 0.0;
 }
 
@@ -167,7 +178,15 @@ static batchResults_t *run_design_points(Model_t *m, cvodeSettings_t *set, varyS
         }
         ODESense_free(os);
       }
-      if (!ODESBatch_runHostAllDevicesSens(om, set, vs->nrparams, idx, 0, NULL, res->nsets, rows, res->value, res->sens, res->status, 0)) { BatchResults_free(res); res = NULL; }
+      /* reaction fluxes: evaluated on the device from the stored rows (the reference walks every kinetic law at every
+         time point of every design point on the host, src/odeSolver.c:519-531); ODES_HOST_FLUX=1 keeps that path */
+      if (Model_getNumReactions(m) > 0 && !(getenv("ODES_HOST_FLUX") && atoi(getenv("ODES_HOST_FLUX"))) && !(getenv("ODES_FLUX") && !atoi(getenv("ODES_FLUX")))) {
+        res->nflux = (int)Model_getNumReactions(m);
+        res->fluxNames = (char **)calloc((size_t)res->nflux, sizeof(char *));
+        for (i = 0; i < res->nflux; i++) res->fluxNames[i] = sdup(Model_getReaction(m, (unsigned int)i)->id);
+        res->flux = (double *)malloc((size_t)res->nsets * (size_t)res->nout * (size_t)res->nflux * sizeof(double) + 8);
+      }
+      if (!ODESBatch_runHostAllDevicesEx(om, set, vs->nrparams, idx, 0, NULL, res->nsets, rows, res->value, res->sens, res->flux, res->status, 0)) { BatchResults_free(res); res = NULL; }
       free(rows);
       if (res && mapped) *mapped = SBMLResultsArray_fromBatch(m, om, res);
     }

@@ -176,19 +176,28 @@ static resultMap_t *ResultMap_create(Model_t *m, const odeModel_t *om, const SBM
   for (j = 0; j < p->nsp; j++) p->sp[j] = name_index(om, nvalues, r->species->tc[j]->name);
   for (j = 0; j < p->ncomp; j++) p->comp[j] = name_index(om, nvalues, r->compartments->tc[j]->name);
   for (j = 0; j < p->npar; j++) p->par[j] = name_index(om, nvalues, r->parameters->tc[j]->name);
-  p->kls = (ASTNode_t **)calloc((size_t)(p->nflux + 1), sizeof(ASTNode_t *));
+  (void)i;
+  SBMLResults_fluxASTs(m, om, &p->kls);
+  return p;
+}
+/* the indexed kinetic laws of the model's reactions, in reaction order (NULL where a reaction has none): what the flux
+   courses are evaluated from -- on the host by ResultMap_fill, on the device by the emitted flux_row (emit.c).  The caller
+   frees the trees and the array.  Returns the number of reactions. */
+int SBMLResults_fluxASTs(Model_t *m, const odeModel_t *om, ASTNode_t ***kls)
+{
+  int nvalues = om->neq + om->nass + om->nconst, n = (int)Model_getNumReactions(m); unsigned int i;
+  *kls = (ASTNode_t **)calloc((size_t)(n + 1), sizeof(ASTNode_t *));
   for (i = 0; i < Model_getNumReactions(m); i++) {
     Reaction_t *rx = Model_getReaction(m, i);
-    ASTNode_t *kl, *ix;
+    ASTNode_t *kl;
     if (!rx->kineticLaw || !rx->kineticLaw->math) continue;
     kl = copyAST(rx->kineticLaw->math);
     AST_replaceNameByParameters(kl, &rx->kineticLaw->parameters);
     AST_replaceConstants(m, kl);
-    ix = indexAST(kl, nvalues, om->names);       /* same values as the name search of evaluateAST, found once */
+    (*kls)[i] = indexAST(kl, nvalues, om->names);       /* same values as the name search of evaluateAST, found once */
     ASTNode_free(kl);
-    p->kls[i] = ix;
   }
-  return p;
+  return n;
 }
 static void ResultMap_free(resultMap_t *p)
 {
@@ -198,7 +207,7 @@ static void ResultMap_free(resultMap_t *p)
   free(p->kls); free(p->sp); free(p->comp); free(p->par); free(p);
 }
 /* one time point: value[] holds the stored values of that time, data is scratch for the flux evaluation */
-static void ResultMap_fill(const resultMap_t *p, SBMLResults_t *r, int n, double time, const double *value, cvodeData_t *data)
+static void ResultMap_fill(const resultMap_t *p, SBMLResults_t *r, int n, double time, const double *value, cvodeData_t *data, const double *flux)
 {
   int j;
   r->time->values[n] = time;
@@ -207,7 +216,8 @@ static void ResultMap_fill(const resultMap_t *p, SBMLResults_t *r, int n, double
   for (j = 0; j < p->nsp; j++) if (p->sp[j] >= 0) r->species->tc[j]->values[n] = value[p->sp[j]];
   for (j = 0; j < p->ncomp; j++) if (p->comp[j] >= 0) r->compartments->tc[j]->values[n] = value[p->comp[j]];
   for (j = 0; j < p->npar; j++) if (p->par[j] >= 0) r->parameters->tc[j]->values[n] = value[p->par[j]];
-  for (j = 0; j < p->nflux; j++) if (p->kls[j]) r->fluxes->tc[j]->values[n] = evaluateAST(p->kls[j], data);
+  if (flux) { for (j = 0; j < p->nflux; j++) if (p->kls[j]) r->fluxes->tc[j]->values[n] = flux[j]; }      /* evaluated on the device */
+  else for (j = 0; j < p->nflux; j++) if (p->kls[j]) r->fluxes->tc[j]->values[n] = evaluateAST(p->kls[j], data);
 }
 
 SBMLResults_t *SBMLResults_fromIntegrator(Model_t *m, integratorInstance_t *ii)
@@ -221,7 +231,7 @@ SBMLResults_t *SBMLResults_fromIntegrator(Model_t *m, integratorInstance_t *ii)
   row = (double *)malloc(sizeof(double) * (size_t)(data->nvalues > 0 ? data->nvalues : 1));
   for (n = 0; n < r->time->timepoints; n++) {
     for (j = 0; j < data->nvalues; j++) row[j] = cv->value[j][n];
-    ResultMap_fill(map, r, n, cv->time[n], row, data);      /* leaves data at the last time point, as the reference does */
+    ResultMap_fill(map, r, n, cv->time[n], row, data, NULL);      /* leaves data at the last time point, as the reference does */
   }
   free(row);
   ResultMap_free(map);
@@ -279,7 +289,9 @@ SBMLResultsArray_t *SBMLResultsArray_fromBatch(Model_t *m, odeModel_t *om, const
        results: the reference's results end at the last stored index (integratorInstance.c:1141) */
     while (np > 1 && b->nvalues > 0 && v[(size_t)(np - 1) * (size_t)b->nvalues] != v[(size_t)(np - 1) * (size_t)b->nvalues]) np--;
     a->results[i] = SBMLResults_create(m, np);
-    for (n = 0; n < np; n++) ResultMap_fill(map, a->results[i], n, b->time[n], v + (size_t)n * (size_t)b->nvalues, data);
+    /* fluxes: the device evaluated them (b->flux, Model_odeSolverBatch); else the kinetic laws are walked here */
+    for (n = 0; n < np; n++) ResultMap_fill(map, a->results[i], n, b->time[n], v + (size_t)n * (size_t)b->nvalues, data,
+                                            (b->flux && b->nflux == map->nflux) ? b->flux + ((size_t)i * (size_t)b->nout + (size_t)n) * (size_t)b->nflux : NULL);
     if (b->nsens > 0 && b->sens) {             /* SBMLResults_createSens per design point (src/odeSolver.c:545-575) */
       SBMLResults_t *r = a->results[i]; int j, e;
       const double *sv = b->sens + (size_t)i * (size_t)b->nout * (size_t)b->nsens * (size_t)b->neq;

@@ -165,6 +165,48 @@ def test_run_host_pipeline_and_one_shot_entry():
     L.IntegratorInstance_free(ii)
 
 
+def test_one_shot_entry_keeps_its_plans_on_the_model():
+    """IntegratorInstance_integrateBatch, the reference-shaped entry (caller's malloc'd arrays, all model values): the second
+    call with the same model / settings / varied set compiles nothing, loads no module and allocates nothing on the device
+    (buffers cached on ii / om); changed tolerances and a changed time grid reuse the plan and still give the
+    vendored CVODE's bits."""
+    L = so.lib()
+    w = H.workload("mapk", nout=20)
+    m = w["model"]
+    vals = H.workload_values(w, 96, seed=77)
+    ii = L.IntegratorInstance_create(m.om, w["opt"])
+    vis = (C.c_void_p * len(w["vary"]))(*[L.ODEModel_getVariableIndexByNum(m.om, i) for i in w["vary"]])
+
+    def call(opt_ii):
+        out = np.full((96, 21, m.nvalues), -1.0)
+        st = np.full(96, -99, dtype=np.int32)
+        assert L.IntegratorInstance_integrateBatch(opt_ii, 96, len(w["vary"]), vis, vals.ctypes.data, out.ctypes.data, st.ctypes.data) == 0
+        return out
+    first = call(ii)
+    c1 = so.counters()
+    second = call(ii)
+    c2 = so.counters()
+    assert np.array_equal(first, second)
+    for k in ("nvrtc_compiles", "cubin_cache_loads", "module_loads", "device_allocations", "plans_created"):
+        assert c2[k] == c1[k], (k, c1, c2)
+    assert c2["plan_cache_hits"] == c1["plan_cache_hits"] + 1 and c2["kernel_launches"] > c1["kernel_launches"]
+    ref = _oracle(w, vals)
+    assert np.array_equal(first, ref["out"], equal_nan=True)
+    # tighter tolerances and another end time through the same cached plan
+    opt2 = so.settings(w["end"] / 2, 20, 1e-10, 1e-7)
+    ii2 = L.IntegratorInstance_create(m.om, opt2)
+    third = call(ii2)
+    c3 = so.counters()
+    assert c3["plans_created"] == c2["plans_created"] and c3["nvrtc_compiles"] == c2["nvrtc_compiles"] and c3["module_loads"] == c2["module_loads"]
+    w2 = dict(w, opt=opt2)
+    assert np.array_equal(third, _oracle(w2, vals)["out"], equal_nan=True)
+    L.ODEModel_freeKernelCache(m.om)
+    fourth = call(ii)
+    assert np.array_equal(fourth, first) and so.counters()["plans_created"] == c3["plans_created"] + 1
+    L.IntegratorInstance_free(ii2)
+    L.IntegratorInstance_free(ii)
+
+
 def test_full_size_properties():
     """BASELINE config 2 at a size the oracle cannot cover: size-independent properties of the model.
     MAPK conserves MKKK+MKKK_P, MKK+MKK_P+MKK_PP and MAPK+MAPK_P+MAPK_PP (stoichiometry), concentrations stay

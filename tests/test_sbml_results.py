@@ -18,7 +18,8 @@ import sbml_odesolver_b200 as so
 class BatchResults(C.Structure):
     _fields_ = [("nsets", C.c_int), ("nout", C.c_int), ("nvalues", C.c_int), ("names", C.c_void_p),
                 ("time", C.POINTER(C.c_double)), ("value", C.POINTER(C.c_double)), ("status", C.POINTER(C.c_int)),
-                ("nsens", C.c_int), ("neq", C.c_int), ("sensParam", C.c_void_p), ("sens", C.POINTER(C.c_double))]
+                ("nsens", C.c_int), ("neq", C.c_int), ("sensParam", C.c_void_p), ("sens", C.POINTER(C.c_double)),
+                ("nflux", C.c_int), ("fluxNames", C.c_void_p), ("flux", C.POINTER(C.c_double))]
 
 
 def _flat(out, status, times):
@@ -27,7 +28,7 @@ def _flat(out, status, times):
     status = np.ascontiguousarray(status, dtype=np.int32)
     times = np.ascontiguousarray(times, dtype=np.float64)
     b = BatchResults(out.shape[0], out.shape[1], out.shape[2], None, times.ctypes.data_as(C.POINTER(C.c_double)),
-                     out.ctypes.data_as(C.POINTER(C.c_double)), status.ctypes.data_as(C.POINTER(C.c_int)), 0, 0, None, None)
+                     out.ctypes.data_as(C.POINTER(C.c_double)), status.ctypes.data_as(C.POINTER(C.c_int)), 0, 0, None, None, 0, None, None)
     b._keep = (out, status, times)
     return b
 
@@ -192,3 +193,54 @@ def test_model_odesolverbatch_on_gpu_returns_results_per_design_point():
             assert np.array_equal(_course(res, name), ref["out"][s, :, mg.names.index(name)]), (s, name)
     L.SBMLResultsArray_free(arr)
     L.VarySettings_free(vs)
+
+
+@pytest.mark.gpu
+def test_device_fluxes_equal_the_host_interpreter_and_the_reference_printout():
+    """odes_flux_kernel over the stored rows == evaluateAST on the host (the reference's mapping, src/odeSolver.c:519-531)
+    bit for bit, on the nominal MAPK run (examples/testrun.out:132-234 digits) and on a scanned batch."""
+    L = so.lib()
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    opt = so.settings(1000.0, 100, 1e-9, 1e-4, mxstep=1000)
+    b = so.Batch(m, opt, [])
+    assert b.nflux == 10
+    b.reserve(32)
+    b.integrate(1)
+    fl = b.fluxes(1)[0]                                                # [row][reaction]
+    gold = _gold("mapk_testrun_fluxes.txt")
+    for k in range(10):
+        assert np.array_equal(_six(fl[:, k]), gold[:, 1 + k]), f"J{k}"
+    out = np.transpose(b.results(1), (2, 0, 1))                        # [set][row][value]
+    flat = _flat(out, np.array([0]), np.array([L.CvodeSettings_getTime(opt, i) for i in range(101)]))
+    arr = L.SBMLResultsArray_fromBatch(m.sbml, m.om, C.byref(flat))     # no device fluxes in this record: host evaluateAST
+    res = L.SBMLResultsArray_getResults(arr, 0)
+    for k in range(10):
+        assert np.array_equal(_course(res, f"J{k}"), fl[:, k]), f"J{k}"
+    L.SBMLResultsArray_free(arr)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_model_odesolverbatch_fluxes_device_path_equals_host_path(monkeypatch):
+    """Model_odeSolverBatch maps fluxes on the device; ODES_HOST_FLUX=1 keeps the reference's host walk: same bits, incl.
+    the scanned kinetic-law parameter (globalised r_J1_V2) and row 0."""
+    L = so.lib()
+    rng = np.random.default_rng(11)
+    pts = np.array([[2.5 * 2 ** rng.uniform(-1, 1), 0.25 * 2 ** rng.uniform(-1, 1)] for _ in range(40)])
+
+    def run():
+        m = so.Model(H.model_path("mapk_cascade.xml"))
+        vs = L.VarySettings_allocate(2, len(pts))
+        assert L.VarySettings_addParameter(vs, b"V1", None) and L.VarySettings_addParameter(vs, b"V2", b"J1")
+        for row in pts:
+            assert L.VarySettings_addDesignPoint(vs, np.ascontiguousarray(row).ctypes.data)
+        arr = L.Model_odeSolverBatch(m.sbml, so.settings(1000.0, 50, 1e-9, 1e-6), vs)
+        assert arr, so.errors()
+        got = np.array([[_course(L.SBMLResultsArray_getResults(arr, s), f"J{k}") for k in range(10)] for s in range(len(pts))])
+        L.SBMLResultsArray_free(arr)
+        L.VarySettings_free(vs)
+        return got
+    dev = run()
+    monkeypatch.setenv("ODES_HOST_FLUX", "1")
+    host = run()
+    assert np.array_equal(dev, host) and np.isfinite(dev).all() and (dev[:, 1, 1:] != dev[0, 1, 1:]).any()
