@@ -6,6 +6,7 @@ identical event firing order, identical failure flags.  The kernel replays CVODE
 operations in the reference's order, no FMA contraction, glibc's pow restated), so the tests demand more than the
 gate: the same per-trajectory work counters (nst, nfe, nsetups, nje, nni, ncfn, netf) and BIT-IDENTICAL stored
 values against the oracle driven with the same emitted right-hand side (the reference's compiled mode)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -131,7 +132,6 @@ def test_failure_flags_and_nan_rows():
 
 def test_run_host_pipeline_and_one_shot_entry():
     """ODESBatch_runHost (chunked H2D / kernel / D2H overlap) and IntegratorInstance_integrateBatch give the plan's results."""
-    import ctypes as C
     w = H.workload("mapk", nout=20)
     m, L = w["model"], so.lib()
     vals = H.workload_values(w, 1000, seed=6)
