@@ -20,6 +20,13 @@ struct cvodeSettings {
   int HaltOnEvent; int SteadyState; double ssThreshold;
   int UseJacobian; int StoreResults; int compileFunctions;
   int observation_data_type; int DoAdjoint;
+  /* adjoint / discrete-data / FIM tail of the reference's struct (integratorSettings.h:118-148): inert here -- kept so that
+     sizeof(struct cvodeSettings) and every field offset are the reference's for callers that allocate or copy the struct */
+  double AdjTime; int AdjPrintStep; double *AdjTimePoints;
+  int nSaveSteps; int ncheck;
+  double AdjError; double AdjRError; int AdjStoreResults;
+  int OffSet; int InterStep;
+  int doFIM;
 };
 
 /* reference integratorSettings.h:150-169 ("not used currently"): start and end time, step, number of steps */

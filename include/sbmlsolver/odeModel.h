@@ -177,7 +177,16 @@ char *ODEModel_generateCSourceSens(odeModel_t *, const odeSense_t *os);
 compiled_code_t *Compiler_compile(const char *sourceCode);
 void *CompiledCode_getFunction(compiled_code_t *, const char *symbol);
 void CompiledCode_free(compiled_code_t *);
+/* reference odeModel.h:356-363, the callback seam: compile the model's right-hand side / Jacobian / event functions (here:
+   the model's sm_100a kernel module under default settings, kept in the model's plan cache) and hand out the compiled
+   callbacks.  The reference returns host function pointers (CVRhsFn, CVDlsDenseJacFn, CVSensRhs1Fn); here the handle is the
+   CUfunction of the module's kernel -- opaque to the caller, NULL + SolverError when the Jacobian (130501) or the
+   parametric matrix (130505) is missing or no device can load the module. */
 int ODEModel_compileCVODEFunctions(odeModel_t *);
+int ODESense_compileCVODESenseFunctions(odeSense_t *);
+void *ODEModel_getCompiledCVODERHSFunction(odeModel_t *);
+void *ODEModel_getCompiledCVODEJacobianFunction(odeModel_t *);
+void *ODESense_getCompiledCVODESenseFunction(odeSense_t *);
 
 #ifdef __cplusplus
 }

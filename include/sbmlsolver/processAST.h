@@ -16,6 +16,8 @@ struct cvodeData;
 ASTNode_t *copyAST(const ASTNode_t *f);
 ASTNode_t *indexAST(const ASTNode_t *f, int nvalues, char **names);
 ASTNode_t *simplifyAST(const ASTNode_t *f);
+/* reference processAST.h:62: determinant of an N x N matrix of expressions (cofactor expansion, simplified); caller frees */
+ASTNode_t *determinantNAST(ASTNode_t ***A, int N);
 ASTNode_t *differentiateAST(ASTNode_t *f, char *x);
 void AST_dump(const char *context, ASTNode_t *node);
 int ASTNode_getIndices(const ASTNode_t *node, List_t *indices);

@@ -49,6 +49,10 @@ int TimeCourse_getNumValues(const timeCourse_t *);
 double TimeCourse_getValue(const timeCourse_t *, int);
 double TimeCourse_getSensitivity(const timeCourse_t *, int, int);
 void SBMLResults_dump(const SBMLResults_t *);
+/* reference sbmlResults.h:134 (declared there, never defined): writes the LAST stored value of every species, non-constant
+   compartment and non-constant global parameter course into the model's initial values, so that a following run continues
+   from the end state; returns the model */
+Model_t *Model_setValues(Model_t *, SBMLResults_t *);
 void SBMLResults_dumpSpecies(const SBMLResults_t *);
 void SBMLResults_dumpCompartments(const SBMLResults_t *);
 void SBMLResults_dumpParameters(const SBMLResults_t *);

@@ -57,6 +57,10 @@ static struct {
     SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "%s failed: %s", #call, cudaGetErrorString(e_)); return 0; } } while (0)
 #define DRV_OK(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { \
     SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "%s failed with CUresult %d", #call, (int)r_); return 0; } } while (0)
+/* Host-to-device uploads from PAGEABLE caller memory with the synchronous copy calls return once the data is staged, not once
+   the DMA has landed, and the kernels run on non-blocking streams that do not order against the NULL stream: wait for the
+   NULL stream after every such group of uploads, before anything can be launched that reads them */
+#define UPLOAD_FENCE() CUDA_OK(cudaStreamSynchronize(cudaStreamLegacy))
 
 static int load_driver(void)
 {
@@ -488,6 +492,11 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
     return NULL;
   }
   if (om->nevents > 32) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "at most 32 events are supported"); return NULL; }
+  /* reference src/cvodeSolver.c:971-975: with DetectNegState the right-hand side reports a RECOVERABLE failure on a negative
+     state and CVODE (>= 2.4) repeats the step with a quarter of the step size.  The vendored CVODE 2.3.0 this path is pinned
+     to has no recoverable right-hand-side failures (its RhsFn returns void), so there is no reference arithmetic to reproduce:
+     the switch is refused instead of being ignored */
+  if (opt->DetectNegState) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "DetectNegState is not supported by the batched integrator (no recoverable right-hand-side failures); unset it with CvodeSettings_setDetectNegState(set, 0)"); return NULL; }
   odesBatch_t *b = new odesBatch();
   b->om = om; b->opt = opt; b->device = device; b->nvary = nvary; b->nout = opt->PrintStep;
   b->nvalues = om->neq + om->nass + om->nconst;
@@ -531,6 +540,7 @@ static int ensure_loaded(odesBatch_t *b)
   if (b->nvalues > 0) DRV_OK(drv.MemcpyHtoD(sym, b->base.data(), sizeof(double) * (size_t)b->nvalues));
   DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
   if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
+  UPLOAD_FENCE();
   if (b->warpMode) {
     unsigned int wmBytes = 0;
     DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_warpmem_bytes"));
@@ -565,6 +575,7 @@ static int ensure_loaded(odesBatch_t *b)
   if (b->laMode == 1) CUDA_OK(cudaMalloc(&b->d_scratch, sizeof(double) * (size_t)b->laWords * (size_t)b->numSMs * (size_t)b->blocksPerSM * (size_t)b->block));
   CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * (size_t)(b->opt->PrintStep + 1)));
   CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
   return 1;
 }
 
@@ -591,6 +602,7 @@ extern "C" int ODESBatch_setTimeGrid(odesBatch_t *b, int nout, const double *tpo
   if (!ensure_loaded(b)) return 0;
   if (nout > b->opt->PrintStep || nout < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "time grid longer than the plan's"); return 0; }
   CUDA_OK(cudaMemcpy(b->d_tpoints, tpoints, sizeof(double) * (size_t)(nout + 1), cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
   b->nout = nout;
   return 1;
 }
@@ -601,6 +613,7 @@ extern "C" int ODESBatch_setInitialSensitivities(odesBatch_t *b, const double *s
   if (!ODESBatch_reserve(b, 1)) return 0;
   b->sensFromRow0 = s0 ? 1 : 0;
   if (s0) CUDA_OK(cudaMemcpy(b->d_sens, s0, sizeof(double) * (size_t)b->nsens * (size_t)b->om->neq, cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
   return 1;
 }
 extern "C" int ODESBatch_setInitialTriggers(odesBatch_t *b, const int *trigger)
@@ -610,6 +623,7 @@ extern "C" int ODESBatch_setInitialTriggers(odesBatch_t *b, const int *trigger)
     CUdeviceptr sym; size_t bytes;
     DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
     DRV_OK(drv.MemcpyHtoD(sym, trigger, sizeof(int) * (size_t)b->om->nevents));
+    UPLOAD_FENCE();
   }
   return 1;
 }
@@ -741,6 +755,7 @@ extern "C" int ODESBatch_generateValues(odesBatch_t *b, int nsets, unsigned long
   CUDA_OK(cudaMemcpy(d, base, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d + b->nvary, lo, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d + 2 * b->nvary, hi, sizeof(double) * (size_t)b->nvary, cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
   odes_generate_values_kernel<<<(nsets + 255) / 256, 256, 0, b->stream>>>(b->d_vary, (size_t)b->capacity, nsets, b->nvary, seed, firstSet,
                                                                          d, d + b->nvary, d + 2 * b->nvary, log10Scale);
   CUDA_OK(cudaGetLastError());
@@ -1011,6 +1026,7 @@ static int refresh_plan(odesBatch_t *b)
   DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
   if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
   CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
   return 1;
 }
 static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex, int device, std::string &src);
@@ -1108,8 +1124,75 @@ extern "C" int IntegratorInstance_integrateBatchSens(integratorInstance_t *ii, i
   return failed;
 }
 
-extern "C" int ODEModel_compileCVODEFunctions(odeModel_t *om)
+/* ---- the callback seam of the reference (src/sbmlsolver/odeModel.h:356-363, src/odeModel.c:3191-3299, :3382-3440) ----
+   ODEModel_compileCVODEFunctions assembles the model's right-hand side, Jacobian and event functions, compiles them and
+   keeps the code on the model; the getters hand out what CVODE is given as callbacks.  Here the compiled code is the
+   model's kernel module for sm_100a (the right-hand side, Jacobian and event functions are device functions inside it), kept
+   in the model's plan cache under DEFAULT settings, and the getters return the CUfunction of that module's kernel as an
+   opaque handle -- there is no host-callable function to return; NULL with a SolverError when the Jacobian / parametric
+   matrix is missing (the reference's error codes) or when no device can load the module. */
+static cvodeSettings_t *seam_settings(const odeSense_t *os)
 {
-  /* kept for API compatibility: compilation happens per (model, varied set) in ODESBatch_create */
-  return om != NULL;
+  cvodeSettings_t *opt = CvodeSettings_create();
+  if (opt && os) {
+    std::vector<char *> ids;
+    for (int k = 0; k < os->nsens; k++) ids.push_back(os->om->names[os->index_sens[k]]);
+    opt->Sensitivity = 1;
+    CvodeSettings_setSensParams(opt, ids.data(), (int)ids.size());
+  }
+  return opt;
+}
+static int seam_compile(odeModel_t *om, const odeSense_t *os)
+{
+  if (!om) return 0;
+  cvodeSettings_t *opt = seam_settings(os);
+  if (!opt) return 0;
+  /* a run over zero sets: generates, compiles and caches the plan (without a device: compiles and drops it) */
+  const int ok = ODESBatch_runHostAllDevicesEx(om, opt, 0, NULL, 0, NULL, 0, NULL, NULL, NULL, NULL, NULL, 1) > 0;
+  CvodeSettings_free(opt);
+  return ok;
+}
+static void *seam_kernel(odeModel_t *om, const odeSense_t *os)
+{
+  if (!seam_compile(om, os)) return NULL;
+  if (!om->kernelCache) { need_device(0); return NULL; }                  /* no device: the error is on the stack */
+  cvodeSettings_t *opt = seam_settings(os);
+  std::string src;
+  odesBatch_t *probe = batch_prepare(om, opt, 0, NULL, 0, NULL, 0, src);
+  if (probe) ODESBatch_free(probe);
+  CvodeSettings_free(opt);
+  KernelCache *kc = (KernelCache *)om->kernelCache;
+  std::lock_guard<std::mutex> g(g_cacheCreate);
+  for (size_t i = 0; i < kc->sets.size(); i++)
+    if (kc->sets[i]->src == src && !kc->sets[i]->plans.empty() && kc->sets[i]->plans[0]) {
+      odesBatch_t *b = kc->sets[i]->plans[0];
+      if (!ensure_loaded(b)) return NULL;
+      return (void *)b->kernel;
+    }
+  return NULL;
+}
+extern "C" int ODEModel_compileCVODEFunctions(odeModel_t *om) { return seam_compile(om, NULL); }
+extern "C" void *ODEModel_getCompiledCVODERHSFunction(odeModel_t *om) { return om ? seam_kernel(om, NULL) : NULL; }
+extern "C" void *ODEModel_getCompiledCVODEJacobianFunction(odeModel_t *om)
+{
+  if (!om) return NULL;
+  if (!om->jacobian) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CANNOT_COMPILE_JACOBIAN_NOT_COMPUTED,
+                      "Attempting to compile jacobian before the jacobian is computed\nCall ODEModel_constructJacobian before calling\n"
+                      "ODEModel_getCompiledCVODEJacobianFunction or ODEModel_getCompiledCVODERHSFunction\n");
+    return NULL;
+  }
+  return seam_kernel(om, NULL);
+}
+extern "C" int ODESense_compileCVODESenseFunctions(odeSense_t *os) { return (os && os->om && os->sensitivity) ? seam_compile(os->om, os) : 0; }
+extern "C" void *ODESense_getCompiledCVODESenseFunction(odeSense_t *os)
+{
+  if (!os || !os->om) return NULL;
+  if (!os->sensitivity) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CANNOT_COMPILE_SENSITIVITY_NOT_COMPUTED,
+                      "Attempting to compile sensitivity matrix before the matrix is computed\nCall ODESense_constructSensitivity before calling\n"
+                      "ODESense_getCompiledCVODESenseFunction\n");
+    return NULL;
+  }
+  return seam_kernel(os->om, os);
 }

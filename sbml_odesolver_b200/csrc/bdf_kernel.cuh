@@ -1490,6 +1490,24 @@ struct Solver {
   }
 };
 
+/* development instrumentation (-DODES_LANE_PROFILE=1): per block of the pass, how often it ran and with how many lanes;
+   the last block of the grid prints the totals */
+#ifndef ODES_LANE_PROFILE
+#define ODES_LANE_PROFILE 0
+#endif
+#if ODES_LANE_PROFILE && !defined(ODES_HOST_EMULATION)
+__device__ unsigned long long odes_prof[40];
+__device__ unsigned int odes_prof_done;
+#define PROF_DECL unsigned int prof_runs[16], prof_lanes[16]; _Pragma("unroll") for (int k_ = 0; k_ < 16; k_++) { prof_runs[k_] = 0u; prof_lanes[k_] = 0u; }
+#define PROF(k, pred) do { const unsigned int n_ = ODES_WARP_COUNT(pred); prof_runs[k] += 1u; prof_lanes[k] += n_; } while (0)
+#define PROF_IF_ANY(k, pred) do { if (ODES_WARP_ANY(pred)) PROF(k, pred); } while (0)
+#define PROF_FLUSH do { if ((threadIdx.x & 31u) == 0u) { _Pragma("unroll") for (int k_ = 0; k_ < 16; k_++) { atomicAdd(&odes_prof[k_], (unsigned long long)prof_runs[k_]); atomicAdd(&odes_prof[16 + k_], (unsigned long long)prof_lanes[k_]); } } } while (0)
+#else
+#define PROF_DECL
+#define PROF(k, pred) ((void)0)
+#define PROF_IF_ANY(k, pred) ((void)0)
+#define PROF_FLUSH ((void)0)
+#endif
 /* One lane integrates one trajectory at a time: reset, set varied values, integrate over the output grid with
    the reference's output-time event handling (src/odeSolver.c:313-330, src/integratorInstance.c:1088-1237).
    Lanes are persistent: a lane whose trajectory is finished takes the next set index from a global counter
@@ -1519,9 +1537,11 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
   bool exhausted = false;
   s.st = ST_DONE;
   s.init_state();
+  PROF_DECL
 
   for (;;) {
     ODES_WARP_SYNC();
+    PROF(0, true); PROF(8, s.st == ST_DONE && !exhausted); PROF(9, s.st == ST_DONE && exhausted); PROF(10, s.st == ST_SETUP); PROF(11, s.st == ST_F); PROF(12, s.st == ST_PRE);
     /* ---- FINISH + REFILL: close finished trajectories, hand out new set indices ---- */
     if (s.st == ST_FINISH) {
       /* rows never reached (solver failure or halt on event) are marked not-a-number */
@@ -1592,6 +1612,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     /* ---- START: solver (re)start at t from y[] (first call, or after an event assignment) ---- */
     if (ODES_WARP_ANY(s.st == ST_START)) {
       const bool act = (s.st == ST_START);
+      PROF(1, act);
       if (act) {
         s.reinit(t);
         tout = a.tpoints[iout];
@@ -1605,6 +1626,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     }
     /* ---- PRE ---- */
     ODES_BLOCK_ALIGN(1);
+    PROF_IF_ANY(2, s.st == ST_PRE);
     if (s.st == ST_PRE) {
       const int rc = s.blk_pre(a.mxstep);
       if (rc < 0) { status = rc; s.st = ST_FINISH; }
@@ -1614,6 +1636,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     ODES_BLOCK_ALIGN(2);
     if (ODES_WARP_ANY(s.st == ST_F)) {
       const bool act = (s.st == ST_F);
+      PROF(3, act);
       s.f(s.tn, act);
       if (act) s.after_f();
       ODES_WARP_SYNC();
@@ -1633,7 +1656,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
         const bool run = (nwant >= ODES_SETUP_MIN) || ODES_WARP_ANY(want && s.waited >= ODES_SETUP_WAIT) ||
                          ODES_WARP_ALL(want || s.st == ST_DONE);
 #endif
-        if (run) { const int rc = s.blk_setup(want); if (want && rc < 0) { status = rc; s.st = ST_FINISH; } }
+        if (run) { PROF(4, want); const int rc = s.blk_setup(want); if (want && rc < 0) { status = rc; s.st = ST_FINISH; } }
         else if (want) s.waited++;
         ODES_WARP_SYNC();
       }
@@ -1642,6 +1665,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     ODES_BLOCK_ALIGN(4);
     if (ODES_WARP_ANY(s.st == ST_NEWTON)) {
       const bool act = (s.st == ST_NEWTON);
+      PROF(5, act);
       const int rc = s.blk_newton(act);
       if (act && rc < 0) { status = rc; s.st = ST_FINISH; }
       ODES_WARP_SYNC();
@@ -1650,6 +1674,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     ODES_BLOCK_ALIGN(8);
     if (ODES_WARP_ANY(s.st == ST_COMPLETE)) {
       const bool act = (s.st == ST_COMPLETE);
+      PROF(6, act);
       s.blk_complete(act, tout);
       if (act && s.after_step(tout, t)) s.st = ST_OUTPUT;
       ODES_WARP_SYNC();
@@ -1659,6 +1684,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
 #endif
     /* ---- OUTPUT: rows covered by the last step ---- */
     if (ODES_WARP_ANY(s.st == ST_OUTPUT)) {
+      PROF(7, s.st == ST_OUTPUT);
       double pvl[A1(NPVP)];
       la_load<NPVCH>(la, LAPV, pvl);
       PvRef pv; pv.p = pvl; pv.s = 1u;
@@ -1709,6 +1735,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
 #endif
     }
   }
+  PROF_FLUSH;
 }
 
 #ifndef ODES_HOST_EMULATION
@@ -1734,6 +1761,19 @@ extern "C" __global__ void __launch_bounds__(ODES_BLOCK, ODES_MINBLOCKS) odes_bd
   la.taddr = tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16) + (threadIdx.x >> 7) * (unsigned int)(2 * ODES_LA_WORDS);
 #endif
   integrate_lanes(a, odes_smem + threadIdx.x, la);
+#if ODES_LANE_PROFILE
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&odes_prof_done, 1u) + 1u == gridDim.x) {
+      __threadfence();
+      static const char *const nm[16] = {"pass", "START", "PRE", "F", "SETUP", "NEWTON", "COMPLETE", "OUTPUT", "idle:refill", "idle:exhausted", "wait:setup", "in:F", "in:PRE", "-", "-", "-"};
+      for (int k = 0; k < 13; k++) printf("PROF %-16s runs %12llu lanes %14llu avg %.2f\n", nm[k], odes_prof[k], odes_prof[16 + k], odes_prof[k] ? (double)odes_prof[16 + k] / (double)odes_prof[k] : 0.0);
+      for (int k = 0; k < 32; k++) odes_prof[k] = 0ull;
+      odes_prof_done = 0u;
+    }
+  }
+#endif
 #if ODES_LA == 2
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();

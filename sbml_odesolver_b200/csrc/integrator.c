@@ -375,23 +375,24 @@ void IntegratorInstance_printResults(const integratorInstance_t *ii, FILE *fp)
     fprintf(fp, "\n");
   }
 }
-/* reference src/integratorInstance.c:1442-1507: mean and std of the ODE right-hand sides below threshold */
+/* reference src/integratorInstance.c:1442-1507: mean of the |rates| plus the deviation of the SIGNED rates from that mean
+   (d = rate_i - mean(|rate|), variance over neq - 1 -- for one equation that is 0/0, not-a-number, and no steady state is
+   ever reported, exactly like the reference and the emitted device steady_f) below the threshold */
 int IntegratorInstance_checkSteadyState(integratorInstance_t *engine)
 {
   int i; double dy_mean = 0.0, dy_var = 0.0, dy_std; cvodeData_t *data = engine->data; odeModel_t *om = engine->om;
-  double *dy;
-  if (om->neq == 0) return 0;
-  dy = (double *)malloc((size_t)om->neq * sizeof(double));
-  for (i = 0; i < om->nass; i++) { nonzeroElem_t *o = om->assignmentOrder[i]; data->value[o->i] = evaluateAST(o->ij, data); }
-  for (i = 0; i < om->neq; i++) { dy[i] = fabs(evaluateAST(om->ode[i], data)); dy_mean += dy[i]; }
-  dy_mean /= om->neq;
-  for (i = 0; i < om->neq; i++) dy_var += (dy[i] - dy_mean) * (dy[i] - dy_mean);
-  free(dy);
-  dy_var = om->neq > 1 ? dy_var / (om->neq - 1) : 0.0;
+  if (om->neq == 0) { data->steadystate = 0; return 0; }
+  if (!data->allRulesUpdated)
+    for (i = 0; i < om->nassbeforeodes; i++) { nonzeroElem_t *o = om->assignmentsBeforeODEs[i]; data->value[o->i] = evaluateAST(o->ij, data); }
+  for (i = 0; i < om->neq; i++) dy_mean += fabs(evaluateAST(om->ode[i], data));
+  dy_mean = dy_mean / om->neq;
+  for (i = 0; i < om->neq; i++) { const double d = evaluateAST(om->ode[i], data) - dy_mean; dy_var += d * d; }
+  dy_var = dy_var / (om->neq - 1);
   dy_std = sqrt(dy_var);
   if ((dy_mean + dy_std) < engine->opt->ssThreshold) {
     data->steadystate = 1;
-    SolverError_error(MESSAGE_ERROR_TYPE, SOLVER_ERROR_NO_ERROR, "Steady state found. Simulation aborted at %g seconds. Mean of rates: %g, std %g", (double)data->currenttime, dy_mean, dy_std);
+    if (engine->opt->SteadyState)
+      SolverError_error(MESSAGE_ERROR_TYPE, SOLVER_MESSAGE_STEADYSTATE_FOUND, "Steady state found. Simulation aborted at %g seconds. Mean of rates: %g, std %g", (double)data->currenttime, dy_mean, dy_std);
     return 1;
   }
   data->steadystate = 0;

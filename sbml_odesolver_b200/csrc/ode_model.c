@@ -786,6 +786,22 @@ ASTNode_t *ODEModel_constructDeterminant(const odeModel_t *om)
   return det;
 }
 
+/* reference src/processAST.c:1152-1251 (processAST.h:62, "experimental"): the determinant of an N x N matrix of expression
+   trees, as a simplified tree; the caller frees it.  Same cofactor expansion as above over a caller-supplied matrix. */
+ASTNode_t *determinantNAST(ASTNode_t ***A, int N)
+{
+  int i, *idx; ASTNode_t *det, *simple;
+  if (!A || N < 1) return NULL;
+  idx = (int *)malloc((size_t)N * sizeof(int));
+  for (i = 0; i < N; i++) idx[i] = i;
+  det = minor_det(A, idx, idx, N);
+  free(idx);
+  if (!det) { det = ASTNode_create(); ASTNode_setInteger(det, 0); }
+  simple = simplifyAST(det);
+  ASTNode_free(det);
+  return simple;
+}
+
 void ODEModel_freeJacobian(odeModel_t *om)
 {
   int i, j;

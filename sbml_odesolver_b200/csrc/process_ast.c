@@ -72,51 +72,45 @@ static int depends_on(const ASTNode_t *f, const char *x)
   return found;
 }
 
-/* ------------------------------------------------------------- indexAST */
+/* ------------------------------------------------------------- indexAST
+   Copy of an expression in which every symbol that names a model value carries its position in value[] (reference
+   src/processAST.c:1276-1360).  A symbol "<id>_data" stands for the observation data of <id>: it is indexed like <id> and
+   flagged.  Whichever of the two readings occurs FIRST in names[] wins, as in the reference's single pass over names[]. */
+static int name_position(char **names, int nvalues, const char *s, size_t len)
+{
+  int i;
+  for (i = 0; i < nvalues; i++) if (strlen(names[i]) == len && strncmp(names[i], s, len) == 0) return i;
+  return nvalues;
+}
+static ASTNode_t *indexed_symbol(const ASTNode_t *f, int nvalues, char **names)
+{
+  const char *id = ASTNode_getName(f);
+  const size_t len = id ? strlen(id) : 0;
+  const int whole = id ? name_position(names, nvalues, id, len) : nvalues;
+  const int stem = (id && len > 5 && strstr(id, "_data")) ? name_position(names, nvalues, id, len - 5) : nvalues;
+  ASTNode_t *n;
+  if (whole == nvalues && stem == nvalues) { n = ASTNode_create(); ASTNode_setName(n, id); }
+  else {
+    n = ASTNode_createIndexName();
+    if (whole < stem) { ASTNode_setName(n, id); ASTNode_setIndex(n, (unsigned int)whole); }
+    else { ASTNode_setName(n, names[stem]); ASTNode_setIndex(n, (unsigned int)stem); ASTNode_setData(n); }
+  }
+  ASTNode_setType(n, ASTNode_getType(f));            /* AST_NAME_TIME stays what it is */
+  return n;
+}
 ASTNode_t *indexAST(const ASTNode_t *f, int nvalues, char **names)
 {
-  int i; unsigned int k;
-  ASTNode_t *index = ASTNode_create();
-
-  if (ASTNode_isInteger(f)) ASTNode_setInteger(index, ASTNode_getInteger(f));
-  else if (ASTNode_isReal(f)) ASTNode_setReal(index, ASTNode_getReal(f));
-  else if (ASTNode_isName(f)) {
-    int found = 0;
-    const char *str = ASTNode_getName(f);
-    char *short_str = NULL;
-    /* "<id>_data" refers to observation data of <id> (reference :1308-1334) */
-    if (str && strstr(str, "_data") != NULL && strlen(str) > 5) {
-      short_str = (char *)calloc(strlen(str) - 5 + 1, 1);
-      strncpy(short_str, str, strlen(str) - 5);
-    }
-    for (i = 0; i < nvalues && str; i++) {
-      if (strcmp(str, names[i]) == 0) {
-        ASTNode_free(index);
-        index = ASTNode_createIndexName();
-        ASTNode_setName(index, str);
-        ASTNode_setIndex(index, (unsigned int)i);
-        found++;
-        break;
-      } else if (short_str && strcmp(short_str, names[i]) == 0) {
-        ASTNode_free(index);
-        index = ASTNode_createIndexName();
-        ASTNode_setName(index, short_str);
-        ASTNode_setIndex(index, (unsigned int)i);
-        ASTNode_setData(index);
-        found++;
-        break;
-      }
-    }
-    if (!found) ASTNode_setName(index, str);
-    free(short_str);
-    ASTNode_setType(index, ASTNode_getType(f));     /* keeps AST_NAME_TIME */
-  } else {
-    ASTNode_setType(index, ASTNode_getType(f));
-    if (ASTNode_getType(f) == AST_FUNCTION) ASTNode_setName(index, ASTNode_getName(f)), ASTNode_setType(index, AST_FUNCTION);
-    for (k = 0; k < ASTNode_getNumChildren(f); k++)
-      ASTNode_addChild(index, indexAST(ASTNode_getChild(f, k), nvalues, names));
+  ASTNode_t *n; unsigned int k;
+  if (ASTNode_isName(f)) return indexed_symbol(f, nvalues, names);
+  n = ASTNode_create();
+  if (ASTNode_isInteger(f)) ASTNode_setInteger(n, ASTNode_getInteger(f));
+  else if (ASTNode_isReal(f)) ASTNode_setReal(n, ASTNode_getReal(f));
+  else {
+    if (ASTNode_getType(f) == AST_FUNCTION) ASTNode_setName(n, ASTNode_getName(f));
+    ASTNode_setType(n, ASTNode_getType(f));
+    for (k = 0; k < ASTNode_getNumChildren(f); k++) ASTNode_addChild(n, indexAST(ASTNode_getChild(f, k), nvalues, names));
   }
-  return index;
+  return n;
 }
 
 int ASTNode_getIndices(const ASTNode_t *node, List_t *indices)

@@ -85,6 +85,28 @@ const char *TimeCourse_getName(const timeCourse_t *tc) { return tc->name; }
 int TimeCourse_getNumValues(const timeCourse_t *tc) { return tc->timepoints; }
 double TimeCourse_getValue(const timeCourse_t *tc, int i) { return tc->values[i]; }
 double TimeCourse_getSensitivity(const timeCourse_t *tc, int i, int j) { return tc->sensitivity ? tc->sensitivity[i][j] : 0.0; }
+/* reference sbmlResults.h:134 declares Model_setValues without defining it; the natural reading next to
+   Model_odeSolver: carry the end state of a run back into the SBML model (species keep the quantity they were set in) */
+Model_t *Model_setValues(Model_t *m, SBMLResults_t *r)
+{
+  int k;
+  if (!m || !r) return m;
+  for (k = 0; r->species && k < r->species->num_val; k++) {
+    const timeCourse_t *tc = r->species->tc[k]; Species_t *sp = Model_getSpeciesById(m, tc->name);
+    if (!sp || tc->timepoints < 1) continue;
+    if (sp->isSetInitialAmount && !sp->isSetInitialConcentration) sp->initialAmount = tc->values[tc->timepoints - 1];
+    else { sp->initialConcentration = tc->values[tc->timepoints - 1]; sp->isSetInitialConcentration = 1; }
+  }
+  for (k = 0; r->compartments && k < r->compartments->num_val; k++) {
+    const timeCourse_t *tc = r->compartments->tc[k]; Compartment_t *c = Model_getCompartmentById(m, tc->name);
+    if (c && tc->timepoints > 0) { c->size = tc->values[tc->timepoints - 1]; c->isSetSize = 1; }
+  }
+  for (k = 0; r->parameters && k < r->parameters->num_val; k++) {
+    const timeCourse_t *tc = r->parameters->tc[k]; Parameter_t *p = Model_getParameterById(m, tc->name);
+    if (p && tc->timepoints > 0) Parameter_setValue(p, tc->values[tc->timepoints - 1]);
+  }
+  return m;
+}
 void SBMLResults_dumpSpecies(const SBMLResults_t *r) { printf("## Printing Species time courses\n"); TimeCourseArray_dump(r->species, r->time); }
 void SBMLResults_dumpCompartments(const SBMLResults_t *r) { printf("## Printing Variable Compartment time courses\n"); TimeCourseArray_dump(r->compartments, r->time); }
 void SBMLResults_dumpParameters(const SBMLResults_t *r) { printf("## Printing Variable Parameter time courses\n"); TimeCourseArray_dump(r->parameters, r->time); }

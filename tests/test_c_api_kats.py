@@ -50,3 +50,21 @@ def test_sensitivity_unit_tests_in_c(tmp_path):
     exe = _build(tmp_path, "test_sens_kats")
     r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+def test_boundary_kats_in_c_host_part(tmp_path):
+    """sizeof / offsets of struct cvodeSettings, DetectNegState refused, the callback-seam exports, determinantNAST,
+    Model_setValues (tests/c/test_boundary_kats.c); without a device the getters fail loudly."""
+    exe = _build(tmp_path, "test_boundary_kats")
+    import sbml_odesolver_b200 as so
+    args = [str(exe), H.model_path("mapk_cascade.xml")] + (["cpu"] if so.lib().ODES_deviceCount() == 0 else [])
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+@pytest.mark.gpu
+def test_boundary_kats_in_c(tmp_path):
+    """... and with a device: the seam getters return the cached kernel handle without compiling or loading again."""
+    exe = _build(tmp_path, "test_boundary_kats")
+    r = subprocess.run([str(exe), H.model_path("mapk_cascade.xml")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr

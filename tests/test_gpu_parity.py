@@ -372,6 +372,29 @@ def test_steady_state_halt_on_gpu(monkeypatch, warp):
     assert np.array_equal(out, want, equal_nan=True)
 
 
+def test_single_instance_steady_state_matches_the_batch():
+    """IntegratorInstance_integrate with HaltOnSteadyState on a model with NEGATIVE rates (huang96): the host's
+    IntegratorInstance_checkSteadyState (src/integratorInstance.c:1442-1507: signed rates against the mean of the |rates|)
+    must stop at the output time at which the device's steady_f and the oracle stop -- a test on |rate| - mean would stop
+    earlier."""
+    L = so.lib()
+    w = H.workload("huang", nout=40)
+    m = w["model"]
+    opt = so.settings(400.0, 40, 1e-9, 1e-6, steady_state=1, ss_threshold=1e-5)
+    vals = w["nominal"][None, :].copy()
+    ref = H.oracle_run(m, opt, w["vary"], vals, 40, compiled_so=H.compile_c_model(m, "huang"), backend=H.gpu_tier_backend())
+    rows = np.where(~np.isnan(ref["out"][0, :, 0]))[0]
+    assert 0 < rows[-1] < 40, "the nominal huang96 run must settle inside the grid for this test"
+    t_halt = H.tpoints(opt, 40)[rows[-1]]
+    ii = L.IntegratorInstance_create(m.om, opt)
+    assert ii
+    L.IntegratorInstance_integrate(ii)
+    assert L.IntegratorInstance_getTime(ii) == t_halt, (L.IntegratorInstance_getTime(ii), t_halt)
+    assert "120501" in so.errors() and "Steady state found" in so.errors()     # SOLVER_MESSAGE_STEADYSTATE_FOUND
+    L.SolverError_clear()
+    L.IntegratorInstance_free(ii)
+
+
 def test_all_devices_entry_matches_one_device():
     """ODESBatch_runHostAllDevices: the batch split by index range over every GPU of the box (one plan + one host thread
     per device, no collective) returns what one device returns, bit for bit.  On a one-GPU box it degenerates to one range."""
