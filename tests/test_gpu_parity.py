@@ -395,13 +395,15 @@ def test_single_instance_steady_state_matches_the_batch():
     L.IntegratorInstance_free(ii)
 
 
-def test_all_devices_entry_matches_one_device():
+@pytest.mark.parametrize("name,n,nout", [("mapk", 6000, 10), ("huang", 640, 20), ("goodwin", 2000, 20)])
+def test_all_devices_entry_matches_one_device(name, n, nout):
     """ODESBatch_runHostAllDevices: the batch split by index range over every GPU of the box (one plan + one host thread
-    per device, no collective) returns what one device returns, bit for bit.  On a one-GPU box it degenerates to one range."""
+    per device, no collective) returns what one device returns, bit for bit -- lane layout (MAPK, Goodwin) and the
+    warp-per-trajectory layout (huang96, BASELINE configs[4] "at 2/4/8 GPUs") -- and what the reference's CVODE returns.
+    On a one-GPU box it degenerates to one range."""
     L = so.lib()
-    w = H.workload("mapk", nout=10)
+    w = H.workload(name, nout=nout)
     m = w["model"]
-    n = 6000
     vals = np.ascontiguousarray(H.workload_values(w, n, seed=21))
     vary = np.asarray(w["vary"], dtype=np.int32)
     store = np.arange(m.neq, dtype=np.int32)
@@ -410,9 +412,12 @@ def test_all_devices_entry_matches_one_device():
     b.integrate(n)
     direct = np.transpose(b.results(n), (2, 0, 1)).copy()
     b.close()
+    ns = min(n, 512)
+    ref = _oracle(w, vals[:ns])
+    assert np.array_equal(direct[:ns], ref["out"][:, :, :m.neq], equal_nan=True)
     ndev = L.ODES_deviceCount()
     for want in sorted({1, min(2, ndev), ndev}):
-        res = np.full((n, 11, m.neq), -1.0)
+        res = np.full((n, nout + 1, m.neq), -1.0)
         st = np.full(n, -1, dtype=np.int32)
         used = L.ODESBatch_runHostAllDevices(m.om, w["opt"], len(vary), vary.ctypes.data, len(store), store.ctypes.data, n,
                                              vals.ctypes.data, res.ctypes.data, st.ctypes.data, want)
