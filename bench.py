@@ -136,6 +136,135 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def cpu_model_name():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
+def status_histogram(st):
+    """failed trajectories by CVODE flag"""
+    vals, cnt = np.unique(np.asarray(st)[np.asarray(st) != 0], return_counts=True)
+    return {str(int(v)): int(c) for v, c in zip(vals, cnt)}
+
+
+def flops_for(b, m, stats_mean):
+    Ff, FJ = count_ops(b.source())
+    return algorithmic_flops(m.neq, Ff, FJ, stats_mean), Ff, FJ
+
+
+def other_config_line(H, so, name, n, fp64_peak, cores, device):
+    """One parity-test configuration of BASELINE.json (configs[2..4]) at n sets: device-resident trajectories/s, roofline
+    fraction with the oracle's work counters, and the parity of a sample against the reference's vendored CVODE."""
+    w = H.workload(name)
+    m = w["model"]
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)), device=device)
+    vals = H.workload_values(w, n, seed=77)
+    b.set_values(vals)
+    b.integrate(n)
+    ms = min(b.integrate(n) for _ in range(2))
+    st = b.status(n)
+    stats = b.stats(n)
+    ns = min(n, 256 if name == "huang" else 512)
+    backend = H.REF if H.have_ref() else H.PORT
+    cso = H.compile_c_model(m, name)
+    t0 = time.perf_counter()
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals[:ns], w["nout"], backend=backend, threads=cores, compiled_so=cso)
+    dt = time.perf_counter() - t0
+    gpu = b.results(ns)
+    rep = H.parity_report(gpu, np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), stats[:, :ns].T, ref["stats"], w["rtol"], w["atol"])
+    fired_same = bool(np.array_equal(b.event_log(ns).T, ref["fired"])) if name == "events" else None
+    omean = dict(zip("nst nfe nsetups nje nni ncfn netf".split(), [float(x) for x in ref["stats"].mean(axis=0)]))
+    F, Ff, FJ = flops_for(b, m, omean)
+    achieved = F * n / (ms * 1e-3) / 1e12
+    info = b.kernel_info()
+    line = {"workload": name, "baseline_config": {"repressilator": "configs[2]", "events": "configs[3]", "huang": "configs[4]", "goodwin": "configs[4]"}[name],
+            "sets": n, "neq": m.neq, "output_points": w["nout"], "t_end": w["end"], "value": n / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms,
+            "failed_sets": int((st != 0).sum()), "layout": "warp per trajectory" if "-DODES_WARP=1" in b.source().split("\n")[0] else "trajectory per lane", "kernel_info": info,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "flop_per_trajectory": F},
+            "oracle_mean_stats": omean,
+            "parity_on_sample": {"sets": ns, "checker": "vendored CVODE 2.3.0 (oracle/_ref)" if backend == H.REF else "restated port", "bit_identical": bool(np.array_equal(gpu, np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), equal_nan=True)),
+                                 "frac_within_10rtol": rep["frac_within"], "frac_same_step_sequence": rep["frac_same_path"], "max_ratio": rep["max_ratio"], "event_firing_order_identical": fired_same},
+            "cpu_traj_per_s": ns / dt, "cpu_cores": cores}
+    b.close()
+    return line
+
+
+def entry_leg(H, so, L, w, n, steps):
+    """The reference-shaped one-shot entry: IntegratorInstance_integrateBatch with the caller's malloc'd (pageable) arrays and
+    ALL model values per row (what the reference's batch loop stores per design point, src/odeSolver.c:313-330)."""
+    import ctypes as C
+    m = w["model"]
+    nv, nrows = len(w["vary"]), w["nout"] + 1
+    ii = L.IntegratorInstance_create(m.om, w["opt"])
+    vis = (C.c_void_p * nv)(*[L.ODEModel_getVariableIndexByNum(m.om, i) for i in w["vary"]])
+    vals = np.ascontiguousarray(philox_sets(w["nominal"], 0, n))
+    out = np.zeros((n, nrows, m.nvalues))                       # malloc'd, pageable; touched
+    st = np.zeros(n, dtype=np.int32)
+    call = lambda: L.IntegratorInstance_integrateBatch(ii, n, nv, vis, vals.ctypes.data, out.ctypes.data, st.ctypes.data)
+    t0 = time.perf_counter(); failed0 = call(); first_s = time.perf_counter() - t0       # builds and caches the plan, buffers, ring
+    c1 = so.counters()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        failed = call()
+    dt = (time.perf_counter() - t0) / steps
+    c2 = so.counters()
+    assert failed0 == 0 and failed == 0, (failed0, failed)
+    reuse = {k: c2[k] - c1[k] for k in ("nvrtc_compiles", "cubin_cache_loads", "module_loads", "device_allocations", "plans_created", "plan_cache_hits", "kernel_launches")}
+    # the same shape through ODESBatch_runHost with pinned buffers, for the comparison
+    b = so.Batch(m, w["opt"], w["vary"], device=0)
+    rows = b.nrows * b.nstore
+    hv, hr, hs = L.ODES_hostAlloc(n * nv * 8), L.ODES_hostAlloc(rows * n * 8), L.ODES_hostAlloc(n * 4)
+    pv = np.ctypeslib.as_array(C.cast(hv, C.POINTER(C.c_double)), shape=(n, nv)); pv[:] = vals
+    pr = np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_double)), shape=(n, b.nrows, b.nstore))
+    ps = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_int)), shape=(n,))
+    b.run_host(pv, pr, ps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        b.run_host(pv, pr, ps)
+    dt_pinned = (time.perf_counter() - t0) / steps
+    same = bool(np.array_equal(pr, out, equal_nan=True))
+    L.ODES_hostFree(hv); L.ODES_hostFree(hr); L.ODES_hostFree(hs)
+    b.close()
+    L.IntegratorInstance_free(ii)
+    d2h = n * nrows * m.nvalues * 8 + n * 4
+    return {"entry": "IntegratorInstance_integrateBatch", "value": n / dt, "unit": UNIT, "sets": n, "values_per_row": m.nvalues, "ms_per_call": 1e3 * dt,
+            "first_call_s": first_s, "h2d_bytes_per_call": n * nv * 8, "d2h_bytes_per_call": d2h, "d2h_gbs": d2h / dt / 1e9,
+            "host_arrays": "malloc'd (pageable), staged through the plan's pinned ring", "second_call_work": reuse,
+            "runhost_pinned_same_shape": {"value": n / dt_pinned, "ms_per_call": 1e3 * dt_pinned, "d2h_gbs": d2h / dt_pinned / 1e9},
+            "ratio_to_runhost_pinned": dt_pinned / dt, "identical_to_runhost": same,
+            "bound": "device-to-host copy of %d values per row: %.1f GB per call" % (m.nvalues, d2h / 1e9)}
+
+
+def fmad_variant(H, so, L, w, n, fp64_peak, device, cores):
+    """NOT the headline: the same kernel compiled with --fmad=true (ODES_FMAD=1).  Contraction into fused multiply-adds
+    changes the last bits, so trajectories follow the tolerance gate instead of the reference's exact steps -- the
+    difference to the headline value is the price of bit-exactness."""
+    m = w["model"]
+    os.environ["ODES_FMAD"] = "1"
+    try:
+        b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)), device=device)
+        b.reserve(n)
+        nv = len(w["vary"])
+        b.generate_values(n, SEED, 0, w["nominal"], w["span"][0] * np.ones(nv), w["span"][1] * np.ones(nv), log10=w["log10"])
+        b.integrate(n)
+        ms = min(b.integrate(n) for _ in range(2))
+        ns = 4096
+        vals = b.get_values(ns)
+        ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if H.have_ref() else H.PORT, threads=cores, compiled_so=H.compile_c_model(m, "mapk"))
+        rep = H.parity_report(b.results(ns), np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), b.stats(ns).T, ref["stats"], w["rtol"], w["atol"])
+        out = {"value": n / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "build": "--fmad=true (ODES_FMAD=1)", "headline": False,
+               "parity_on_sample": {"sets": ns, "frac_within_10rtol": rep["frac_within"], "frac_same_step_sequence": rep["frac_same_path"], "max_ratio": rep["max_ratio"]}}
+        b.close()
+        return out
+    finally:
+        os.environ.pop("ODES_FMAD", None)
+
+
 def reference_arm(args, rank):
     """The reference's CPU implementation of the path (vendored CVODE 2.3.0 via oracle/_ref when it was built in the
     container, else the restated port) with all host threads, on bounded samples of the same seeded workload."""
@@ -184,6 +313,8 @@ def main():
     ap.add_argument("--cpu-sets", type=int, default=0, help="sample size of the cpu_baseline leg (default: scaled to the core count)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block (BASELINE configs[2..4] at 10^5 sets), the e2e_entry leg and the FMA variant")
+    ap.add_argument("--entry-sets", type=int, default=200_000, help="sets of the e2e_entry leg (IntegratorInstance_integrateBatch, all model values, malloc'd arrays)")
     ap.add_argument("--sens", default="", help="forward sensitivities (SURVEY 8f rank 4): comma-separated ids, or 'all' for every constant; "
                                                "not the headline -- a line for profiles/ with the vendored CVODES timed beside it")
     args = ap.parse_args()
@@ -321,21 +452,42 @@ def main():
             sens_same = bool(np.array_equal(b.sensitivities(ns), ref["sens"], equal_nan=True))
         else:
             cso = H.compile_c_model(m, args.workload)
+            dts = []
+            for _ in range(3):                                     # best of 3
+                t0 = time.perf_counter()
+                ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
+                dts.append(time.perf_counter() - t0)
+            dt = min(dts)
+            n1 = max(256, ns // (4 * cores))                       # the single-core figure
             t0 = time.perf_counter()
-            ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=cores, compiled_so=cso)
-            dt = time.perf_counter() - t0
+            H.oracle_run(m, w["opt"], w["vary"], vals[:n1], w["nout"], backend=H.REF if kind == "reference" else H.PORT, threads=1, compiled_so=cso)
+            single_core = n1 / (time.perf_counter() - t0)
             sens_same = None
         gpu = b.results(ns)
         rep = H.parity_report(gpu, np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0)), stats[:, :ns].T, ref["stats"], w["rtol"], w["atol"])
         cpu = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"first {ns} sets of this step's batch, {cores} threads, vendored {'CVODES 2.3.0 + emitted C rhs/Jacobian/sense_f' if b.nsens else 'CVODE 2.3.0 + emitted C rhs/Jacobian'}, gcc -O2 -ffp-contract=off",
+               "cpu_model": cpu_model_name(), "timing": "best of 3, wall clock around the integration loop" if not b.nsens else "one run",
+               "single_core": None if b.nsens else {"value": single_core, "unit": UNIT, "sets": n1},
+               "failed_by_flag": status_histogram(ref["status"]),
                "sensitivities_bit_identical_on_sample": sens_same,
                "parity_on_sample": {"frac_within_10rtol": rep["frac_within"], "frac_same_step_sequence": rep["frac_same_path"], "max_ratio": rep["max_ratio"]},
                "oracle_mean_stats": dict(zip("nst nfe nsetups nje nni ncfn netf".split(), [float(x) for x in ref["stats"].mean(axis=0)]))}
 
+    extra = {}
+    if args.workload == "mapk" and not b.nsens and not args.no_other:
+        if rank == 0 and world == 1:
+            cores = os.cpu_count() or 1
+            if not args.no_e2e:
+                extra["e2e_entry"] = entry_leg(H, so, L, w, args.entry_sets, max(1, min(args.steps, 3)))
+            extra["other_configs"] = [other_config_line(H, so, nm, 100_000, fp64_peak, cores, local) for nm in ("repressilator", "events", "huang", "goodwin")]
+            extra["fmad_variant"] = fmad_variant(H, so, L, w, n, fp64_peak, local, cores)
+    barrier()
     if rank == 0:
         Ff, FJ = count_ops(b.source())
-        F = algorithmic_flops(m.neq, Ff, FJ, mean_stats)
+        # the work counters of the ORACLE (the reference's CVODE on the CPU sample) where that leg ran, else the device's
+        flop_stats = cpu["oracle_mean_stats"] if cpu else mean_stats
+        F = algorithmic_flops(m.neq, Ff, FJ, flop_stats)
         if b.nsens:
             # the simultaneous corrector adds, per right-hand-side evaluation, one Jacobian and per sensitivity a sparse
             # matrix-vector product (2 nnz; the parametric term is neglected), per Newton iteration one more solve per
@@ -344,12 +496,14 @@ def main():
             F += mean_stats["nfe"] * (FJ + nS * 2 * nnz) + mean_stats["nni"] * nS * (2 * nn * nn + 6 * nn) + mean_stats["nst"] * nS * nn * (qb * (qb + 1) / 2 + 2 * (qb + 1) + 10)
         achieved = F * n / (kernel_ms * 1e-3) / 1e12
         out_bytes = 8 * b.nrows * b.nstore + 8 * nv + 8 * b.nrows * b.nsens * m.neq
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")
-        if os.path.exists(prof) and args.workload == "mapk" and not b.nsens:
-            pj = json.load(open(prof))
-            if pj.get("sets") and pj.get("dram_bytes") is not None:
-                traffic = pj["dram_bytes"] / pj["sets"] * n        # per launch of this size, scaled from the capture
+        traffic, traffic_src = None, None
+        for prof_name in ("r02_ncu_metrics.json", "r01_ncu_metrics.json"):        # one ncu --set full capture of this kernel (profiles/)
+            prof = os.path.join(ROOT, "profiles", prof_name)
+            if traffic is None and os.path.exists(prof) and args.workload == "mapk" and not b.nsens:
+                pj = json.load(open(prof))
+                if pj.get("sets") and pj.get("dram_bytes") is not None:
+                    traffic = pj["dram_bytes"] / pj["sets"] * n    # per launch; measured at this size when the capture's sets == n
+                    traffic_src = f"profiles/{prof_name}: dram__bytes_read.sum + dram__bytes_write.sum of one launch of {pj['sets']} sets" + ("" if pj["sets"] == n else f", scaled to {n}")
         info = b.kernel_info()
         workload_text = ("MAPK.xml parameter scan (BASELINE configs[1]): 21 kinetic constants x 2^U(-1,1), rtol 1e-6 atol 1e-9, t=0..1000, 100 output points, 8 species stored"
                          if args.workload == "mapk" and not b.nsens else
@@ -363,12 +517,24 @@ def main():
                            "l2": f"per step {1e-9 * n * (8 * b.nrows * b.nstore + 8 * nv):.1f} GB of outputs + inputs, far larger than the 126 MB L2; no explicit flush"},
                 "failed_sets": failed, "mean_stats": mean_stats, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                             "traffic": traffic, "peak_source": "measured live: ODES_measureFP64Peak (FMA chain micro-benchmark); MEASURED_PEAKS.json holds no FP64 figure",
+                             "traffic": traffic, "traffic_source": traffic_src, "flop_counters": "oracle (reference CVODE on the CPU sample)" if cpu else "device", "peak_source": "measured live: ODES_measureFP64Peak (FMA chain micro-benchmark); MEASURED_PEAKS.json holds no FP64 figure",
                              "flop_per_trajectory": F, "flop_model": {"F_f": Ff, "F_J": FJ, "qbar": 4.0, "formula": "SURVEY 8(d)"},
                              "kernel": "odes_bdf_kernel", "kernel_ms": kernel_ms, "kernel_info": info,
                              "hbm_view": {"algorithmic_bytes_per_trajectory": out_bytes, "achieved_gbs": out_bytes * n / (kernel_ms * 1e-3) / 1e9,
                                           "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}},
                 "cpu_baseline": cpu}
+        line.update(extra)
+        ceil = os.path.join(ROOT, "profiles", "r02_d2h_ceiling.json")
+        if e2e and os.path.exists(ceil):
+            # what the host of this pool's boxes absorbs (plain pinned cudaMemcpyAsync, tools/micro/d2h_ceiling.cu)
+            cj = {r["gpus"]: r["aggregate_gbs"] for r in json.load(open(ceil))["runs"] if r["direction"] == "d2h" and r["shape"] == "106MB groups"}
+            if world in cj:
+                got = world * e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+                e2e["d2h_gbs"] = got
+                e2e["bound"] = f"host D2H {got:.1f} GB/s of {cj[world]:.1f} GB/s ceiling at {world} GPU(s) (profiles/r02_d2h_ceiling.json)" if got > 0.85 * cj[world] else f"kernel (D2H {got:.1f} GB/s of {cj[world]:.1f} GB/s ceiling)"
+        rec = os.path.join(ROOT, "profiles", "MEASURED_FP64_PEAK.json")
+        if os.path.exists(rec):
+            line["roofline"]["peak_recorded"] = json.load(open(rec))
         print(json.dumps(line), flush=True)
     b.close()
     if dist is not None:

@@ -132,6 +132,7 @@ static std::string cache_dir(void)
    entries keep their plans and device buffers on the odeModel_t, so a second call with the same model, settings
    and varied set must not move any of the first four. */
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 enum { CNT_NVRTC = 0, CNT_CUBIN_LOAD, CNT_MODULE_LOAD, CNT_DEVICE_ALLOC, CNT_PLAN_CREATE, CNT_PLAN_HIT, CNT_LAUNCH, CNT_HOST_REGISTER, CNT_NUM };
 static std::atomic<long long> g_counters[CNT_NUM];
@@ -329,6 +330,8 @@ struct odesBatch {
   int sensFromRow0;                               /* initial sensitivities supplied by the host (single-instance restarts) */
   int nflux; CUfunction fluxKernel; double *d_flux; size_t fluxCap; float lastFluxMs; cudaEvent_t f0, f1;   /* reaction fluxes of the stored rows: [capacity][nout+1][nflux] */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
+  /* pinned staging ring for results that go to PAGEABLE caller memory (the reference-shaped entries hand in malloc'd arrays) */
+  char *stage; size_t stageSlotBytes; int stageSlots; cudaEvent_t stageEv[8];
 };
 
 /* values after CvodeData_initialize with the model's own parameters (uniform for the whole batch) */
@@ -354,6 +357,8 @@ extern "C" void ODESBatch_free(odesBatch_t *b)
     cudaFree(b->d_vary); cudaFree(b->d_out); cudaFree(b->d_tpoints); cudaFree(b->d_rows);
     cudaFree(b->d_status); cudaFree(b->d_stats); cudaFree(b->d_fired); cudaFree(b->d_counter); cudaFree(b->d_scratch); cudaFree(b->d_groupDone); if (b->h_flags) cudaFreeHost(b->h_flags);
     cudaFree(b->d_sens); cudaFree(b->d_flux);
+    if (b->stage) cudaFreeHost(b->stage);
+    for (int i = 0; i < 8; i++) if (b->stageEv[i]) cudaEventDestroy(b->stageEv[i]);
     if (b->f0) cudaEventDestroy(b->f0);
     if (b->f1) cudaEventDestroy(b->f1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -895,6 +900,74 @@ static int run_host_chunked(odesBatch_t *b, int nsets, const double *values, dou
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return 1;
 }
+/* Results for PAGEABLE caller memory.  A device-to-host copy into pageable memory runs at 17 GB/s on this pool's boxes and
+   pinning the caller's array in place costs more than it saves (cudaHostRegister 4.6 GB/s), while copies into pinned memory
+   run at 54 GB/s and eight host threads move pinned blocks into pageable memory at 43 GB/s (tools/micro/d2h_ceiling.cu,
+   profiles/r02_d2h_ceiling.json).  So finished groups are copied into a small pinned ring the plan owns and a few host
+   threads move each block to its place in the caller's array while the next blocks are in flight. */
+struct StagePiece { size_t s0, cnt; int slot; };
+struct Stager {
+  odesBatch_t *b; double *dst; size_t rows, slotSets; int R;
+  std::vector<StagePiece> pieces; size_t taken; bool closed;
+  std::mutex mu; std::condition_variable cv;
+  std::vector<std::atomic<long long>> slotDone;       /* index of the last piece consumed from a slot */
+  std::vector<std::thread> workers;
+  std::atomic<int> failed;
+  Stager(odesBatch_t *b_, double *dst_, size_t rows_, int nthreads)
+    : b(b_), dst(dst_), rows(rows_), slotSets(b_->stageSlotBytes / (rows_ * sizeof(double))), R(b_->stageSlots), taken(0), closed(false), slotDone((size_t)b_->stageSlots), failed(0)
+  {
+    for (int i = 0; i < R; i++) slotDone[(size_t)i].store(-1);
+    for (int t = 0; t < nthreads; t++) workers.emplace_back([this]() { run(); });
+  }
+  void run()
+  {
+    cudaSetDevice(b->device);
+    for (;;) {
+      StagePiece pc; long long index;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this]() { return taken < pieces.size() || closed; });
+        if (taken >= pieces.size()) return;
+        index = (long long)taken; pc = pieces[taken++];
+      }
+      if (cudaEventSynchronize(b->stageEv[pc.slot]) != cudaSuccess) { cudaGetLastError(); failed.store(1); }
+      memcpy(dst + pc.s0 * rows, b->stage + (size_t)pc.slot * b->stageSlotBytes, pc.cnt * rows * sizeof(double));
+      slotDone[(size_t)pc.slot].store(index);
+    }
+  }
+  /* main thread: sets [s0, s0 + cnt) have landed in d_out; split into slot-sized pieces and send them through the ring */
+  int emit(size_t s0, size_t cnt)
+  {
+    while (cnt > 0) {
+      const size_t n = cnt < slotSets ? cnt : slotSets;
+      size_t p;
+      { std::lock_guard<std::mutex> lk(mu); p = pieces.size(); }
+      const int slot = (int)(p % (size_t)R);
+      while (p >= (size_t)R && slotDone[(size_t)slot].load() < (long long)(p - (size_t)R)) sched_yield();
+      CUDA_OK(cudaMemcpyAsync(b->stage + (size_t)slot * b->stageSlotBytes, b->d_out + s0 * rows, n * rows * sizeof(double), cudaMemcpyDeviceToHost, b->copyOut));
+      CUDA_OK(cudaEventRecord(b->stageEv[slot], b->copyOut));
+      { std::lock_guard<std::mutex> lk(mu); StagePiece pc; pc.s0 = s0; pc.cnt = n; pc.slot = slot; pieces.push_back(pc); }
+      cv.notify_one();
+      s0 += n; cnt -= n;
+    }
+    return 1;
+  }
+  int finish()
+  {
+    { std::lock_guard<std::mutex> lk(mu); closed = true; }
+    cv.notify_all();
+    for (auto &w : workers) w.join();
+    workers.clear();
+    return failed.load() ? 0 : 1;
+  }
+  ~Stager() { if (!workers.empty()) finish(); }
+};
+static bool is_pageable(const void *p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
 extern "C" int ODESBatch_runHost(odesBatch_t *b, int nsets, const double *values, double *results, int *status, int chunk)
 { return ODESBatch_runHostSens(b, nsets, values, results, NULL, status, chunk); }
 extern "C" int ODESBatch_runHostSens(odesBatch_t *b, int nsets, const double *values, double *results, double *sens, int *status, int chunk)
@@ -913,7 +986,22 @@ extern "C" int ODESBatch_runHostEx(odesBatch_t *b, int nsets, const double *valu
   if (chunk < 0) return run_host_chunked(b, nsets, values, results, status, ((-chunk) + 31) & ~31);
   if (chunk == 0) chunk = 1 << 22;
   chunk = (chunk + 31) & ~31;
-  const int shift = env_int("ODES_GROUP_SHIFT", 14);
+  int shift = env_int("ODES_GROUP_SHIFT", 14);
+  /* pageable destination: stage through the pinned ring, in groups of at most ~64 MB */
+  const bool staged = results && rows > 0 && env_int("ODES_STAGE", 1) != 0 && is_pageable(results);
+  if (staged) {
+    const size_t target = (size_t)env_int("ODES_STAGE_MB", 64) << 20;
+    while (shift > 5 && ((size_t)1 << shift) * rows * sizeof(double) > target) shift--;
+    const size_t slotBytes = ((size_t)1 << shift) * rows * sizeof(double);
+    const int slots = env_int("ODES_STAGE_SLOTS", 8) > 8 ? 8 : (env_int("ODES_STAGE_SLOTS", 8) < 2 ? 2 : env_int("ODES_STAGE_SLOTS", 8));
+    if (!b->stage || b->stageSlotBytes < slotBytes || b->stageSlots != slots) {
+      if (b->stage) { cudaFreeHost(b->stage); b->stage = NULL; }
+      CUDA_OK(cudaHostAlloc((void **)&b->stage, slotBytes * (size_t)slots, cudaHostAllocDefault));
+      g_counters[CNT_DEVICE_ALLOC]++;
+      b->stageSlotBytes = slotBytes; b->stageSlots = slots;
+      for (int i = 0; i < 8; i++) if (!b->stageEv[i]) CUDA_OK(cudaEventCreateWithFlags(&b->stageEv[i], cudaEventDisableTiming));
+    }
+  }
   const int gsize = 1 << shift;
   const int maxGroups = (chunk + gsize - 1) / gsize;
   if (maxGroups > b->groupCap) {
@@ -937,6 +1025,8 @@ extern "C" int ODESBatch_runHostEx(odesBatch_t *b, int nsets, const double *valu
     if (!launch(b, n, off, b->stream, off == 0, shift)) return 0;
     CUDA_OK(cudaEventRecord(b->evK[0], b->stream));
     /* copy finished groups while the kernel runs; consecutive finished groups go out as one copy */
+    Stager *stager = staged ? new Stager(b, results, rows, env_int("ODES_STAGE_THREADS", 8)) : NULL;
+    struct StagerGuard { Stager *s; ~StagerGuard() { delete s; } } stagerGuard = { stager };
     int next = 0;
     while (next < ngroups) {
       const cudaError_t q = cudaEventQuery(b->evK[0]);
@@ -948,7 +1038,8 @@ extern "C" int ODESBatch_runHostEx(odesBatch_t *b, int nsets, const double *valu
       if (upto > next) {
         const size_t s0 = off + (size_t)next * (size_t)gsize;
         const size_t cnt = (size_t)(upto == ngroups ? n : upto * gsize) - (size_t)next * (size_t)gsize;
-        if (results) CUDA_OK(cudaMemcpyAsync(results + s0 * rows, b->d_out + s0 * rows, sizeof(double) * cnt * rows, cudaMemcpyDeviceToHost, b->copyOut));
+        if (stager) { if (!stager->emit(s0, cnt)) return 0; }
+        else if (results) CUDA_OK(cudaMemcpyAsync(results + s0 * rows, b->d_out + s0 * rows, sizeof(double) * cnt * rows, cudaMemcpyDeviceToHost, b->copyOut));
         if (status) CUDA_OK(cudaMemcpyAsync(status + s0, b->d_status + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, b->copyOut));
         if (sens) CUDA_OK(cudaMemcpyAsync(sens + s0 * srows, b->d_sens + s0 * srows, sizeof(double) * cnt * srows, cudaMemcpyDeviceToHost, b->copyOut));
         next = upto;
@@ -962,6 +1053,7 @@ extern "C" int ODESBatch_runHostEx(odesBatch_t *b, int nsets, const double *valu
     }
     CUDA_OK(cudaStreamSynchronize(b->copyOut));
     CUDA_OK(cudaStreamSynchronize(b->stream));
+    if (stager && !stager->finish()) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_CUDA_CALL_FAILED, "staged device-to-host copy failed"); return 0; }
     if (flux) { float ms = 0; if (cudaEventElapsedTime(&ms, b->f0, b->f1) == cudaSuccess) b->lastFluxMs = ms; else cudaGetLastError(); }
   }
   return 1;
