@@ -30,6 +30,7 @@ struct cvodeSolver {
   double *course;      /* [nsteps][nvalues] rows computed ahead by the device */
   int *courseFired;    /* [nsteps] event bitmask per row                       */
   int courseFirst, courseLen, courseStatus, courseFailRow;
+  int courseEvents;    /* the course was computed with (1) or without (0) event processing */
   double *courseSens;  /* [nsteps][nsens][neq] forward sensitivities of the course, or NULL */
   int nsens;
   long nst, nfe, nsetups, nje, nni, ncfn, netf;

@@ -330,6 +330,8 @@ struct odesBatch {
   int sensFromRow0;                               /* initial sensitivities supplied by the host (single-instance restarts) */
   int nflux; CUfunction fluxKernel; double *d_flux; size_t fluxCap; float lastFluxMs; cudaEvent_t f0, f1;   /* reaction fluxes of the stored rows: [capacity][nout+1][nflux] */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
+  int noEvents;                                   /* launches skip the emitted event function (single instance without event processing) */
+  int stepRes;                                    /* cvodeSettings_t.StepResolution: solver / event grid points per print step */
   /* pinned staging ring for results that go to PAGEABLE caller memory (the reference-shaped entries hand in malloc'd arrays) */
   char *stage; size_t stageSlotBytes; int stageSlots; cudaEvent_t stageEv[8];
 };
@@ -432,8 +434,8 @@ static std::string build_source(odesBatch_t *b)
     if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[640];
-    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
@@ -457,8 +459,8 @@ static std::string build_source(odesBatch_t *b)
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   b->maxBlocksPerSM = (la == 2) ? 512 / tmemCols : 32;
   char head[640];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
-           env_int("ODES_FMAD", 0) ? "true" : "false", b->block, b->minblocks, b->matLocal,
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
+           env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->block, b->minblocks, b->matLocal,
            env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
@@ -502,8 +504,13 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
      to has no recoverable right-hand-side failures (its RhsFn returns void), so there is no reference arithmetic to reproduce:
      the switch is refused instead of being ignored */
   if (opt->DetectNegState) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "DetectNegState is not supported by the batched integrator (no recoverable right-hand-side failures); unset it with CvodeSettings_setDetectNegState(set, 0)"); return NULL; }
+  if (opt->StepResolution > 1 && (opt->HaltOnEvent || opt->SteadyState)) {
+    SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "StepResolution > 1 keeps rows at the print steps only: it cannot be combined with HaltOnEvent or HaltOnSteadyState (the halting row may fall between print steps)");
+    return NULL;
+  }
   odesBatch_t *b = new odesBatch();
   b->om = om; b->opt = opt; b->device = device; b->nvary = nvary; b->nout = opt->PrintStep;
+  b->stepRes = opt->StepResolution > 1 ? opt->StepResolution : 1;
   b->nvalues = om->neq + om->nass + om->nconst;
   for (int j = 0; j < nvary; j++) {
     if (varyIndex[j] < 0 || varyIndex[j] >= b->nvalues) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "varied index %d out of range", varyIndex[j]); delete b; return NULL; }
@@ -534,6 +541,18 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
   return b;
 }
 
+/* the grid the kernel is driven over: stepRes equal sub-steps per print step (stepRes == 1: the print grid itself) */
+static int upload_time_grid(odesBatch_t *b, const double *tpoints, int nout)
+{
+  const int k = b->stepRes;
+  std::vector<double> grid((size_t)nout * (size_t)k + 1);
+  for (int i = 0; i < nout; i++)
+    for (int j = 0; j < k; j++) grid[(size_t)i * (size_t)k + (size_t)j] = (j == 0) ? tpoints[i] : tpoints[i] + j * ((tpoints[i + 1] - tpoints[i]) / k);
+  grid[(size_t)nout * (size_t)k] = tpoints[nout];
+  CUDA_OK(cudaMemcpy(b->d_tpoints, grid.data(), sizeof(double) * grid.size(), cudaMemcpyHostToDevice));
+  UPLOAD_FENCE();
+  return 1;
+}
 static int ensure_loaded(odesBatch_t *b)
 {
   if (b->kernel) { CUDA_OK(cudaSetDevice(b->device)); return 1; }
@@ -578,9 +597,8 @@ static int ensure_loaded(odesBatch_t *b)
   }
   if (env_int("ODES_BLOCKS_PER_SM", 0) > 0) b->blocksPerSM = env_int("ODES_BLOCKS_PER_SM", 0);
   if (b->laMode == 1) CUDA_OK(cudaMalloc(&b->d_scratch, sizeof(double) * (size_t)b->laWords * (size_t)b->numSMs * (size_t)b->blocksPerSM * (size_t)b->block));
-  CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * (size_t)(b->opt->PrintStep + 1)));
-  CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
-  UPLOAD_FENCE();
+  CUDA_OK(cudaMalloc(&b->d_tpoints, sizeof(double) * ((size_t)b->opt->PrintStep * (size_t)b->stepRes + 1)));
+  if (!upload_time_grid(b, b->opt->TimePoints, b->nout)) return 0;
   return 1;
 }
 
@@ -606,8 +624,7 @@ extern "C" int ODESBatch_setTimeGrid(odesBatch_t *b, int nout, const double *tpo
 {
   if (!ensure_loaded(b)) return 0;
   if (nout > b->opt->PrintStep || nout < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "time grid longer than the plan's"); return 0; }
-  CUDA_OK(cudaMemcpy(b->d_tpoints, tpoints, sizeof(double) * (size_t)(nout + 1), cudaMemcpyHostToDevice));
-  UPLOAD_FENCE();
+  if (!upload_time_grid(b, tpoints, nout)) return 0;
   b->nout = nout;
   return 1;
 }
@@ -648,12 +665,13 @@ extern "C" int ODESBatch_getSensitivities(odesBatch_t *b, int nsets, double *sen
   if (b->nsens <= 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "the plan was created without sensitivity analysis"); return 0; }
   if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
   CUDA_OK(cudaSetDevice(b->device));
-  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nsens * (size_t)b->om->neq;
+  const size_t per = (size_t)(b->nout + 1) * (size_t)b->nsens * (size_t)b->om->neq;      /* dense pitch of the current grid, like the kernels */
   CUDA_OK(cudaMemcpyAsync(sens, b->d_sens, sizeof(double) * per * (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return 1;
 }
 extern "C" int ODESBatch_getNflux(const odesBatch_t *b) { return b->nflux; }
+extern "C" void ODESBatch_setEventProcessing(odesBatch_t *b, int on) { if (b) b->noEvents = on ? 0 : 1; }
 extern "C" double *ODESBatch_deviceFluxes(odesBatch_t *b) { return b->d_flux; }
 extern "C" float ODESBatch_getLastFluxMs(const odesBatch_t *b) { return b->lastFluxMs; }
 /* fluxes of the sets [offset, offset + nsets) of the device-resident results, on `stream` */
@@ -666,7 +684,7 @@ static int launch_fluxes(odesBatch_t *b, int nsets, size_t offset, cudaStream_t 
     if (!b->fluxKernel) return 0;
     CUDA_OK(cudaEventCreate(&b->f0)); CUDA_OK(cudaEventCreate(&b->f1));
   }
-  const size_t rowsPerSet = (size_t)(b->opt->PrintStep + 1);
+  const size_t rowsPerSet = (size_t)(b->nout + 1);
   const size_t need = (size_t)b->capacity * rowsPerSet * (size_t)b->nflux;
   if (need > b->fluxCap) { cudaFree(b->d_flux); b->d_flux = NULL; b->fluxCap = 0; CUDA_OK(cudaMalloc(&b->d_flux, need * sizeof(double))); b->fluxCap = need; }
   if (nsets == 0) return 1;
@@ -699,7 +717,7 @@ extern "C" int ODESBatch_getFluxes(odesBatch_t *b, int nsets, double *flux)
   if (b->nflux <= 0 || !b->d_flux) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "no fluxes have been computed on this plan"); return 0; }
   if (nsets > b->capacity || nsets < 0) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
   CUDA_OK(cudaSetDevice(b->device));
-  CUDA_OK(cudaMemcpyAsync(flux, b->d_flux, sizeof(double) * (size_t)nsets * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nflux, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaMemcpyAsync(flux, b->d_flux, sizeof(double) * (size_t)nsets * (size_t)(b->nout + 1) * (size_t)b->nflux, cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   { float ms = 0; if (b->f0 && cudaEventElapsedTime(&ms, b->f0, b->f1) == cudaSuccess) b->lastFluxMs = ms; else cudaGetLastError(); }
   return 1;
@@ -776,12 +794,12 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   OdesArgs a;
   a.groupDone = NULL; a.hostFlags = NULL; a.groupShift = 0; a.pad2 = b->sensFromRow0;
   if (groupShift >= 0) { a.groupDone = b->d_groupDone; a.hostFlags = b->d_flags; a.groupShift = groupShift; }
-  a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
+  a.vary = b->d_vary + offset; a.out = b->d_out + offset * (size_t)(b->nout + 1) * (size_t)b->nstore; a.status = b->d_status + offset; a.stats = b->d_stats + offset;
   a.fired = b->d_fired + offset; a.tpoints = b->d_tpoints;
-  a.sens = b->d_sens ? b->d_sens + offset * (size_t)(b->opt->PrintStep + 1) * (size_t)b->nsens * (size_t)b->om->neq : NULL;
+  a.sens = b->d_sens ? b->d_sens + offset * (size_t)(b->nout + 1) * (size_t)b->nsens * (size_t)b->om->neq : NULL;
   a.counter = b->d_counter + (b->counterSlot++ & 63);
   a.scratch = b->d_scratch;
-  a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout; a.mxstep = b->opt->Mxstep; a.pad = 0;
+  a.stride = (unsigned long long)b->capacity; a.nsets = nsets; a.nout = b->nout * b->stepRes; a.mxstep = b->opt->Mxstep; a.pad = b->noEvents;
   a.reltol = b->opt->RError; a.abstol = b->opt->Error;
   void *params[] = { &a };
   const int perBlock = b->warpMode ? b->block / 32 : b->block;       /* trajectories in flight per block */
@@ -829,27 +847,33 @@ extern "C" float ODESBatch_timerStop(odesBatch_t *b)
   return ms;
 }
 
+/* The trajectories on the device are dense in the CURRENT grid: set s starts at s * (nout + 1) * nstore, also after
+   ODESBatch_setTimeGrid shortened the grid (the kernels, the launch offsets and these getters use the same pitch). */
+static int check_sets(const odesBatch_t *b, int nsets)
+{
+  if (nsets < 0 || nsets > b->capacity) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "nsets %d exceeds reserved capacity %d", nsets, b->capacity); return 0; }
+  return 1;
+}
 extern "C" int ODESBatch_getResults(odesBatch_t *b, int nsets, double *results)
 {
+  if (!check_sets(b, nsets)) return 0;
   CUDA_OK(cudaSetDevice(b->device));
-  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore;
-  if (b->nout == b->opt->PrintStep)
-    CUDA_OK(cudaMemcpyAsync(results, b->d_out, sizeof(double) * per * (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
-  else       /* shortened grid (single-instance restarts): rows [0, nout] of every trajectory */
-    CUDA_OK(cudaMemcpy2DAsync(results, sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, b->d_out, sizeof(double) * per,
-                              sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
+  const size_t per = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  CUDA_OK(cudaMemcpyAsync(results, b->d_out, sizeof(double) * per * (size_t)nsets, cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   return 1;
 }
 extern "C" int ODESBatch_getTrajectory(odesBatch_t *b, int set, double *traj)
 {
+  if (set < 0 || set >= b->capacity) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "set %d outside the reserved capacity %d", set, b->capacity); return 0; }
   CUDA_OK(cudaSetDevice(b->device));
-  const size_t per = (size_t)(b->opt->PrintStep + 1) * (size_t)b->nstore;
-  CUDA_OK(cudaMemcpy(traj, b->d_out + (size_t)set * per, sizeof(double) * (size_t)(b->nout + 1) * (size_t)b->nstore, cudaMemcpyDeviceToHost));
+  const size_t per = (size_t)(b->nout + 1) * (size_t)b->nstore;
+  CUDA_OK(cudaMemcpy(traj, b->d_out + (size_t)set * per, sizeof(double) * per, cudaMemcpyDeviceToHost));
   return 1;
 }
 extern "C" int ODESBatch_getStatus(odesBatch_t *b, int nsets, int *status)
 {
+  if (!check_sets(b, nsets)) return 0;
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaMemcpy(status, b->d_status, sizeof(int) * (size_t)nsets, cudaMemcpyDeviceToHost));
   return 1;
@@ -1117,9 +1141,8 @@ static int refresh_plan(odesBatch_t *b)
   if (b->nvalues > 0) DRV_OK(drv.MemcpyHtoD(sym, b->base.data(), sizeof(double) * (size_t)b->nvalues));
   DRV_OK(drv.ModuleGetGlobal(&sym, &bytes, (CUmodule)b->code->module, "c_trigger0"));
   if (b->om->nevents > 0) DRV_OK(drv.MemcpyHtoD(sym, b->trigger0.data(), sizeof(int) * (size_t)b->om->nevents));
-  CUDA_OK(cudaMemcpy(b->d_tpoints, b->opt->TimePoints, sizeof(double) * (size_t)(b->nout + 1), cudaMemcpyHostToDevice));
   UPLOAD_FENCE();
-  return 1;
+  return upload_time_grid(b, b->opt->TimePoints, b->nout);
 }
 static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvary, const int *varyIndex, int nstore, const int *storeIndex, int device, std::string &src);
 

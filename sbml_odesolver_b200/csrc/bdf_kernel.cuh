@@ -79,6 +79,17 @@
 #ifndef ODES_LOCKSTEP
 #define ODES_LOCKSTEP 0
 #endif
+/* cvodeSettings_t.StepResolution ("number of internal integration steps between output steps ... useful for fine-grained
+   event detection", reference integratorSettings.h:61-63; the reference never reads the field): the grid the solver is
+   driven over -- and on which events are examined, assignments applied and the solver re-initialised, exactly as at the
+   reference's output times -- has ODES_STEPRES points per print step; a.nout counts those, rows are KEPT at the print
+   steps only, and the event mask of a kept row collects the events fired since the row before. */
+#ifndef ODES_STEPRES
+#define ODES_STEPRES 1
+#endif
+#define ODES_ROWS(a) ((size_t)((a).nout / ODES_STEPRES + 1))
+#define ODES_ROW(iout) ((size_t)((iout) / ODES_STEPRES))
+#define ODES_KEEP(iout) (ODES_STEPRES == 1 || (iout) % ODES_STEPRES == 0)
 #ifndef ODES_GESL_UNROLL
 #define ODES_GESL_UNROLL 4            /* measured on MAPK (B200): 8 (full) 4.07 M, 4 4.17 M trajectories/s */
 #endif
@@ -214,7 +225,7 @@ struct OdesArgs {
   unsigned long long *counter; /* next set index to hand out (zeroed before the launch) */
   double *scratch;             /* [ODES_GLOBAL_WORDS][lanes of the grid] (ODES_GLOBAL_LA) */
   unsigned long long stride;
-  int nsets, nout, mxstep, pad;
+  int nsets, nout, mxstep, pad;       /* pad != 0: events are not processed (IntegratorInstance_integrateOneStepWithoutEventProcessing) */
   double reltol, abstol;
   /* completion signalling for the host pipeline (ODESBatch_runHost): sets are handed out in index order, so groups of
      2^groupShift consecutive sets finish roughly in order; the lane that completes a group publishes it to a flag array
@@ -1533,6 +1544,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
   _Pragma("unroll") for (int e = 0; e < NEVENTS; e++) trigger[e] = 0;
   double t = 0.0, tout = 0.0;
   int status = 0, iout = 1, idle = 0;
+  unsigned int firedacc = 0u;             /* events fired since the last kept row (StepResolution) */
   size_t set = 0;
   bool exhausted = false;
   s.st = ST_DONE;
@@ -1545,10 +1557,11 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     /* ---- FINISH + REFILL: close finished trajectories, hand out new set indices ---- */
     if (s.st == ST_FINISH) {
       /* rows never reached (solver failure or halt on event) are marked not-a-number */
-      for (; iout <= a.nout; iout++) {
-        _Pragma("unroll 1") for (int k = 0; k < NSTORE; k++) a.out[(set * (size_t)(a.nout + 1) + (size_t)iout) * NSTORE + k] = __longlong_as_double(0x7ff8000000000000LL);
-        if (a.fired) a.fired[(size_t)iout * stride + set] = 0u;
+      for (size_t r = ODES_ROW(iout + ODES_STEPRES - 1); r < ODES_ROWS(a); r++) {
+        _Pragma("unroll 1") for (int k = 0; k < NSTORE; k++) a.out[(set * ODES_ROWS(a) + r) * NSTORE + k] = __longlong_as_double(0x7ff8000000000000LL);
+        if (a.fired) a.fired[r * stride + set] = 0u;
       }
+      iout = a.nout + 1;
       if (a.status) a.status[set] = status;
       if (a.stats) {
         a.stats[0 * stride + set] = s.c_nst; a.stats[1 * stride + set] = s.c_nfe; a.stats[2 * stride + set] = s.c_nsetups;
@@ -1587,7 +1600,8 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
             FORI yl[i] = 0.0;
             PvRef pv; pv.p = pvl; pv.s = 1u;
             model_init(yl, pv, a.vary, stride, set);
-            store_row0(a.out + set * (size_t)(a.nout + 1) * NSTORE, 1, yl, pv);
+            store_row0(a.out + set * ODES_ROWS(a) * NSTORE, 1, yl, pv);
+            firedacc = 0u;
             if (a.fired) a.fired[set] = 0u;
             /* static assigned values (rules not recomputed before the ODEs) for this trajectory's inputs */
             double atmp[A1(NASS)];
@@ -1699,12 +1713,16 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
         unsigned int firedmask = 0u;
         int restart = 0;
 #if NEVENTS > 0
-        firedmask = event_f(t, yl, pv, trigger, restart);
+        if (!a.pad) firedmask = event_f(t, yl, pv, trigger, restart);          /* a.pad: event processing switched off for this launch */
         if (firedmask) wrote = true;
         if (restart) { FORI YV(i) = yl[i]; }
 #endif
-        store_row(a.out + (set * (size_t)(a.nout + 1) + (size_t)iout) * NSTORE, 1, t, yl, pv);
-        if (a.fired) a.fired[(size_t)iout * stride + set] = firedmask;
+        firedacc |= firedmask;
+        if (ODES_KEEP(iout)) {
+          store_row(a.out + (set * ODES_ROWS(a) + ODES_ROW(iout)) * NSTORE, 1, t, yl, pv);
+          if (a.fired) a.fired[ODES_ROW(iout) * stride + set] = firedacc;
+          firedacc = 0u;
+        }
         iout++;
 #if HALT_ON_EVENT
         if (firedmask) { s.st = ST_FINISH; break; }

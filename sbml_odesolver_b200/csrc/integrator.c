@@ -25,6 +25,9 @@
 /* private plan entry points (batch.cu) */
 int ODESBatch_setTimeGrid(odesBatch_t *, int nout, const double *tpoints);
 int ODESBatch_setInitialTriggers(odesBatch_t *, const int *trigger);
+/* on = 0: launches skip the model's event function (IntegratorInstance_integrateOneStepWithoutEventProcessing,
+   src/integratorInstance.c:843-856) */
+void ODESBatch_setEventProcessing(odesBatch_t *, int on);
 int ODESBatch_setInitialSensitivities(odesBatch_t *, const double *s0);
 
 #define ODES_LOOKAHEAD 256        /* output steps computed ahead by one device run of an indefinite integration */
@@ -41,7 +44,8 @@ static unsigned long plan_signature(const cvodeSettings_t *opt)
 {
   unsigned long h = 1469598103UL; int i; const char *c;
   const long v[] = { opt->PrintStep, opt->Indefinitely, opt->CvodeMethod, opt->IterMethod, opt->MaxOrder, opt->ResetCvodeOnEvent, opt->SetTStop,
-                     opt->Sensitivity, opt->nsens, opt->SensMethod, opt->HaltOnEvent, opt->SteadyState, opt->UseJacobian, opt->sensIDs != NULL };
+                     opt->Sensitivity, opt->nsens, opt->SensMethod, opt->HaltOnEvent, opt->SteadyState, opt->UseJacobian, opt->sensIDs != NULL,
+                     opt->StepResolution > 1 ? opt->StepResolution : 1 };
   for (i = 0; i < (int)(sizeof v / sizeof v[0]); i++) h = (h ^ (unsigned long)v[i]) * 1099511UL;
   for (i = 0; opt->sensIDs && i < opt->nsens; i++) for (c = opt->sensIDs[i]; *c; c++) h = (h ^ (unsigned long)*c) * 1099511UL;
   { double d = opt->ssThreshold + (opt->Indefinitely ? opt->Time : 0.0); unsigned char b[sizeof d]; memcpy(b, &d, sizeof d); for (i = 0; i < (int)sizeof d; i++) h = (h ^ b[i]) * 1099511UL; }
@@ -209,6 +213,9 @@ static int compute_course(integratorInstance_t *engine)
         solver->planOpt->StoreResults = 0;
       }
     }
+    /* the clone is made once; what a launch reads from it follows the caller's settings, which may be changed in place
+       between runs (CvodeSettings_setErrors and a reset: the ParameterScanner pattern) */
+    solver->planOpt->Error = engine->opt->Error; solver->planOpt->RError = engine->opt->RError; solver->planOpt->Mxstep = engine->opt->Mxstep;
     planOpt = solver->planOpt;
   }
   if (!solver->plan) {
@@ -235,6 +242,8 @@ static int compute_course(integratorInstance_t *engine)
     free(s0);
     if (!ok) { free(grid); free(values); free(rows); free(fired); return 0; }
   }
+  ODESBatch_setEventProcessing(solver->plan, engine->processEvents);
+  solver->courseEvents = engine->processEvents;
   if (!ODESBatch_setTimeGrid(solver->plan, nrem, grid) || !ODESBatch_setInitialTriggers(solver->plan, data->trigger) ||
       !ODESBatch_setValues(solver->plan, 1, values) || !ODESBatch_integrate(solver->plan, 1) || !ODESBatch_synchronize(solver->plan) ||
       !ODESBatch_getTrajectory(solver->plan, 0, rows) || !ODESBatch_getStatus(solver->plan, 1, &st) ||
@@ -309,10 +318,17 @@ static const char *cvode_message(int flag)
   }
 }
 
+/* rows the device course did not reach (solver failure, halt) are not-a-number in EVERY value */
+static int row_unreached(const double *row, int n)
+{
+  int i;
+  for (i = 0; i < n; i++) if (!isnan(row[i])) return 0;
+  return n > 0;
+}
 int IntegratorInstance_cvodeOneStep(integratorInstance_t *engine)
 {
   cvodeSolver_t *solver = engine->solver; cvodeData_t *data = engine->data; int i, row;
-  if (!engine->isValid || !solver->course ||
+  if (!engine->isValid || !solver->course || solver->courseEvents != engine->processEvents ||       /* the device course handled events the other way */
       (engine->opt->Indefinitely && solver->iout - solver->courseFirst + 1 > solver->courseLen)) {       /* look-ahead used up */
     solver->t0 = solver->t;
     if (!compute_course(engine)) return 0;
@@ -320,7 +336,7 @@ int IntegratorInstance_cvodeOneStep(integratorInstance_t *engine)
   }
   if (!engine->clockStarted) { engine->startTime = clock(); engine->clockStarted = 1; }
   row = solver->iout - solver->courseFirst + 1;
-  if (row < 1 || row > solver->courseLen || isnan(solver->course[(size_t)row * (size_t)data->nvalues])) {
+  if (row < 1 || row > solver->courseLen || row_unreached(solver->course + (size_t)row * (size_t)data->nvalues, data->nvalues)) {
     int flag = solver->courseStatus ? solver->courseStatus : -2;
     SolverError_error(ERROR_ERROR_TYPE, (errorCode_t)flag, cvode_message(flag), solver->tout, engine->opt->Mxstep);
     SolverError_error(WARNING_ERROR_TYPE, SOLVER_ERROR_INTEGRATION_NOT_SUCCESSFUL, "Integration not successful. Results are not complete.");

@@ -166,26 +166,28 @@ class Emu:
         if not os.path.exists(lib):
             open(cu, "w").write(src)
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + extra + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
+                                  [t for t in src.split("\n")[0].split() if t.startswith("-DODES_STEPRES")] +
                                   ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W") or t.startswith("-DODES_ADAMS") or t.startswith("-DODES_FUNCTIONAL")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
                                    f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
         self.lib = C.CDLL(lib)
         self.batch = batch
 
-    def run(self, base, trig0, values, tpoints, mxstep, rtol, atol):
+    def run(self, base, trig0, values, tpoints, mxstep, rtol, atol, stepres=1):
+        """stepres: the ODES_STEPRES the unit was built with (tpoints is then the refined grid; rows are kept every stepres)"""
         b = self.batch
         values = np.ascontiguousarray(values, dtype=np.float64)
         nsets = values.shape[0]
         nout = len(tpoints) - 1
         vary = np.ascontiguousarray(values.T)                      # SoA [nvary][nsets]
-        raw = np.zeros((nsets, nout + 1, b.nstore))                # the library's [set][row][value] layout
+        raw = np.zeros((nsets, nout // stepres + 1, b.nstore))     # the library's [set][row][value] layout
         out = np.transpose(raw, (1, 2, 0))                         # viewed as [row][value][set]
         status = np.zeros(nsets, dtype=np.int32)
         stats = np.zeros((7, nsets), dtype=np.int32)
-        fired = np.zeros((nout + 1, nsets), dtype=np.uint32)
+        fired = np.zeros((nout // stepres + 1, nsets), dtype=np.uint32)
         base = np.ascontiguousarray(base, dtype=np.float64)
         trig0 = np.ascontiguousarray(trig0, dtype=np.int32)
         tp = np.ascontiguousarray(tpoints, dtype=np.float64)
-        sens = np.zeros((nsets, nout + 1, max(b.nsens, 1), b.model.neq))
+        sens = np.zeros((nsets, nout // stepres + 1, max(b.nsens, 1), b.model.neq))
         self.lib.emu_run(C.c_void_p(base.ctypes.data), C.c_void_p(trig0.ctypes.data), C.c_void_p(vary.ctypes.data), C.c_void_p(raw.ctypes.data),
                          C.c_void_p(status.ctypes.data), C.c_void_p(stats.ctypes.data), C.c_void_p(fired.ctypes.data), C.c_void_p(tp.ctypes.data),
                          C.c_ulonglong(nsets), C.c_int(nsets), C.c_int(nout), C.c_int(mxstep), C.c_double(rtol), C.c_double(atol),

@@ -88,6 +88,38 @@ def test_emulated_events_halt_and_no_reset():
     assert [(e, i) for i in range(101) for e in (0, 1) if fired[i] >> e & 1][:4] == [(1, 7), (0, 24), (1, 25), (1, 34)]
 
 
+@pytest.mark.parametrize("warp", [0, 1])
+def test_emulated_step_resolution(monkeypatch, warp):
+    """StepResolution = k: the kernel walks k sub-steps per print step with the reference's output-time event handling at
+    each and keeps the rows of the print steps -- equal, bit for bit, to rows k, 2k, ... of the oracle run on the refined
+    grid; the event mask of a kept row is the OR of the masks since the row before (tests/test_gpu_parity.py has the GPU twin)."""
+    import ctypes as C
+    monkeypatch.setenv("ODES_WARP", str(warp))
+    k, nout = 4, 25
+    m = so.Model(H.model_path("two_events_one_assignment.xml"))
+    vary = [m.index("S1"), m.index("S2")]
+    vals = np.array([[1.0, 0.0], [1.7, 0.3], [0.6, 0.1], [0.9, 0.25]])
+    opt = so.settings(10.0, nout, 1e-9, 1e-6)
+    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = k            # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    b = so.Batch(m, opt, vary)
+    assert "-DODES_STEPRES=4" in b.source().split("\n")[0]
+    tp = H.tpoints(opt, nout)
+    grid = np.array([tp[i] if j == 0 else tp[i] + j * ((tp[i + 1] - tp[i]) / k) for i in range(nout) for j in range(k)] + [tp[-1]])
+    emu = H.Emu(b, f"events_stepres{warp}")
+    base, trig = b.base_values()
+    got = emu.run(base, trig, vals, grid, 10000, 1e-6, 1e-9, stepres=k)
+    opt_ref = so.settings(10.0, nout * k, 1e-9, 1e-6)
+    arr = (C.c_double * (len(grid) - 1))(*grid[1:])
+    assert so.lib().CvodeSettings_setTimeSeries(opt_ref, arr, len(grid) - 1) == 1
+    ref = H.oracle_run(m, opt_ref, vary, vals, nout * k, compiled_so=H.compile_c_model(m, "events"))
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0))[::k], equal_nan=True)
+    acc = np.zeros((nout + 1, len(vals)), dtype=np.uint32)
+    for r in range(1, nout + 1):
+        acc[r] = np.bitwise_or.reduce(ref["fired"][:, (r - 1) * k + 1:r * k + 1], axis=1)
+    assert np.array_equal(got["fired"], acc) and acc.any()
+    b.close()
+
+
 def test_generated_source_has_single_hot_instances():
     """The block pipeline keeps one instance of the model functions in the instruction stream of the hot loop."""
     w = H.workload("mapk", nout=10)

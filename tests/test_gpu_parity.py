@@ -497,3 +497,83 @@ def test_functional_iteration_on_gpu(name, method, nsets):
     assert np.array_equal(got["stats"], ref["stats"])
     assert np.array_equal(got["fired"], ref["fired"])
     assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+
+
+def _refined_settings(w, k):
+    """The print grid of a workload with k equal sub-steps per print step, as a designed time series (what the kernel walks
+    with StepResolution = k)."""
+    tp = H.tpoints(w["opt"], w["nout"])
+    grid = np.empty(w["nout"] * k + 1)
+    for i in range(w["nout"]):
+        for j in range(k):
+            grid[i * k + j] = tp[i] if j == 0 else tp[i] + j * ((tp[i + 1] - tp[i]) / k)
+    grid[-1] = tp[-1]
+    opt = so.settings(w["end"], w["nout"] * k, w["atol"], w["rtol"])
+    arr = (C.c_double * (len(grid) - 1))(*grid[1:])
+    assert so.lib().CvodeSettings_setTimeSeries(opt, arr, len(grid) - 1) == 1
+    return opt, grid
+
+
+@pytest.mark.parametrize("warp", [0, 1])
+def test_step_resolution_refines_event_detection(monkeypatch, warp):
+    """cvodeSettings_t.StepResolution = k (reference integratorSettings.h:61-63, "useful for fine-grained event detection";
+    the reference never reads it): the solver is driven over k sub-steps per print step and events are examined, assignments
+    applied and the solver re-initialised at every sub-step with the reference's output-time semantics; rows are kept at the
+    print steps.  Checked against the reference's CVODE run ON THE REFINED GRID: the kept rows are its rows k, 2k, ...
+    bit for bit, and the event mask of a kept row is the OR of its masks since the row before."""
+    monkeypatch.setenv("ODES_WARP", str(warp))
+    L = so.lib()
+    k = 4
+    w = H.workload("events", nout=25)
+    m = w["model"]
+    vals = H.workload_values(w, 256, seed=5)
+    opt_k = so.settings(w["end"], w["nout"], w["atol"], w["rtol"])
+    C.cast(opt_k, C.POINTER(C.c_int * 4)).contents[3] = k          # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    b = so.Batch(m, opt_k, w["vary"])
+    assert ("-DODES_WARP=1" in b.source().split("\n")[0]) == bool(warp)
+    b.set_values(vals)
+    b.integrate(256)
+    out, fired, st = b.results(256), b.event_log(256), b.status(256)
+    b.close()
+    opt_ref, grid = _refined_settings(w, k)
+    ref = H.oracle_run(m, opt_ref, w["vary"], vals, w["nout"] * k, backend=H.gpu_tier_backend(), compiled_so=H.compile_c_model(m, "events"), threads=8)
+    assert (st == 0).all() and (ref["status"] == 0).all()
+    want = np.transpose(ref["out"], (1, 2, 0))[::k]
+    assert np.array_equal(out, want, equal_nan=True)
+    acc = np.zeros((w["nout"] + 1, 256), dtype=np.uint32)
+    for r in range(1, w["nout"] + 1):
+        acc[r] = np.bitwise_or.reduce(ref["fired"][:, (r - 1) * k + 1:r * k + 1], axis=1)
+    assert np.array_equal(fired, acc)
+    # the refinement matters: on the print grid alone some events are seen later (different rows)
+    b1 = so.Batch(m, w["opt"], w["vary"])
+    b1.set_values(vals)
+    b1.integrate(256)
+    coarse = b1.results(256)
+    b1.close()
+    assert not np.array_equal(coarse, out, equal_nan=True)
+    # halting modes are refused with StepResolution > 1
+    opt_h = so.settings(w["end"], w["nout"], w["atol"], w["rtol"], halt_on_event=1)
+    C.cast(opt_h, C.POINTER(C.c_int * 4)).contents[3] = k
+    with pytest.raises(so.OdesError):
+        so.Batch(m, opt_h, w["vary"])
+    L.SolverError_clear()
+
+
+def test_single_instance_without_event_processing():
+    """IntegratorInstance_integrateOneStepWithoutEventProcessing (src/integratorInstance.c:1634-1642): the device course of a
+    single instance skips the model's event function, so the plain decay S1 -> S2 follows exp(-t); a following
+    IntegratorInstance_integrateOneStep switches event handling back on from the current state."""
+    L = so.lib()
+    m = so.Model(H.model_path("two_events_one_assignment.xml"))
+    opt = so.settings(10.0, 100, 1e-12, 1e-9)
+    ii = L.IntegratorInstance_create(m.om, opt)
+    assert ii
+    vi = L.ODEModel_getVariableIndex(m.om, b"S1")
+    for k in range(1, 61):
+        assert L.IntegratorInstance_integrateOneStepWithoutEventProcessing(ii) == 1
+        t = L.IntegratorInstance_getTime(ii)
+        assert abs(L.IntegratorInstance_getVariableValue(ii, vi) - np.exp(-t)) < 1e-7, (k, t)
+    assert L.IntegratorInstance_getVariableValue(ii, vi) < 0.01           # far below the trigger threshold 0.1: no event was applied
+    assert L.IntegratorInstance_integrateOneStep(ii) == 1                  # with events: S1 < 0.1 fires and S1 is set back to 1
+    assert abs(L.IntegratorInstance_getVariableValue(ii, vi) - 1.0) < 1e-12
+    L.IntegratorInstance_free(ii)
