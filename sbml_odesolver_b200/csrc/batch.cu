@@ -434,8 +434,8 @@ static std::string build_source(odesBatch_t *b)
     if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[640];
-    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0),
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d -DODES_WLOCK=%d -DODES_WJE=%d -DODES_WDAG=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0), env_int("ODES_WLOCK", (b->nsens > 0 && slabs > 4) ? 1 : 0), env_int("ODES_WJE", -1), env_int("ODES_WDAG", -1),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
@@ -571,7 +571,12 @@ static int ensure_loaded(odesBatch_t *b)
     DRV_OK(drv.MemcpyDtoH(&wmBytes, sym, sizeof wmBytes));
     b->smemBytes = (size_t)wmBytes * (size_t)(b->block / 32);
   }
-  if (b->smemBytes > 48 * 1024) DRV_OK(drv.FuncSetAttribute(b->kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)b->smemBytes));
+  {
+    /* the opt-in above 48 KB counts the kernel's static shared memory (task tables, staging of the pow requests) as well */
+    int staticBytes = 0;
+    DRV_OK(drv.FuncGetAttribute(&staticBytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, b->kernel));
+    if (b->smemBytes + (size_t)staticBytes > 48 * 1024) DRV_OK(drv.FuncSetAttribute(b->kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)b->smemBytes));
+  }
   CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&b->copyIn, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&b->copyOut, cudaStreamNonBlocking));

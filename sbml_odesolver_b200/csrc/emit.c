@@ -80,17 +80,21 @@ typedef struct emit_ctx {
 /* leaf mode (warp flavour): operands of one expression.  An operand is a word of the warp's value space V (state,
    rule values, per-trajectory constants) or a number that goes to the literal pool behind it. */
 #define LEAF_MAX 16
-struct leafrec { int n, failed; int isnum[LEAF_MAX]; int off[LEAF_MAX]; double num[LEAF_MAX]; };
+struct leafrec { int n, failed; int isnum[LEAF_MAX]; int off[LEAF_MAX]; double num[LEAF_MAX]; int dedup; /* 1: an operand that occurs again gets its first placeholder */ };
 static void leaf_number(charBuffer_t *s, const emit_ctx_t *c, double v)
 {
-  struct leafrec *lr = c->leaf; char t[24];
+  struct leafrec *lr = c->leaf; char t[24]; int k;
+  /* 1.0 (compartment sizes, stoichiometries) stays a literal in the text: x / 1.0 and 1.0 * x fold away at compile time */
+  if (lr->dedup && v == 1.0) { CharBuffer_append(s, "1.0"); return; }
+  for (k = 0; lr->dedup && k < lr->n; k++) if (lr->isnum[k] && memcmp(&lr->num[k], &v, sizeof v) == 0) { snprintf(t, sizeof t, "x%d", k); CharBuffer_append(s, t); return; }
   if (lr->n >= LEAF_MAX) { lr->failed = 1; CharBuffer_append(s, "0.0"); return; }
   lr->isnum[lr->n] = 1; lr->num[lr->n] = v; lr->off[lr->n] = -1;
   snprintf(t, sizeof t, "x%d", lr->n++); CharBuffer_append(s, t);
 }
 static void leaf_word(charBuffer_t *s, const emit_ctx_t *c, int off)
 {
-  struct leafrec *lr = c->leaf; char t[24];
+  struct leafrec *lr = c->leaf; char t[24]; int k;
+  for (k = 0; lr->dedup && k < lr->n; k++) if (!lr->isnum[k] && lr->off[k] == off) { snprintf(t, sizeof t, "x%d", k); CharBuffer_append(s, t); return; }
   if (lr->n >= LEAF_MAX) { lr->failed = 1; CharBuffer_append(s, "0.0"); return; }
   lr->isnum[lr->n] = 0; lr->num[lr->n] = 0.0; lr->off[lr->n] = off;
   snprintf(t, sizeof t, "x%d", lr->n++); CharBuffer_append(s, t);
@@ -514,6 +518,7 @@ static void emit_refresh_all(charBuffer_t *b, const odeModel_t *om, const emit_c
 #define W_MAXGROUPS 8
 #define W_GROUP_LEAVES 5
 #define W_ODE_TERMS_MAX 10
+#define JE_MAX_ROUNDS 8
 typedef struct { int npv, nass, neq, nlit; double *lit; int naspad, npvpad; const kinfo_t *k; } wspace_t;
 static int w_as_off(const wspace_t *w) { (void)w; return 32; }
 static int w_pv_off(const wspace_t *w) { return 32 + w->naspad; }
@@ -573,6 +578,88 @@ static int w_flatten_sum(const ASTNode_t *n, int neg, const wspace_t *w, int *of
   }
   return cnt;
 }
+/* ---- the entries as ONE expression DAG, evaluated level by level (w_dag_pass in bdf_warp_kernel.cuh) ----
+   Every entry's tree is taken apart into binary IEEE operations exactly as gen() writes them (n-ary + - * / fold from the
+   left, a literal-2 power is x * x, constant sub-trees are folded by the host evaluator, multiplications / divisions by the
+   literal 1.0 drop out -- x * 1.0 == x / 1.0 == x for every x); identical sub-expressions become one node (same operands,
+   same operation: same bits).  A node's level is one above its operands'; the nodes of a level with the same operation
+   form a step of at most 32 tasks, one per lane.  The kernel then walks a table of steps with one small loop: the whole
+   Jacobian and parametric matrix cost (levels x operation kinds) short passes instead of one code body per shape. */
+enum { D_LEAF = 0, D_ADD, D_SUB, D_MUL, D_DIV, D_NEG, D_POW, D_EXP, D_LOG, D_NOPS };
+typedef struct { int op, a, b, level, off, isone; } dagnode_t;
+typedef struct { dagnode_t *n; int cnt, cap, failed; wspace_t *w; const kinfo_t *k; const emit_ctx_t *c; } dag_t;
+static int dag_new(dag_t *d, int op, int a, int b, int level, int off, int isone)
+{
+  if (d->cnt == d->cap) { d->cap = d->cap ? 2 * d->cap : 256; d->n = (dagnode_t *)realloc(d->n, sizeof(dagnode_t) * (size_t)d->cap); }
+  d->n[d->cnt].op = op; d->n[d->cnt].a = a; d->n[d->cnt].b = b; d->n[d->cnt].level = level; d->n[d->cnt].off = off; d->n[d->cnt].isone = isone;
+  return d->cnt++;
+}
+static int dag_leaf(dag_t *d, int off, int isone)
+{
+  int i;
+  for (i = 0; i < d->cnt; i++) if (d->n[i].op == D_LEAF && d->n[i].off == off) return i;
+  return dag_new(d, D_LEAF, -1, -1, 0, off, isone);
+}
+static int dag_num(dag_t *d, double v) { return dag_leaf(d, w_lit_off(d->w) + w_literal(d->w, v), v == 1.0 && !signbit(v)); }
+static int dag_op(dag_t *d, int op, int a, int b)
+{
+  int i, lv;
+  if (a < 0 || (b < 0 && op != D_NEG && op != D_EXP && op != D_LOG)) { d->failed = 1; return -1; }
+  if (op == D_MUL && d->n[a].isone) return b;
+  if ((op == D_MUL || op == D_DIV) && d->n[b].isone) return a;
+  if (b < 0) b = a;
+  for (i = 0; i < d->cnt; i++) if (d->n[i].op == op && d->n[i].a == a && d->n[i].b == b) return i;
+  lv = d->n[a].level > d->n[b].level ? d->n[a].level : d->n[b].level;
+  return dag_new(d, op, a, b, lv + 1, -1, 0);
+}
+static int dag_new_or_find_sqr(dag_t *d, int a)
+{
+  int i;
+  for (i = 0; i < d->cnt; i++) if (d->n[i].op == D_MUL && d->n[i].a == a && d->n[i].b == a) return i;
+  return dag_new(d, D_MUL, a, a, d->n[a].level + 1, -1, 0);
+}
+static int dag_build(dag_t *d, const ASTNode_t *n)
+{
+  unsigned int i; int r, op;
+  if (d->failed) return -1;
+  if (n->nchildren > 0 && is_const_tree(n) && !ASTNode_isLogical(n) && !ASTNode_isRelational(n) && n->type != AST_FUNCTION_PIECEWISE)
+    return dag_num(d, evaluateAST((ASTNode_t *)n, NULL));
+  switch (n->type) {
+  case AST_PLUS: case AST_TIMES: case AST_DIVIDE: case AST_MINUS:
+    if (n->nchildren < 1) { d->failed = 1; return -1; }
+    if (n->type == AST_MINUS && n->nchildren == 1) return dag_op(d, D_NEG, dag_build(d, n->children[0]), -1);
+    op = n->type == AST_PLUS ? D_ADD : n->type == AST_TIMES ? D_MUL : n->type == AST_DIVIDE ? D_DIV : D_SUB;
+    r = dag_build(d, n->children[0]);
+    for (i = 1; i < n->nchildren; i++) r = dag_op(d, op, r, dag_build(d, n->children[i]));
+    return r;
+  case AST_POWER: case AST_FUNCTION_POWER:
+    if (n->nchildren != 2) { d->failed = 1; return -1; }
+    if (is_const_tree(n->children[1])) {
+      const double e = evaluateAST(n->children[1], NULL);
+      if (e == 0.0) return dag_num(d, 1.0);
+      if (e == 1.0) return dag_build(d, n->children[0]);
+      if (e == 2.0 && !d->c->interp) { r = dag_build(d, n->children[0]); return d->failed ? -1 : dag_new_or_find_sqr(d, r); }
+    }
+    r = dag_build(d, n->children[0]);
+    return dag_op(d, D_POW, r, dag_build(d, n->children[1]));
+  case AST_INTEGER: return dag_num(d, (double)n->ival);
+  case AST_REAL: case AST_REAL_E: case AST_RATIONAL: return dag_num(d, ASTNode_getReal(n));
+  case AST_NAME: {
+      const kinfo_t *k = d->k; int idx;
+      if (!ASTNode_isSetIndex(n)) { d->failed = 1; return -1; }
+      idx = (int)ASTNode_getIndex(n);
+      switch (k->kind[idx]) {
+      case K_ODE: return dag_leaf(d, idx, 0);
+      case K_ASSIGNED: if (k->local[idx]) { d->failed = 1; return -1; } return dag_leaf(d, w_pv_off(d->w) + k->slot[idx], 0);   /* rule values are not refreshed here */
+      case K_THREAD: return dag_leaf(d, w_pv_off(d->w) + k->slot[idx], 0);
+      default: if (k->base) return dag_num(d, k->base[idx]); d->failed = 1; return -1;
+      }
+    }
+  case AST_FUNCTION_EXP: return dag_op(d, D_EXP, dag_build(d, n->children[0]), -1);
+  case AST_FUNCTION_LN: return dag_op(d, D_LOG, dag_build(d, n->children[0]), -1);
+  default: d->failed = 1; return -1;        /* time, piecewise, other functions: the shape form evaluates those */
+  }
+}
 static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k, emit_ctx_t *c, int *ode_local, int usejac, int npv, const odeSense_t *os)
 {
   int nb = om->nassbeforeodes, nlev = 0, lev, i, j, g, ngroups = 0, nvalues = om->neq + om->nass + om->nconst;
@@ -584,6 +671,9 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
   int *odeoff = (int *)calloc((size_t)om->neq * W_ODE_TERMS_MAX + 1, sizeof(int)), *odeneg = (int *)calloc((size_t)om->neq * W_ODE_TERMS_MAX + 1, sizeof(int));
   int *odecnt = (int *)calloc((size_t)om->neq + 1, sizeof(int)); double *odediv = (double *)calloc((size_t)om->neq + 1, sizeof(double));
   int odeterms = 0, odefallback = 0, odedivide = 0, negzero;
+  char **je_text = NULL; struct leafrec *je_leaf = NULL; int *je_dest = NULL, *je_neg = NULL, *je_shape = NULL, je_n = 0, je_shapes = 0, je_total = 0;
+  dag_t dag; int *je_node = NULL, *je_dneg = NULL, dag_ok = 0, ntemp = 0;
+  memset(&dag, 0, sizeof dag);
   wspace_t w;
   w.npv = npv; w.nass = om->nass; w.neq = om->neq; w.nlit = 0; w.lit = NULL; w.k = k;
   w.naspad = 8 * ((om->nass + 8) / 8); w.npvpad = 8 * ((npv + 7) / 8) + 8;
@@ -634,9 +724,61 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
     if (cnt > odeterms) odeterms = cnt;
     if (div != 1.0) odedivide = 1;
   }
+  /* ---- Jacobian and parametric-matrix ENTRIES of identical shape, one entry per lane ----
+     The row form below (w_jac_row, w_sens_row) makes lane i walk the expressions of row i: NEQ different code bodies one
+     after the other, each run by one lane -- with the simultaneous corrector that is most of a trajectory's instructions
+     (the Jacobian is evaluated at every corrector iteration).  Here every structurally non-zero entry d f_i / d y_j and
+     d f_i / d p_k is a task of its own: a top-level negation is split off as a flag (-(x) is exact), repeated operands
+     share a placeholder, entries whose text is then identical form a shape, and a lane evaluates the entry its task words
+     name -- all entries of a shape at once, every one with exactly the operations of its emitted expression. */
+  {
+    int total = usejac ? om->sparsesize : 0, e;
+    if (os && usejac && os->sens) for (i = 0; i < om->neq; i++) for (j = 0; j < os->nsensP; j++) if (os->sensLogic[i][j]) total++;
+    je_n = 0; je_shapes = 0;
+    if (usejac && total > 0 && total <= 32 * JE_MAX_ROUNDS) {
+      je_total = total;
+      je_text = (char **)calloc((size_t)total, sizeof(char *)); je_leaf = (struct leafrec *)calloc((size_t)total, sizeof(struct leafrec));
+      je_dest = (int *)calloc((size_t)total, sizeof(int)); je_neg = (int *)calloc((size_t)total, sizeof(int)); je_shape = (int *)calloc((size_t)total, sizeof(int));
+      for (e = 0; e < total; e++) {
+        const ASTNode_t *ast; charBuffer_t *tb = CharBuffer_create(); emit_ctx_t lc = *c; int q;
+        if (e < om->sparsesize) { ast = om->jacobSparse[e]->ij; je_dest[e] = 32 * om->jacobSparse[e]->j + om->jacobSparse[e]->i; }
+        else {
+          int cnt = om->sparsesize, found = 0;
+          ast = NULL;
+          for (i = 0; i < om->neq && !found; i++) for (j = 0; j < os->nsensP && !found; j++) if (os->sensLogic[i][j]) { if (cnt == e) { ast = os->sens[i][j]; je_dest[e] = 32 * om->neq + 32 * j + i; found = 1; } cnt++; }
+        }
+        if (ast && ast->type == AST_MINUS && ast->nchildren == 1) { je_neg[e] = 1; ast = ast->children[0]; }
+        je_leaf[e].dedup = 1; lc.leaf = &je_leaf[e]; lc.name = name_leaf;
+        if (ast) gen(tb, ast, &lc); else je_leaf[e].failed = 1;
+        je_text[e] = tb->b; tb->b = NULL; CharBuffer_free(tb);
+        for (q = 0; q < je_leaf[e].n; q++) if (!je_leaf[e].isnum[q] && je_leaf[e].off[q] >= w_as_off(&w) && je_leaf[e].off[q] < w_pv_off(&w)) je_leaf[e].failed = 1;   /* rule values are not refreshed here */
+        if (je_leaf[e].failed) break;
+        for (q = 0; q < e; q++) if (strcmp(je_text[q], je_text[e]) == 0 && je_leaf[q].n == je_leaf[e].n) break;
+        je_shape[e] = q < e ? je_shape[q] : je_shapes++;
+      }
+      if (e == total && je_shapes <= 64) {
+        int q2;
+        je_n = total;
+        /* the same entries as a DAG (falls back to the shapes when a tree holds something the DAG has no operation for) */
+        dag.w = &w; dag.k = k; dag.c = c;
+        je_node = (int *)calloc((size_t)total, sizeof(int)); je_dneg = (int *)calloc((size_t)total, sizeof(int));
+        for (q2 = 0; q2 < total && !dag.failed; q2++) {
+          const ASTNode_t *ast = NULL; int cnt2 = om->sparsesize, ii, jj;
+          if (q2 < om->sparsesize) ast = om->jacobSparse[q2]->ij;
+          else for (ii = 0; ii < om->neq && !ast; ii++) for (jj = 0; jj < os->nsensP && !ast; jj++) if (os->sensLogic[ii][jj]) { if (cnt2 == q2) ast = os->sens[ii][jj]; cnt2++; }
+          je_node[q2] = ast ? dag_build(&dag, ast) : -1;
+          if (je_node[q2] < 0) dag.failed = 1;
+          else if (dag.n[je_node[q2]].op == D_NEG) { je_dneg[q2] = 1; je_node[q2] = dag.n[je_node[q2]].a; }
+        }
+        dag_ok = !dag.failed;
+        for (e = 0; e < total; e++) for (j = 0; j < je_leaf[e].n; j++) if (je_leaf[e].isnum[j]) je_leaf[e].off[j] = w_lit_off(&w) + w_literal(&w, je_leaf[e].num[j]);
+      }
+    }
+  }
   /* pool the literals of the grouped rules */
   for (i = 0; i < nb; i++) if (group[i] >= 0) for (j = 0; j < leaves[i].n; j++) if (leaves[i].isnum[j]) leaves[i].off[j] = w_lit_off(&w) + w_literal(&w, leaves[i].num[j]);
 
+  /* (the literal pool is complete from here on: the DAG's temporaries live behind it) */
   cbprintf(b, "#ifndef ODES_WARP\n#define ODES_WARP 0\n#endif\n#if ODES_WARP\n#define W_NLEVELS %d\n#define W_AS_OFF %d\n#define W_PV_OFF %d\n#define W_LIT_OFF %d\n#define W_NLIT %d\n#define W_NGROUPS %d\n"
               "#define W_ODE_NTERMS %d\n#define W_ODE_DIVIDE %d\n#define W_ODE_FALLBACK %d\n#define W_NEGZERO_OFF %d\n",
            nlev, w_as_off(&w), w_pv_off(&w), w_lit_off(&w), w.nlit, ngroups, odeterms, odedivide, odefallback, w_lit_off(&w) + negzero);
@@ -755,7 +897,116 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
     }
     CharBuffer_append(b, "  default: break;\n  }\n  return r;\n}\n");
   }
+  /* the entry tasks: word 0 = operands 0..3 (10 bits each), destination (bits 40..51: 32 * column + row in the row-per-lane
+     matrix, the parametric columns behind the NEQ Jacobian columns), shape (52..57), negate (62), valid (63); words 1, 2 =
+     operands 4..9 and 10..15.  Slots are filled shape by shape so that a round of 32 entries holds few shapes. */
+  cbprintf(b, "#define W_JE_N %d\n#define W_JE_ROUNDS %d\n#define W_NSENSP %d\n", je_n, (je_n + 31) / 32, (os && usejac) ? os->nsensP : 0);
+  if (je_n > 0) {
+    int slot = 0, sh, e, q;
+    CharBuffer_append(b, "DEV unsigned long long w_je_task(int slot, int word)\n{\n  switch (3 * slot + word) {\n");
+    for (sh = 0; sh < je_shapes; sh++)
+      for (e = 0; e < je_n; e++) {
+        unsigned long long wd[3] = {0ull, 0ull, 0ull};
+        if (je_shape[e] != sh) continue;
+        wd[0] = (1ull << 63) | ((unsigned long long)je_neg[e] << 62) | ((unsigned long long)sh << 52) | ((unsigned long long)je_dest[e] << 40);
+        for (q = 0; q < je_leaf[e].n; q++) {
+          if (q < 4) wd[0] |= (unsigned long long)je_leaf[e].off[q] << (10 * q);
+          else wd[1 + (q - 4) / 6] |= (unsigned long long)je_leaf[e].off[q] << (10 * ((q - 4) % 6));
+        }
+        for (q = 0; q < 3; q++) if (wd[q]) cbprintf(b, "  case %d: return 0x%llxull;\n", 3 * slot + q, wd[q]);
+        slot++;
+      }
+    CharBuffer_append(b, "  default: return 0ull;\n  }\n}\n");
+    CharBuffer_append(b, "DEV void w_je_eval(const unsigned long long w0, const unsigned long long w1, const unsigned long long w2, double t, const double *V, double *dst, unsigned int limit)\n{\n"
+                         "  (void)t; (void)w1; (void)w2;\n  const unsigned int d_ = (unsigned int)(w0 >> 40) & 4095u;\n  if (!(w0 >> 63) || d_ >= limit) return;\n  double r_ = 0.0;\n  switch ((int)((w0 >> 52) & 63u)) {\n");
+    for (sh = 0; sh < je_shapes; sh++) {
+      for (e = 0; e < je_n && je_shape[e] != sh; e++) ;
+      cbprintf(b, "  case %d: {\n", sh);
+      for (q = 0; q < je_leaf[e].n; q++) {
+        if (q < 4) cbprintf(b, "    const double x%d = V[(w0 >> %d) & 1023u];\n", q, 10 * q);
+        else cbprintf(b, "    const double x%d = V[(w%d >> %d) & 1023u];\n", q, 1 + (q - 4) / 6, 10 * ((q - 4) % 6));
+      }
+      cbprintf(b, "    r_ = %s;\n  } break;\n", je_text[e]);
+    }
+    CharBuffer_append(b, "  default: break;\n  }\n  dst[d_] = ((w0 >> 62) & 1ull) ? -r_ : r_;\n}\n");
+    /* rows of the sensitivity right-hand side: the non-zero Jacobian columns of a row (bit j), the parametric column of a
+       sensitivity (or -1: it belongs to a variable) and the non-zero parametric columns of a row */
+    CharBuffer_append(b, "DEV unsigned int w_row_mask(int i)\n{\n  switch (i) {\n");
+    for (i = 0; i < om->neq && i < 32; i++) {
+      unsigned int m = 0u; int last = -1, sorted = 1;
+      for (j = 0; j < om->sparsesize; j++) if (om->jacobSparse[j]->i == i) { if (om->jacobSparse[j]->j <= last) sorted = 0; last = om->jacobSparse[j]->j; m |= 1u << om->jacobSparse[j]->j; }
+      cbprintf(b, "  case %d: return 0x%xu;%s\n", i, m, sorted ? "" : " /* UNSORTED */");
+      if (!sorted) je_n = -1;
+    }
+    CharBuffer_append(b, "  default: return 0u;\n  }\n}\n");
+    CharBuffer_append(b, "DEV int w_sens_pcol(int is)\n{\n  switch (is) {\n");
+    if (os) for (i = 0; i < os->nsens; i++) if (os->index_sensP[i] != -1) cbprintf(b, "  case %d: return %d;\n", i, os->index_sensP[i]);
+    CharBuffer_append(b, "  default: return -1;\n  }\n}\nDEV unsigned int w_sens_pmask(int i)\n{\n  switch (i) {\n");
+    if (os && os->sens) for (i = 0; i < om->neq; i++) {
+      unsigned int m = 0u;
+      for (j = 0; j < os->nsensP && j < 32; j++) if (os->sensLogic[i][j]) m |= 1u << j;
+      if (m) cbprintf(b, "  case %d: return 0x%xu;\n", i, m);
+    }
+    CharBuffer_append(b, "  default: return 0u;\n  }\n}\n");
+    if (je_n < 0) CharBuffer_append(b, "#undef W_JE_N\n#define W_JE_N 0\n");          /* column order of a row not ascending: keep the row form */
+  }
+  /* the DAG form: steps (level, operation) of at most 32 tasks; task word = operand a (12 bits) | operand b << 12 |
+     result << 24 | valid << 63, all three offsets into V (temporaries behind the literal pool); then the entries:
+     node | destination << 12 | negate << 62 | valid << 63 */
+  {
+    int nsteps = 0, opmask = 0, lv, op, maxlv = 0, q;
+    if (dag_ok && je_n > 0) {
+      const int tmp_off = 8 * ((w_lit_off(&w) + w.nlit + 7) / 8);
+      for (q = 0; q < dag.cnt; q++) { if (dag.n[q].op != D_LEAF) dag.n[q].off = tmp_off + ntemp++; if (dag.n[q].level > maxlv) maxlv = dag.n[q].level; }
+      if (tmp_off + ntemp >= 4096) dag_ok = 0;
+    }
+    if (dag_ok && je_n > 0) {
+      charBuffer_t *tasks = CharBuffer_create(), *ops = CharBuffer_create();
+      for (lv = 1; lv <= maxlv; lv++) for (op = D_ADD; op < D_NOPS; op++) {
+        int lane = 0, any = 0;
+        for (q = 0; q < dag.cnt; q++) {
+          unsigned long long word;
+          if (dag.n[q].op != op || dag.n[q].level != lv) continue;
+          if (lane == 32) { cbprintf(ops, "  case %d: return %d;\n", nsteps, op); nsteps++; lane = 0; }
+          word = (1ull << 63) | ((unsigned long long)dag.n[q].off << 24) | ((unsigned long long)dag.n[dag.n[q].b].off << 12) | (unsigned long long)dag.n[dag.n[q].a].off;
+          cbprintf(tasks, "  case %d: return 0x%llxull;\n", 32 * nsteps + lane, word);
+          lane++; any = 1; opmask |= 1 << op;
+        }
+        if (any) { cbprintf(ops, "  case %d: return %d;\n", nsteps, op); nsteps++; }
+      }
+      if (nsteps > 0 && nsteps <= 192) {
+        /* does the DAG pay?  instruction estimates: a shape body costs its operations (a division ~22 instructions, pow / exp /
+           log a few hundred) plus operand fetches, a DAG step its one operation plus ~16 of task decoding and traffic -- but a
+           step is also a dependent chain of two loads, the operation and a store, so the DAG must win by a factor (measured,
+           see bdf_warp_kernel.cuh) */
+        int shape_cost = 0, dag_cost = 0, sh;
+        for (sh = 0; sh < je_shapes; sh++) {
+          const char *t; int e2, nd = 0, no = 0, nf = 0;
+          for (e2 = 0; e2 < je_n && je_shape[e2] != sh; e2++) ;
+          for (t = je_text[e2]; *t; t++) { if (*t == '/') nd++; else if (*t == '+' || *t == '*' || (*t == '-' && t[1] == ' ')) no++; else if (*t == 'o' && (!strncmp(t, "odes_pow", 8) || !strncmp(t, "odes_exp", 8) || !strncmp(t, "odes_log", 8))) nf++; }
+          shape_cost += 22 * nd + 2 * no + 250 * nf + 6 * je_leaf[e2].n + 12;
+        }
+        {
+          const char *t = ops->b ? ops->b : "";
+          for (; (t = strstr(t, "return ")) != NULL; t += 7) { const int o = atoi(t + 7); dag_cost += (o == D_DIV ? 38 : (o == D_POW || o == D_EXP || o == D_LOG) ? 266 : 18); }
+        }
+        cbprintf(b, "#define W_DAG_STEPS %d\n#define W_DAG_OPMASK %d\n#define W_DAG_NTEMP %d\n#define W_DAG_NODES %d\n#define W_DAG_PAYS %d /* estimate: shapes %d, DAG %d instructions */\n",
+                 nsteps, opmask, ntemp, dag.cnt, shape_cost > 2 * dag_cost, shape_cost, dag_cost);
+        CharBuffer_append(b, "DEV unsigned long long w_dag_task(int slot)\n{\n  switch (slot) {\n"); if (tasks->b) CharBuffer_append(b, tasks->b);
+        CharBuffer_append(b, "  default: return 0ull;\n  }\n}\nDEV int w_dag_op(int step)\n{\n  switch (step) {\n"); if (ops->b) CharBuffer_append(b, ops->b);
+        CharBuffer_append(b, "  default: return 0;\n  }\n}\n");
+        CharBuffer_append(b, "DEV unsigned long long w_dag_out(int slot)\n{\n  switch (slot) {\n");
+        for (q = 0; q < je_n; q++)
+          cbprintf(b, "  case %d: return 0x%llxull;\n", q, (1ull << 63) | ((unsigned long long)je_dneg[q] << 62) | ((unsigned long long)je_dest[q] << 12) | (unsigned long long)dag.n[je_node[q]].off);
+        CharBuffer_append(b, "  default: return 0ull;\n  }\n}\n");
+      } else dag_ok = 0;
+      CharBuffer_free(tasks); CharBuffer_free(ops);
+    }
+    if (!(dag_ok && je_n > 0)) CharBuffer_append(b, "#define W_DAG_STEPS 0\n#define W_DAG_NTEMP 0\n");
+  }
   CharBuffer_append(b, "#endif\n");
+  for (i = 0; je_text && i < je_total; i++) free(je_text[i]);
+  free(je_text); free(je_leaf); free(je_dest); free(je_neg); free(je_shape); free(je_node); free(je_dneg); free(dag.n);
   for (i = 0; i < nb; i++) free(text[i]);
   free(text); free(leaves); free(group); free(depth); free(refs); free(odeoff); free(odeneg); free(odecnt); free(odediv); free(w.lit);
 }

@@ -105,6 +105,60 @@ def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets
     assert set(np.unique(got["sens"][:, 0])) <= {0.0, 1.0}
 
 
+FORMS = {"rows": dict(ODES_WJE="0"), "shapes": dict(ODES_WJE="1", ODES_WDAG="0"), "dag": dict(ODES_WJE="1", ODES_WDAG="1")}
+
+
+@needs_ref
+@pytest.mark.parametrize("form", sorted(FORMS))
+@pytest.mark.parametrize("name,nsets", [("mapk", 12), ("goodwin", 4), ("huang", 3)])
+def test_emulated_jacobian_forms_agree_with_vendored_cvodes(monkeypatch, name, nsets, form):
+    """The three ways the warp kernel evaluates the Jacobian and the parametric matrix for the sensitivity right-hand sides --
+    row per lane, one entry per lane grouped by expression shape, common sub-expressions level by level (emit.c: entry
+    tasks, entry DAG) -- perform the operations of the emitted expressions: each is bit-identical to the vendored CVODES.
+    (The automatic choice is covered by the test above.)"""
+    for k, v in FORMS[form].items():
+        monkeypatch.setenv(k, v)
+    w = _case(name)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=19)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    head = b.source().split("\n")[0]
+    assert all(f"-D{k}={v}" in head for k, v in FORMS[form].items())
+    if form != "rows":
+        assert "#define W_JE_N 0" not in b.source().split("#if ODES_WARP")[1].split("#endif")[0] or name == "none"
+    tp = H.tpoints(w["opt"], w["nout"])
+    base, trig = b.base_values()
+    got = H.Emu(b, f"{name}_sens_{form}").run(base, trig, vals, tp, 10000, w["rtol"], w["atol"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag=name + "_sens")
+    b.close()
+    assert np.array_equal(got["stats"].T, ref["stats"][:, :7])
+    assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"])
+    assert np.array_equal(got["sens"], ref["sens"])
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("form", sorted(FORMS))
+@pytest.mark.parametrize("name,nsets", [("mapk", 256), ("goodwin", 64), ("repressilator", 64)])
+def test_gpu_jacobian_forms_agree_with_vendored_cvodes(monkeypatch, name, nsets, form):
+    """The same three forms on the device."""
+    for k, v in FORMS[form].items():
+        monkeypatch.setenv(k, v)
+    w = _case(name)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=23)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    n = b.set_values(vals)
+    b.integrate(n)
+    out, sens, stats = b.results(n), b.sensitivities(n), b.stats(n).T
+    tp = H.tpoints(w["opt"], w["nout"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=8, tag=name + "_sens")
+    b.close()
+    assert np.array_equal(stats, ref["stats"][:, :7])
+    assert np.array_equal(np.transpose(out, (2, 0, 1)), ref["out"], equal_nan=True)
+    assert np.array_equal(sens, ref["sens"], equal_nan=True)
+
+
 @needs_ref
 def test_sensitivities_change_the_step_sequence_only_through_the_newton_test():
     """With errconS == FALSE the error test sees the state alone, but the corrector's convergence test sees every variable
