@@ -672,7 +672,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
   int *odecnt = (int *)calloc((size_t)om->neq + 1, sizeof(int)); double *odediv = (double *)calloc((size_t)om->neq + 1, sizeof(double));
   int odeterms = 0, odefallback = 0, odedivide = 0, negzero;
   char **je_text = NULL; struct leafrec *je_leaf = NULL; int *je_dest = NULL, *je_neg = NULL, *je_shape = NULL, je_n = 0, je_shapes = 0, je_total = 0;
-  dag_t dag; int *je_node = NULL, *je_dneg = NULL, dag_ok = 0, ntemp = 0;
+  dag_t dag; int *je_node = NULL, *je_dneg = NULL, dag_ok = 0, ntemp = 0, dag_one = 0;
   memset(&dag, 0, sizeof dag);
   wspace_t w;
   w.npv = npv; w.nass = om->nass; w.neq = om->neq; w.nlit = 0; w.lit = NULL; w.k = k;
@@ -761,6 +761,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
         je_n = total;
         /* the same entries as a DAG (falls back to the shapes when a tree holds something the DAG has no operation for) */
         dag.w = &w; dag.k = k; dag.c = c;
+        dag_one = w_lit_off(&w) + w_literal(&w, 1.0);            /* idle lanes of a step compute 1.0 (op) 1.0 into a scrap word */
         je_node = (int *)calloc((size_t)total, sizeof(int)); je_dneg = (int *)calloc((size_t)total, sizeof(int));
         for (q2 = 0; q2 < total && !dag.failed; q2++) {
           const ASTNode_t *ast = NULL; int cnt2 = om->sparsesize, ii, jj;
@@ -950,30 +951,36 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
     CharBuffer_append(b, "  default: return 0u;\n  }\n}\n");
     if (je_n < 0) CharBuffer_append(b, "#undef W_JE_N\n#define W_JE_N 0\n");          /* column order of a row not ascending: keep the row form */
   }
-  /* the DAG form: steps (level, operation) of at most 32 tasks; task word = operand a (12 bits) | operand b << 12 |
-     result << 24 | valid << 63, all three offsets into V (temporaries behind the literal pool); then the entries:
-     node | destination << 12 | negate << 62 | valid << 63 */
+  /* the DAG form: steps (level, operation) of at most 32 tasks; a task is one 32-bit word, operand a | operand b << 10 |
+     result << 20, offsets into V (temporaries behind the literal pool; idle lanes take 1.0 (op) 1.0 into a scrap word, so
+     a step needs no predicate); the operation of a step carries bit 8 when the next step belongs to a higher level (the
+     warp synchronises there); then the entries: node | destination << 12 | negate << 62 | valid << 63 */
   {
     int nsteps = 0, opmask = 0, lv, op, maxlv = 0, q;
     if (dag_ok && je_n > 0) {
       const int tmp_off = 8 * ((w_lit_off(&w) + w.nlit + 7) / 8);
+      ntemp = 1;                                                 /* word 0: scrap */
       for (q = 0; q < dag.cnt; q++) { if (dag.n[q].op != D_LEAF) dag.n[q].off = tmp_off + ntemp++; if (dag.n[q].level > maxlv) maxlv = dag.n[q].level; }
-      if (tmp_off + ntemp >= 4096) dag_ok = 0;
+      if (tmp_off + ntemp >= 1024) dag_ok = 0;
     }
     if (dag_ok && je_n > 0) {
+      const int tmp_off = 8 * ((w_lit_off(&w) + w.nlit + 7) / 8);
+      const unsigned int idle = (unsigned int)dag_one | ((unsigned int)dag_one << 10) | ((unsigned int)tmp_off << 20);
       charBuffer_t *tasks = CharBuffer_create(), *ops = CharBuffer_create();
-      for (lv = 1; lv <= maxlv; lv++) for (op = D_ADD; op < D_NOPS; op++) {
+      int *stepop = (int *)calloc(1024, sizeof(int)), *steplv = (int *)calloc(1024, sizeof(int));
+      for (lv = 1; lv <= maxlv && nsteps < 1000; lv++) for (op = D_ADD; op < D_NOPS && nsteps < 1000; op++) {
         int lane = 0, any = 0;
-        for (q = 0; q < dag.cnt; q++) {
-          unsigned long long word;
+        for (q = 0; q < dag.cnt && nsteps < 1000; q++) {
+          unsigned int word;
           if (dag.n[q].op != op || dag.n[q].level != lv) continue;
-          if (lane == 32) { cbprintf(ops, "  case %d: return %d;\n", nsteps, op); nsteps++; lane = 0; }
-          word = (1ull << 63) | ((unsigned long long)dag.n[q].off << 24) | ((unsigned long long)dag.n[dag.n[q].b].off << 12) | (unsigned long long)dag.n[dag.n[q].a].off;
-          cbprintf(tasks, "  case %d: return 0x%llxull;\n", 32 * nsteps + lane, word);
+          if (lane == 32) { stepop[nsteps] = op; steplv[nsteps] = lv; nsteps++; lane = 0; }
+          word = (unsigned int)dag.n[dag.n[q].a].off | ((unsigned int)dag.n[dag.n[q].b].off << 10) | ((unsigned int)dag.n[q].off << 20);
+          cbprintf(tasks, "  case %d: return 0x%xu;\n", 32 * nsteps + lane, word);
           lane++; any = 1; opmask |= 1 << op;
         }
-        if (any) { cbprintf(ops, "  case %d: return %d;\n", nsteps, op); nsteps++; }
+        if (any) { stepop[nsteps] = op; steplv[nsteps] = lv; nsteps++; }
       }
+      for (q = 0; q < nsteps; q++) cbprintf(ops, "  case %d: return %d;\n", q, stepop[q] | ((q + 1 == nsteps || steplv[q + 1] != steplv[q]) ? 256 : 0));
       if (nsteps > 0 && nsteps <= 192) {
         /* does the DAG pay?  instruction estimates: a shape body costs its operations (a division ~22 instructions, pow / exp /
            log a few hundred) plus operand fetches, a DAG step its one operation plus ~16 of task decoding and traffic -- but a
@@ -986,21 +993,18 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
           for (t = je_text[e2]; *t; t++) { if (*t == '/') nd++; else if (*t == '+' || *t == '*' || (*t == '-' && t[1] == ' ')) no++; else if (*t == 'o' && (!strncmp(t, "odes_pow", 8) || !strncmp(t, "odes_exp", 8) || !strncmp(t, "odes_log", 8))) nf++; }
           shape_cost += 22 * nd + 2 * no + 250 * nf + 6 * je_leaf[e2].n + 12;
         }
-        {
-          const char *t = ops->b ? ops->b : "";
-          for (; (t = strstr(t, "return ")) != NULL; t += 7) { const int o = atoi(t + 7); dag_cost += (o == D_DIV ? 38 : (o == D_POW || o == D_EXP || o == D_LOG) ? 266 : 18); }
-        }
-        cbprintf(b, "#define W_DAG_STEPS %d\n#define W_DAG_OPMASK %d\n#define W_DAG_NTEMP %d\n#define W_DAG_NODES %d\n#define W_DAG_PAYS %d /* estimate: shapes %d, DAG %d instructions */\n",
-                 nsteps, opmask, ntemp, dag.cnt, shape_cost > 2 * dag_cost, shape_cost, dag_cost);
-        CharBuffer_append(b, "DEV unsigned long long w_dag_task(int slot)\n{\n  switch (slot) {\n"); if (tasks->b) CharBuffer_append(b, tasks->b);
-        CharBuffer_append(b, "  default: return 0ull;\n  }\n}\nDEV int w_dag_op(int step)\n{\n  switch (step) {\n"); if (ops->b) CharBuffer_append(b, ops->b);
+        for (q = 0; q < nsteps; q++) dag_cost += (stepop[q] == D_DIV ? 38 : (stepop[q] == D_POW || stepop[q] == D_EXP || stepop[q] == D_LOG) ? 266 : 18);
+        cbprintf(b, "#define W_DAG_STEPS %d\n#define W_DAG_OPMASK %d\n#define W_DAG_NTEMP %d\n#define W_DAG_NODES %d\n#define W_DAG_IDLE 0x%xu\n#define W_DAG_PAYS %d /* estimate: shapes %d, DAG %d instructions */\n",
+                 nsteps, opmask, ntemp, dag.cnt, idle, shape_cost > 2 * dag_cost, shape_cost, dag_cost);
+        CharBuffer_append(b, "DEV unsigned int w_dag_task(int slot)\n{\n  switch (slot) {\n"); if (tasks->b) CharBuffer_append(b, tasks->b);
+        CharBuffer_append(b, "  default: return W_DAG_IDLE;\n  }\n}\nDEV int w_dag_op(int step)\n{\n  switch (step) {\n"); if (ops->b) CharBuffer_append(b, ops->b);
         CharBuffer_append(b, "  default: return 0;\n  }\n}\n");
         CharBuffer_append(b, "DEV unsigned long long w_dag_out(int slot)\n{\n  switch (slot) {\n");
         for (q = 0; q < je_n; q++)
           cbprintf(b, "  case %d: return 0x%llxull;\n", q, (1ull << 63) | ((unsigned long long)je_dneg[q] << 62) | ((unsigned long long)je_dest[q] << 12) | (unsigned long long)dag.n[je_node[q]].off);
         CharBuffer_append(b, "  default: return 0ull;\n  }\n}\n");
       } else dag_ok = 0;
-      CharBuffer_free(tasks); CharBuffer_free(ops);
+      CharBuffer_free(tasks); CharBuffer_free(ops); free(stepop); free(steplv);
     }
     if (!(dag_ok && je_n > 0)) CharBuffer_append(b, "#define W_DAG_STEPS 0\n#define W_DAG_NTEMP 0\n");
   }
