@@ -1710,7 +1710,16 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     if (ODES_WARP_ANY(s.st == ST_OUTPUT)) {
       PROF(7, s.st == ST_OUTPUT);
       double pvl[A1(NPVP)];
+      /* the per-trajectory constants are fetched only where the output-time code reads them: stored assigned values or
+         constants, events, the steady-state test (three tensor-memory loads per pass otherwise wasted) */
+#ifndef STORE_NEEDS_PV
+#define STORE_NEEDS_PV 1
+#endif
+#if STORE_NEEDS_PV || NEVENTS > 0 || HALT_ON_STEADY
       la_load<NPVCH>(la, LAPV, pvl);
+#else
+      _Pragma("unroll") for (int k = 0; k < NPVP; k++) pvl[k] = 0.0;
+#endif
       PvRef pv; pv.p = pvl; pv.s = 1u;
       bool wrote = false;
       while (s.st == ST_OUTPUT) {

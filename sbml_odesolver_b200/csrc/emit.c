@@ -1042,7 +1042,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
 char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
                                       int nstore, const int *store, const double *base, const odeSense_t *os)
 {
-  int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac;
+  int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac, store_needs_pv = 0;
   charBuffer_t *b = CharBuffer_create();
   kinfo_t k; emit_ctx_t c; char *out;
   int *used_in_ode = (int *)calloc((size_t)nvalues + 1, sizeof(int));
@@ -1159,12 +1159,15 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
   /* store_row: refresh all rules, write the selected values (coalesced: consecutive sets are consecutive addresses) */
   CharBuffer_append(b, "DEV void store_row(double *__restrict__ row, size_t stride, double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  double a[A1(NASS)]; (void)t; (void)a; (void)pv; (void)y;\n");
   {
-    int need_rules = 0;
-    for (j = 0; j < nstore; j++) if (store[j] >= om->neq && store[j] < om->neq + om->nass) need_rules = 1;
+    int need_rules = 0, need_pv = 0;
+    for (j = 0; j < nstore; j++) { if (store[j] >= om->neq && store[j] < om->neq + om->nass) need_rules = 1; if (store[j] >= om->neq) need_pv = 1; }
+    store_needs_pv = need_rules || need_pv;
     if (need_rules) emit_refresh_all(b, om, &c, "  ");
     for (j = 0; j < nstore; j++) { cbprintf(b, "  row[%d * stride] = ", j); name_cuda(b, store[j], &c); CharBuffer_append(b, ";\n"); }
   }
   CharBuffer_append(b, "}\n");
+  /* whether store_row reads anything but y (the output block then skips fetching the per-trajectory constants) */
+  cbprintf(b, "#define STORE_NEEDS_PV %d\n", store_needs_pv);
   /* row 0: values after initial assignments with the model's own parameters, varied entries overwritten
      (setVariableValue at t == 0 patches results->value[idx][0] only, integratorInstance.c:1571-1572) */
   CharBuffer_append(b, "DEV void store_row0(double *__restrict__ row, size_t stride, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  (void)y; (void)pv;\n");
