@@ -458,7 +458,7 @@ __constant__ double c_eta_small[8] =
 DEV bool eta_below_thresh(double x, int n) { return n >= 2 && n <= 7 && x >= c_eta_small[n]; }
 #if !ODES_WARP
 #ifndef ODES_POW_SHARE
-#define ODES_POW_SHARE 1
+#define ODES_POW_SHARE 0      /* measured on MAPK (B200, 10^6 sets) once the certain-below-THRESH requests are skipped: shared 224.6 ms, per lane 222.8 ms */
 #endif
 /* RPowerR for up to three (x, n) requests per lane, warp-converged.  pow is a pure function, so it does not matter WHICH
    lane evaluates a request: the requests of the warp (about one per completing lane plus two for the few lanes that
