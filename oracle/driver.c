@@ -81,6 +81,118 @@ typedef struct {
   int failed;
 } job_t;
 
+/* ---- events located inside the steps (cvodeSettings_t.StepResolution < 0) ----
+   The procedure of the kernel's root mode (bdf_warp_kernel.cuh, integrate_warp), driven over the vendored CVODE step by
+   step (CV_ONE_STEP + CVodeGetDky): after every internal step the triggers are evaluated at the step's end; a trigger that
+   became true since the last known trigger state is traced back by bisection on the dense output to 100 uround
+   (|tn| + |hu|); output times before the located time are handled first (interpolation, the reference's output-time event
+   handling, row store), then the event is applied at the located time and -- if it assigned -- the solver re-initialised
+   there.  The step limit counts per output interval, like the CVode calls of the reference. */
+static unsigned int trigger_mask(odeModel_t *om, double *value, double t)
+{
+  unsigned int m = 0; int i, e;
+  for (i = 0; i < om->nassbeforeevents; i++) { nonzeroElem_t *o = om->assignmentsBeforeEvents[i]; value[o->i] = oracle_eval(o->ij, value, t); }
+  for (e = 0; e < om->nevents; e++) if (oracle_eval(om->event[e], value, t)) m |= 1u << e;
+  return m;
+}
+static unsigned int apply_events(odeModel_t *om, const cvodeSettings_t *opt, double *value, int *trigger, double t, int *isValid)
+{
+  unsigned int firedmask = 0; int i, j, e, neq = om->neq;
+  for (i = 0; i < om->nassbeforeevents; i++) { nonzeroElem_t *o = om->assignmentsBeforeEvents[i]; value[o->i] = oracle_eval(o->ij, value, t); }
+  for (e = 0; e < om->nevents; e++) {
+    if (trigger[e] == 0) {
+      if (oracle_eval(om->event[e], value, t)) {
+        firedmask |= (1u << e);
+        trigger[e] = 1;
+        for (j = 0; j < om->neventAss[e]; j++) {
+          double r = oracle_eval(om->eventAssignment[e][j], value, t);
+          int idx = om->eventIndex[e][j];
+          if (idx >= neq && idx < neq + om->nass) continue;
+          value[idx] = r;
+          if (idx < neq || opt->ResetCvodeOnEvent) *isValid = 0;
+          refresh_rules(om, value, t);
+        }
+      }
+    } else if (!oracle_eval(om->event[e], value, t)) trigger[e] = 0;
+  }
+  return firedmask;
+}
+/* returns the CVODE flag (< 0 on failure); *piout = first row not stored */
+static int run_rootfind(odeModel_t *om, const cvodeSettings_t *opt, const oracle_backend_t *be, void *h, double *value, double *y,
+                        int *trigger, double *rows, unsigned int *fired, int *pcreated, int *piout)
+{
+  const int nvalues = om->neq + om->nass + om->nconst, neq = om->neq, nout = opt->PrintStep;
+  double t = opt->TimePoints[0], troot = 0.0, rlo = 0.0, tn = t, hu = 0.0, tdummy;
+  double *vtmp = (double *)malloc((size_t)nvalues * sizeof(double)), *yend = (double *)malloc((size_t)(neq > 0 ? neq : 1) * sizeof(double));
+  int isValid = 0, pending = 0, fresh = 1, need_check = 0, iout = 1, flag = 0, i, e; long nstloc = 0;
+  unsigned int acc = 0;
+  while (iout <= nout) {
+    const double tout = opt->TimePoints[iout];
+    int at_output;
+    if (!isValid) {
+      for (i = 0; i < neq; i++) y[i] = value[i];
+      flag = be->init(h, t, y, opt->RError, opt->Error, (long)opt->Mxstep, *pcreated);
+      *pcreated = 1; isValid = 1;
+      if (flag < 0) break;
+      pending = 0; fresh = 1; need_check = 0; nstloc = 0; tn = t; hu = 0.0;
+    }
+    at_output = !fresh && tn >= tout;
+    if (need_check) {
+      unsigned int known = 0, cand;
+      need_check = 0;
+      for (e = 0; e < om->nevents; e++) if (trigger[e]) known |= 1u << e;
+      memcpy(vtmp, value, (size_t)nvalues * sizeof(double));
+      for (i = 0; i < neq; i++) vtmp[i] = yend[i];              /* zn[0]: the state at the end of the step */
+      cand = trigger_mask(om, vtmp, tn) & ~known;
+      if (cand) {
+        double lo = rlo, hi = tn; int it;
+        const double ttol = 100.0 * 2.2204460492503131e-16 * (fabs(tn) + fabs(hu));
+        for (it = 0; it < 200 && (hi - lo) > ttol; it++) {
+          const double mid = lo + 0.5 * (hi - lo);
+          be->dky(h, mid, y);
+          for (i = 0; i < neq; i++) vtmp[i] = y[i];
+          if (trigger_mask(om, vtmp, mid) & cand) hi = mid; else lo = mid;
+        }
+        troot = hi; pending = 1;
+      }
+      continue;
+    }
+    if (pending && troot <= tout) {
+      be->dky(h, troot, y);
+      for (i = 0; i < neq; i++) value[i] = y[i];
+      acc |= apply_events(om, opt, value, trigger, troot, &isValid);
+      pending = 0;
+      if (!isValid) t = troot;
+      else { rlo = troot; need_check = 1; }
+      continue;
+    }
+    if (at_output) {
+      t = tout;
+      be->dky(h, t, y);
+      for (i = 0; i < neq; i++) value[i] = y[i];
+      acc |= apply_events(om, opt, value, trigger, t, &isValid);
+      refresh_rules(om, value, t);
+      if (rows) memcpy(rows + (size_t)iout * (size_t)nvalues, value, (size_t)nvalues * sizeof(double));
+      if (fired) fired[iout] = acc;
+      acc = 0;
+      iout++;
+      nstloc = 0;
+      continue;
+    }
+    if (nstloc >= (long)opt->Mxstep) { flag = ORACLE_CV_TOO_MUCH_WORK; break; }
+    flag = be->step(h, tout, y, &tdummy);
+    if (flag < 0) break;
+    flag = 0;
+    nstloc++; fresh = 0;
+    for (i = 0; i < neq; i++) yend[i] = y[i];
+    be->step_info(h, &tn, &hu);
+    rlo = tn - hu; need_check = 1;
+  }
+  free(vtmp); free(yend);
+  *piout = iout;
+  return flag;
+}
+
 static void *run_range(void *arg)
 {
   job_t *jb = (job_t *)arg;
@@ -114,6 +226,10 @@ static void *run_range(void *arg)
     }
     if (jb->status) jb->status[s] = 0;
 
+    if (opt->StepResolution < 0 && om->nevents > 0 && neq > 0 && be->step && be->dky && be->step_info) {
+      flag = run_rootfind(om, opt, be, h, value, y, trigger, rows, jb->fired ? jb->fired + (size_t)s * (size_t)(nout + 1) : NULL, &created, &iout);
+      if (jb->margin) for (i = 1; i <= nout; i++) jb->margin[(size_t)s * (size_t)(nout + 1) + (size_t)i] = INFINITY;
+    } else
     for (iout = 1; iout <= nout; iout++) {
       double tout = opt->TimePoints[iout];
       unsigned int firedmask = 0; double mg = INFINITY;
@@ -206,6 +322,9 @@ static int load_ref_backend(oracle_backend_t *be)
   be->solve = (int (*)(void *, double, double *, double *, int))dlsym(lib, "refcv_solve");
   be->stats = (void (*)(void *, long *))dlsym(lib, "refcv_stats");
   be->destroy = (void (*)(void *))dlsym(lib, "refcv_free");
+  be->step = (int (*)(void *, double, double *, double *))dlsym(lib, "refcv_step");
+  be->dky = (int (*)(void *, double, double *))dlsym(lib, "refcv_dky");
+  be->step_info = (void (*)(void *, double *, double *))dlsym(lib, "refcv_step_info");
   return be->create && be->init && be->solve && be->stats && be->destroy && be->set_stop_time;
 }
 
@@ -220,7 +339,7 @@ int oracle_integrate_batch(odeModel_t *om, const cvodeSettings_t *opt, int nsets
 
   if (!om || !opt || om->hasCycle || opt->Indefinitely || !opt->TimePoints) { snprintf(last_error, sizeof last_error, "bad model or settings"); return -1; }
   if (backend == ORACLE_BACKEND_REF) { if (!load_ref_backend(&be)) return -1; }
-  else { be.create = portcv_create; be.init = portcv_init; be.set_stop_time = portcv_set_stop_time; be.solve = portcv_solve; be.stats = portcv_stats; be.destroy = portcv_free; }
+  else { be.create = portcv_create; be.init = portcv_init; be.set_stop_time = portcv_set_stop_time; be.solve = portcv_solve; be.stats = portcv_stats; be.destroy = portcv_free; be.step = NULL; be.dky = NULL; be.step_info = NULL; }
   /* Jacobian: constructed on first use like IntegratorInstance_initializeJacobian (integratorInstance.c:291-311) */
   if (opt->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   if (rhs_mode == ORACLE_RHS_COMPILED) {

@@ -36,6 +36,10 @@ typedef struct {
   int (*solve)(void *h, double tout, double *yout, double *tret, int use_tstop);
   void (*stats)(void *h, long *stats7);
   void (*destroy)(void *h);
+  /* optional (the vendored CVODE only): one internal step, dense output at t, current time and last step size */
+  int (*step)(void *h, double tout, double *yout, double *tret);
+  int (*dky)(void *h, double t, double *yout);
+  void (*step_info)(void *h, double *tn, double *hu);
 } oracle_backend_t;
 
 void *portcv_create(int n, oracle_rhs_fn f, oracle_jac_fn jac, void *user);

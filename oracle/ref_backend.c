@@ -82,6 +82,29 @@ int refcv_solve(void *h, double tout, double *yout, double *tret, int use_tstop)
   *tret = t;
   return flag;
 }
+/* one internal step (CV_ONE_STEP), the dense output and the step geometry: what the event-location procedure of
+   driver.c (run_rootfind) drives the vendored CVODE with */
+int refcv_step(void *h, double tout, double *yout, double *tret)
+{
+  ref_t *r = (ref_t *)h; int i, flag; realtype t = 0;
+  flag = CVode(r->mem, tout, r->y, &t, CV_ONE_STEP);
+  for (i = 0; i < r->n; i++) yout[i] = NV_Ith_S(r->y, i);
+  *tret = t;
+  return flag;
+}
+int refcv_dky(void *h, double t, double *yout)
+{
+  ref_t *r = (ref_t *)h; int i, flag;
+  flag = CVodeGetDky(r->mem, t, 0, r->y);
+  for (i = 0; i < r->n; i++) yout[i] = NV_Ith_S(r->y, i);
+  return flag;
+}
+void refcv_step_info(void *h, double *tn, double *hu)
+{
+  ref_t *r = (ref_t *)h; realtype v = 0;
+  CVodeGetCurrentTime(r->mem, &v); *tn = v;
+  CVodeGetLastStep(r->mem, &v); *hu = v;
+}
 void refcv_stats(void *h, long *s)
 {
   ref_t *r = (ref_t *)h; long save[7]; int i;

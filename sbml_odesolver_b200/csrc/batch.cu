@@ -331,6 +331,7 @@ struct odesBatch {
   int nflux; CUfunction fluxKernel; double *d_flux; size_t fluxCap; float lastFluxMs; cudaEvent_t f0, f1;   /* reaction fluxes of the stored rows: [capacity][nout+1][nflux] */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
   int noEvents;                                   /* launches skip the emitted event function (single instance without event processing) */
+  int rootFind;                                   /* StepResolution < 0: events located inside the steps (warp kernel) */
   int stepRes;                                    /* cvodeSettings_t.StepResolution: solver / event grid points per print step */
   /* pinned staging ring for results that go to PAGEABLE caller memory (the reference-shaped entries hand in malloc'd arrays) */
   char *stage; size_t stageSlotBytes; int stageSlots; cudaEvent_t stageEv[8];
@@ -422,6 +423,7 @@ static std::string build_source(odesBatch_t *b)
   if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
   if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
   if (b->opt->CvodeMethod == 1 || b->opt->IterMethod == 1) warp = 1;       /* and so do Adams-Moulton and functional iteration */
+  if (b->rootFind) warp = 1;                    /* ... and the event location inside the steps */
   if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
   b->warpMode = warp;
   if (warp) {
@@ -434,8 +436,8 @@ static std::string build_source(odesBatch_t *b)
     if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[640];
-    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d -DODES_WLOCK=%d -DODES_WJE=%d -DODES_WDAG=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0), env_int("ODES_WLOCK", (b->nsens > 0 && slabs > 4) ? 1 : 0), env_int("ODES_WJE", -1), env_int("ODES_WDAG", -1),
+    snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d -DODES_WLOCK=%d -DODES_WJE=%d -DODES_WDAG=%d%s\n",
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0), env_int("ODES_WLOCK", (b->nsens > 0 && slabs > 4) ? 1 : 0), env_int("ODES_WJE", -1), env_int("ODES_WDAG", -1),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
@@ -504,6 +506,15 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
      to has no recoverable right-hand-side failures (its RhsFn returns void), so there is no reference arithmetic to reproduce:
      the switch is refused instead of being ignored */
   if (opt->DetectNegState) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "DetectNegState is not supported by the batched integrator (no recoverable right-hand-side failures); unset it with CvodeSettings_setDetectNegState(set, 0)"); return NULL; }
+  if (opt->StepResolution < 0) {
+    /* event location inside the steps: warp-per-trajectory kernel, plain BDF / Newton run */
+    const char *why = NULL;
+    if (opt->HaltOnEvent || opt->SteadyState) why = "the halting modes";
+    else if (opt->Sensitivity) why = "sensitivity analysis";
+    else if (opt->SetTStop || om->npiecewise) why = "the stop-time mode (SetTStop, piecewise models)";
+    else if (om->neq < 1 || om->neq > 32 || !opt->UseJacobian) why = "models outside 1..32 equations or without the analytic Jacobian";
+    if (why) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "StepResolution < 0 (events located inside the steps) cannot be combined with %s", why); return NULL; }
+  }
   if (opt->StepResolution > 1 && (opt->HaltOnEvent || opt->SteadyState)) {
     SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "StepResolution > 1 keeps rows at the print steps only: it cannot be combined with HaltOnEvent or HaltOnSteadyState (the halting row may fall between print steps)");
     return NULL;
@@ -511,6 +522,7 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
   odesBatch_t *b = new odesBatch();
   b->om = om; b->opt = opt; b->device = device; b->nvary = nvary; b->nout = opt->PrintStep;
   b->stepRes = opt->StepResolution > 1 ? opt->StepResolution : 1;
+  b->rootFind = (opt->StepResolution < 0 && om->nevents > 0) ? 1 : 0;
   b->nvalues = om->neq + om->nass + om->nconst;
   for (int j = 0; j < nvary; j++) {
     if (varyIndex[j] < 0 || varyIndex[j] >= b->nvalues) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "varied index %d out of range", varyIndex[j]); delete b; return NULL; }

@@ -1155,6 +1155,15 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
     for (i = om->neq; i < om->neq + om->nass; i++) if (k.slot[i] >= 0) cbprintf(b, "  pv[%d] = a[%d];\n", k.slot[i], i - om->neq);
   }
   CharBuffer_append(b, "  return fired;\n}\n");
+  /* trigger_f: the truth values of all event triggers at (t, y) as a bit mask, evaluated like event_f evaluates them but
+     without assignments and without touching the trigger state (event location inside a step, ODES_ROOTFIND) */
+  CharBuffer_append(b, "DEV unsigned int trigger_f(double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n"
+                       "  unsigned int m = 0; double a[A1(NASS)]; (void)t; (void)a; (void)y; (void)pv;\n");
+  if (om->nevents > 0) {
+    emit_refresh_all(b, om, &c, "  ");
+    for (e = 0; e < om->nevents; e++) { CharBuffer_append(b, "  if (("); gen(b, om->event[e], &c); cbprintf(b, ") != 0.0) m |= %uu;\n", 1u << e); }
+  }
+  CharBuffer_append(b, "  return m;\n}\n");
 
   /* store_row: refresh all rules, write the selected values (coalesced: consecutive sets are consecutive addresses) */
   CharBuffer_append(b, "DEV void store_row(double *__restrict__ row, size_t stride, double t, const double (&y)[A1(NEQ)], const PvRef pv)\n{\n  double a[A1(NASS)]; (void)t; (void)a; (void)pv; (void)y;\n");

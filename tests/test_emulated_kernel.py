@@ -120,6 +120,48 @@ def test_emulated_step_resolution(monkeypatch, warp):
     b.close()
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref/libcvode_ref.so not built")
+def test_emulated_event_location_inside_steps():
+    """StepResolution < 0: events are LOCATED inside the internal steps (north star: "per-system event root-finding").  After
+    every step the triggers are evaluated at the step's end, a trigger that became true is traced back by bisection on the
+    dense output to CVODE's root tolerance 100 uround (|tn| + |hu|), the event is applied there with the reference's event
+    semantics and the solver restarts.  The checker drives the reference's vendored CVODE through the same procedure step by
+    step (CV_ONE_STEP + CVodeGetDky, oracle/driver.c: run_rootfind): rows, event masks and work counters are bit-identical;
+    and the decay S1' = -S1 with "S1 < 0.1 -> S1 = 1" now resets at t = ln 10 instead of at the next print step."""
+    import ctypes as C
+    nout = 100
+    m = so.Model(H.model_path("two_events_one_assignment.xml"))
+    vary = [m.index("S1"), m.index("S2")]
+    vals = np.array([[1.0, 0.0], [1.7, 0.3], [0.6, 0.1], [0.9, 0.25]])
+    opt = so.settings(10.0, nout, 1e-9, 1e-6)
+    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1           # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    b = so.Batch(m, opt, vary)
+    head = b.source().split("\n")[0]
+    assert "-DODES_ROOTFIND=1" in head and "-DODES_WARP=1" in head
+    tp = H.tpoints(opt, nout)
+    base, trig = b.base_values()
+    got = H.Emu(b, "events_rootfind").run(base, trig, vals, tp, 10000, 1e-6, 1e-9)
+    ref = H.oracle_run(m, opt, vary, vals, nout, backend=H.REF, compiled_so=H.compile_c_model(m, "events"))
+    b.close()
+    assert (got["status"] == 0).all() and (ref["status"] == 0).all()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)))
+    assert np.array_equal(got["fired"].T, ref["fired"]) and ref["fired"].any()
+    assert np.array_equal(got["stats"].T, ref["stats"])
+    # set 0 starts at S1 = 1: the reset happens at ln 10 = 2.3026, so the row at t = 2.4 holds exp(-(2.4 - ln 10))
+    k = int(np.searchsorted(tp, np.log(10.0)))
+    assert abs(got["out"][k, 0, 0] - np.exp(-(tp[k] - np.log(10.0)))) < 1e-4
+    # with the reference's semantics the same row holds the freshly reset value
+    opt0 = so.settings(10.0, nout, 1e-9, 1e-6)
+    plain = H.oracle_run(m, opt0, vary, vals[:1], nout, backend=H.REF, compiled_so=H.compile_c_model(m, "events"))
+    assert plain["out"][0, k, 0] == 1.0
+    # what the mode cannot be combined with is refused at plan creation
+    opt_h = so.settings(10.0, nout, 1e-9, 1e-6, halt_on_event=1)
+    C.cast(opt_h, C.POINTER(C.c_int * 4)).contents[3] = -1
+    with pytest.raises(so.OdesError):
+        so.Batch(m, opt_h, vary)
+    so.lib().SolverError_clear()
+
+
 def test_generated_source_has_single_hot_instances():
     """The block pipeline keeps one instance of the model functions in the instruction stream of the hot loop."""
     w = H.workload("mapk", nout=10)

@@ -577,3 +577,26 @@ def test_single_instance_without_event_processing():
     assert L.IntegratorInstance_integrateOneStep(ii) == 1                  # with events: S1 < 0.1 fires and S1 is set back to 1
     assert abs(L.IntegratorInstance_getVariableValue(ii, vi) - 1.0) < 1e-12
     L.IntegratorInstance_free(ii)
+
+
+def test_event_location_inside_steps_on_gpu():
+    """StepResolution < 0 on the device (see tests/test_emulated_kernel.py::test_emulated_event_location_inside_steps): rows,
+    event masks and work counters of 512 sets bit-identical to the vendored CVODE driven step by step through the same
+    location procedure."""
+    nout = 50
+    w = H.workload("events", nout=nout)
+    m = w["model"]
+    vals = H.workload_values(w, 512, seed=9)
+    opt = so.settings(w["end"], nout, w["atol"], w["rtol"])
+    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1
+    b = so.Batch(m, opt, w["vary"])
+    assert "-DODES_ROOTFIND=1" in b.source().split("\n")[0]
+    b.set_values(vals)
+    b.integrate(512)
+    out, fired, st, stats = b.results(512), b.event_log(512), b.status(512), b.stats(512).T
+    b.close()
+    ref = H.oracle_run(m, opt, w["vary"], vals, nout, backend=H.REF, compiled_so=H.compile_c_model(m, "events"), threads=8)
+    assert (st == 0).all() and (ref["status"] == 0).all()
+    assert np.array_equal(out, np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    assert np.array_equal(fired.T, ref["fired"]) and ref["fired"].any()
+    assert np.array_equal(stats, ref["stats"])
