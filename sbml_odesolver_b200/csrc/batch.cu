@@ -423,7 +423,6 @@ static std::string build_source(odesBatch_t *b)
   if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
   if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
   if (b->opt->CvodeMethod == 1 || b->opt->IterMethod == 1) warp = 1;       /* and so do Adams-Moulton and functional iteration */
-  if (b->rootFind) warp = 1;                    /* ... and the event location inside the steps */
   if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
   b->warpMode = warp;
   if (warp) {
@@ -461,8 +460,8 @@ static std::string build_source(odesBatch_t *b)
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   b->maxBlocksPerSM = (la == 2) ? 512 / tmemCols : 32;
   char head[640];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
-           env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->block, b->minblocks, b->matLocal,
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
+           env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->block, b->minblocks, b->matLocal,
            env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
@@ -507,12 +506,11 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
      the switch is refused instead of being ignored */
   if (opt->DetectNegState) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "DetectNegState is not supported by the batched integrator (no recoverable right-hand-side failures); unset it with CvodeSettings_setDetectNegState(set, 0)"); return NULL; }
   if (opt->StepResolution < 0) {
-    /* event location inside the steps: warp-per-trajectory kernel, plain BDF / Newton run */
+    /* event location inside the steps: either layout, plain run without halting, sensitivities or the stop-time mode */
     const char *why = NULL;
     if (opt->HaltOnEvent || opt->SteadyState) why = "the halting modes";
     else if (opt->Sensitivity) why = "sensitivity analysis";
     else if (opt->SetTStop || om->npiecewise) why = "the stop-time mode (SetTStop, piecewise models)";
-    else if (om->neq < 1 || om->neq > 32 || !opt->UseJacobian) why = "models outside 1..32 equations or without the analytic Jacobian";
     if (why) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "StepResolution < 0 (events located inside the steps) cannot be combined with %s", why); return NULL; }
   }
   if (opt->StepResolution > 1 && (opt->HaltOnEvent || opt->SteadyState)) {

@@ -87,6 +87,12 @@
 #ifndef ODES_STEPRES
 #define ODES_STEPRES 1
 #endif
+/* StepResolution < 0: events are LOCATED inside the internal steps (the procedure is described at the
+   warp kernel's integrate_warp and mirrored by oracle/driver.c: run_rootfind) */
+#ifndef ODES_ROOTFIND
+#define ODES_ROOTFIND 0
+#endif
+#define ODES_ROOTS (ODES_ROOTFIND && NEVENTS > 0 && NEQ > 0)
 #define ODES_ROWS(a) ((size_t)((a).nout / ODES_STEPRES + 1))
 #define ODES_ROW(iout) ((size_t)((iout) / ODES_STEPRES))
 #define ODES_KEEP(iout) (ODES_STEPRES == 1 || (iout) % ODES_STEPRES == 0)
@@ -140,6 +146,7 @@ __device__ __forceinline__ unsigned long long odes_take_sets(unsigned long long 
 #define ST_OUTPUT 6     /* output rows covered by the last step */
 #define ST_DONE 7       /* no trajectory (idle lane) */
 #define ST_FINISH 8     /* trajectory ended (grid done, failure, halt on event): write status, counters, NaN rows */
+#define ST_ROOT 9       /* event location (ODES_ROOTFIND): triggers at the end of the step just completed, bisection on the dense output */
 /* why the right-hand side is being evaluated */
 #define FW_ATTEMPT 0    /* f(tn, predicted z0) at the start of the nonlinear solve */
 #define FW_NEWTON 1     /* f(tn, y) inside the Newton iteration */
@@ -1545,6 +1552,10 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
   double t = 0.0, tout = 0.0;
   int status = 0, iout = 1, idle = 0;
   unsigned int firedacc = 0u;             /* events fired since the last kept row (StepResolution) */
+#if ODES_ROOTS
+  bool pending = false;                   /* an event has been located at troot <= tn and waits for the rows before it */
+  double troot = 0.0, rlo = 0.0;          /* its time; lower end of the interval still to be searched */
+#endif
   size_t set = 0;
   bool exhausted = false;
   s.st = ST_DONE;
@@ -1602,6 +1613,9 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
             model_init(yl, pv, a.vary, stride, set);
             store_row0(a.out + set * ODES_ROWS(a) * NSTORE, 1, yl, pv);
             firedacc = 0u;
+#if ODES_ROOTS
+            pending = false;
+#endif
             if (a.fired) a.fired[set] = 0u;
             /* static assigned values (rules not recomputed before the ODEs) for this trajectory's inputs */
             double atmp[A1(NASS)];
@@ -1628,6 +1642,9 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       const bool act = (s.st == ST_START);
       PROF(1, act);
       if (act) {
+#if ODES_ROOTS
+        pending = false;
+#endif
         s.reinit(t);
         tout = a.tpoints[iout];
 #if USE_TSTOP
@@ -1700,9 +1717,43 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       const bool act = (s.st == ST_COMPLETE);
       PROF(6, act);
       s.blk_complete(act, tout);
+#if ODES_ROOTS
+      if (act) { rlo = s.tn - s.hu; s.st = ST_ROOT; }
+#else
       if (act && s.after_step(tout, t)) s.st = ST_OUTPUT;
+#endif
       ODES_WARP_SYNC();
     }
+#if ODES_ROOTS
+    /* ---- ROOT: which triggers became true over the last step, and where (first crossing in (rlo, tn]) ---- */
+    if (ODES_WARP_ANY(s.st == ST_ROOT)) {
+      const bool act = (s.st == ST_ROOT);
+      double pvl[A1(NPVP)];
+      la_load<NPVCH>(la, LAPV, pvl);
+      PvRef pv; pv.p = pvl; pv.s = 1u;
+      if (act) {
+        double yl[A1(NEQ)];
+        unsigned int known = 0u;
+        _Pragma("unroll") for (int e = 0; e < NEVENTS; e++) if (trigger[e]) known |= 1u << e;
+        FORI yl[i] = ZN(0, i);
+        const unsigned int cand = trigger_f(s.tn, yl, pv) & ~known;
+        if (cand) {
+          double lo = rlo, hi = s.tn;
+          const double ttol = 100.0 * UROUND * (fabs(s.tn) + fabs(s.hu));
+          _Pragma("unroll 1") for (int it = 0; it < 200 && (hi - lo) > ttol; it++) {
+            const double mid = lo + 0.5 * (hi - lo);
+            (void)s.get_dky0(mid);
+            FORI yl[i] = YV(i);
+            if (trigger_f(mid, yl, pv) & cand) hi = mid; else lo = mid;
+          }
+          troot = hi; pending = true;
+        }
+        s.ydone = 0;                                     /* y has served as scratch */
+        s.st = (s.after_step(tout, t) || pending) ? ST_OUTPUT : ST_PRE;
+      }
+      ODES_WARP_SYNC();
+    }
+#endif
 #else
     if (s.st != ST_DONE && s.st != ST_FINISH) { t = a.tpoints[iout]; s.st = ST_OUTPUT; }
 #endif
@@ -1724,6 +1775,26 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       bool wrote = false;
       while (s.st == ST_OUTPUT) {
         double yl[A1(NEQ)];
+#if ODES_ROOTS
+        {
+          const bool reached = (s.tn - tout) * s.h >= 0.0;
+          if (pending && (!reached || troot <= tout)) {
+            /* the located event: state at troot from the dense output, the reference's event handling there */
+            int re = 0;
+            (void)s.get_dky0(troot);
+            FORI yl[i] = YV(i);
+            const unsigned int fm = a.pad ? 0u : event_f(troot, yl, pv, trigger, re);
+            firedacc |= fm;
+            if (fm) wrote = true;
+            pending = false;
+            if (re) { FORI YV(i) = yl[i]; t = troot; s.st = ST_START; }        /* restart from the located time */
+            else { rlo = troot; s.st = ST_ROOT; }                              /* later crossings of the same step */
+            break;
+          }
+          if (!reached) { s.st = ST_PRE; break; }
+          t = tout;
+        }
+#endif
 #if NEQ > 0
         if (!s.ydone) (void)s.get_dky0(t);
         s.ydone = 0;
@@ -1758,7 +1829,11 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
 #endif
         const int r = s.next_call(tout, t);
         if (r < 0) { status = r; s.st = ST_FINISH; break; }
+#if ODES_ROOTS
+        if (r == 0 && !pending) s.st = ST_PRE;      /* a located event before the next output time is handled at the loop's head */
+#else
         if (r == 0) s.st = ST_PRE;
+#endif
 #else
         t = a.tpoints[iout];
 #endif

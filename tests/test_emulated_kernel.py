@@ -121,14 +121,16 @@ def test_emulated_step_resolution(monkeypatch, warp):
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref/libcvode_ref.so not built")
-def test_emulated_event_location_inside_steps():
+@pytest.mark.parametrize("warp", [0, 1])
+def test_emulated_event_location_inside_steps(monkeypatch, warp):
     """StepResolution < 0: events are LOCATED inside the internal steps (north star: "per-system event root-finding").  After
     every step the triggers are evaluated at the step's end, a trigger that became true is traced back by bisection on the
     dense output to CVODE's root tolerance 100 uround (|tn| + |hu|), the event is applied there with the reference's event
-    semantics and the solver restarts.  The checker drives the reference's vendored CVODE through the same procedure step by
+    semantics and the solver restarts -- in both layouts.  The checker drives the reference's vendored CVODE through the same procedure step by
     step (CV_ONE_STEP + CVodeGetDky, oracle/driver.c: run_rootfind): rows, event masks and work counters are bit-identical;
     and the decay S1' = -S1 with "S1 < 0.1 -> S1 = 1" now resets at t = ln 10 instead of at the next print step."""
     import ctypes as C
+    monkeypatch.setenv("ODES_WARP", str(warp))
     nout = 100
     m = so.Model(H.model_path("two_events_one_assignment.xml"))
     vary = [m.index("S1"), m.index("S2")]
@@ -137,10 +139,10 @@ def test_emulated_event_location_inside_steps():
     C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1           # struct cvodeSettings: double Time; int PrintStep; int StepResolution
     b = so.Batch(m, opt, vary)
     head = b.source().split("\n")[0]
-    assert "-DODES_ROOTFIND=1" in head and "-DODES_WARP=1" in head
+    assert "-DODES_ROOTFIND=1" in head and ("-DODES_WARP=1" in head) == bool(warp)
     tp = H.tpoints(opt, nout)
     base, trig = b.base_values()
-    got = H.Emu(b, "events_rootfind").run(base, trig, vals, tp, 10000, 1e-6, 1e-9)
+    got = H.Emu(b, f"events_rootfind{warp}").run(base, trig, vals, tp, 10000, 1e-6, 1e-9)
     ref = H.oracle_run(m, opt, vary, vals, nout, backend=H.REF, compiled_so=H.compile_c_model(m, "events"))
     b.close()
     assert (got["status"] == 0).all() and (ref["status"] == 0).all()

@@ -579,10 +579,12 @@ def test_single_instance_without_event_processing():
     L.IntegratorInstance_free(ii)
 
 
-def test_event_location_inside_steps_on_gpu():
+@pytest.mark.parametrize("warp", [0, 1])
+def test_event_location_inside_steps_on_gpu(monkeypatch, warp):
     """StepResolution < 0 on the device (see tests/test_emulated_kernel.py::test_emulated_event_location_inside_steps): rows,
     event masks and work counters of 512 sets bit-identical to the vendored CVODE driven step by step through the same
     location procedure."""
+    monkeypatch.setenv("ODES_WARP", str(warp))
     nout = 50
     w = H.workload("events", nout=nout)
     m = w["model"]
@@ -590,7 +592,8 @@ def test_event_location_inside_steps_on_gpu():
     opt = so.settings(w["end"], nout, w["atol"], w["rtol"])
     C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1
     b = so.Batch(m, opt, w["vary"])
-    assert "-DODES_ROOTFIND=1" in b.source().split("\n")[0]
+    head = b.source().split("\n")[0]
+    assert "-DODES_ROOTFIND=1" in head and ("-DODES_WARP=1" in head) == bool(warp)
     b.set_values(vals)
     b.integrate(512)
     out, fired, st, stats = b.results(512), b.event_log(512), b.status(512), b.stats(512).T
