@@ -105,6 +105,35 @@ def test_emulated_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets
     assert set(np.unique(got["sens"][:, 0])) <= {0.0, 1.0}
 
 
+@needs_ref
+def test_emulated_step_resolution_with_sensitivities():
+    """StepResolution = k together with forward sensitivities (events re-initialise solver and sensitivities at every
+    sub-step where they fire): kept rows of states AND sensitivities are rows k, 2k, ... of the vendored CVODES on the
+    refined grid, bit for bit."""
+    import ctypes as C
+    k, nout, ids = 3, 20, ["S1", "compartment", "S2"]
+    w = H.workload("events", nout=nout, sensitivity=1, sens_ids=ids)
+    m = w["model"]
+    vals = H.workload_values(w, 6, seed=4)
+    C.cast(w["opt"], C.POINTER(C.c_int * 4)).contents[3] = k          # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    assert "-DODES_STEPRES=3" in b.source().split("\n")[0] and b.nsens == 3
+    tp = H.tpoints(w["opt"], nout)
+    grid = np.array([tp[i] if j == 0 else tp[i] + j * ((tp[i + 1] - tp[i]) / k) for i in range(nout) for j in range(k)] + [tp[-1]])
+    base, trig = b.base_values()
+    got = H.Emu(b, "events_sens_stepres").run(base, trig, vals, grid, 10000, w["rtol"], w["atol"], stepres=k)
+    w2 = H.workload("events", nout=nout * k, sensitivity=1, sens_ids=ids)
+    arr = (C.c_double * (len(grid) - 1))(*grid[1:])
+    assert so.lib().CvodeSettings_setTimeSeries(w2["opt"], arr, len(grid) - 1) == 1
+    b2 = so.Batch(m, w2["opt"], w2["vary"], store=list(range(m.neq)))
+    ref = H.sens_ref_run(m, w2["opt"], b2, w2["vary"], vals, grid, 10000, w["rtol"], w["atol"], tag="events_sens")
+    b.close(); b2.close()
+    assert ref["fired"].any()
+    assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"][:, ::k])
+    assert np.array_equal(got["sens"], ref["sens"][:, ::k])
+    assert np.array_equal(got["stats"].T, ref["stats"][:, :7])
+
+
 FORMS = {"rows": dict(ODES_WJE="0"), "shapes": dict(ODES_WJE="1", ODES_WDAG="0"), "dag": dict(ODES_WJE="1", ODES_WDAG="1")}
 
 
