@@ -331,7 +331,7 @@ struct odesBatch {
   int nflux; CUfunction fluxKernel; double *d_flux; size_t fluxCap; float lastFluxMs; cudaEvent_t f0, f1;   /* reaction fluxes of the stored rows: [capacity][nout+1][nflux] */
   odeSense_t *os; int nsens; double *d_sens;      /* forward sensitivities (opt->Sensitivity): [capacity][nout+1][nsens][neq] */
   int noEvents;                                   /* launches skip the emitted event function (single instance without event processing) */
-  int rootFind;                                   /* StepResolution < 0: events located inside the steps (warp kernel) */
+  int rootFind;                                   /* StepResolution < 0: events located inside the steps (both kernels) */
   int stepRes;                                    /* cvodeSettings_t.StepResolution: solver / event grid points per print step */
   /* pinned staging ring for results that go to PAGEABLE caller memory (the reference-shaped entries hand in malloc'd arrays) */
   char *stage; size_t stageSlotBytes; int stageSlots; cudaEvent_t stageEv[8];
