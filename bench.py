@@ -194,6 +194,26 @@ def other_config_line(H, so, name, n, fp64_peak, cores, device):
     return line
 
 
+def scaled_config_line(H, so, name, n, device, world, rank, barrier, max_over_ranks):
+    """BASELINE configs[4] "at 2/4/8 GPUs": every rank integrates n sets of the configuration on its GPU (range sharding, no
+    collective); trajectories/s of the whole job from the slowest rank's device time.  Parity of this configuration is
+    checked at N = 1 (other_configs)."""
+    w = H.workload(name)
+    m = w["model"]
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)), device=device)
+    vals = H.workload_values(w, n, seed=77 + rank)
+    b.set_values(vals)
+    b.integrate(n)
+    barrier()
+    ms = max_over_ranks(min(b.integrate(n) for _ in range(2)))
+    failed = int((b.status(n) != 0).sum())
+    info = b.kernel_info()
+    warp = "-DODES_WARP=1" in b.source().split("\n")[0]
+    b.close()
+    return {"workload": name, "baseline_config": "configs[4]", "sets_per_gpu": n, "n_gpus": world, "value": world * n / (ms * 1e-3), "unit": UNIT,
+            "kernel_ms_max_over_ranks": ms, "failed_sets_rank0": failed, "layout": "warp per trajectory" if warp else "trajectory per lane", "kernel_info": info}
+
+
 def entry_leg(H, so, L, w, n, steps):
     """The reference-shaped one-shot entry: IntegratorInstance_integrateBatch with the caller's malloc'd (pageable) arrays and
     ALL model values per row (what the reference's batch loop stores per design point, src/odeSolver.c:313-330)."""
@@ -482,6 +502,11 @@ def main():
                 extra["e2e_entry"] = entry_leg(H, so, L, w, args.entry_sets, max(1, min(args.steps, 3)))
             extra["other_configs"] = [other_config_line(H, so, nm, 100_000, fp64_peak, cores, local) for nm in ("repressilator", "events", "huang", "goodwin")]
             extra["fmad_variant"] = fmad_variant(H, so, L, w, n, fp64_peak, local, cores)
+        if world > 1:
+            # config 5 on all GPUs of the job (every rank takes part)
+            line5 = scaled_config_line(H, so, "huang", 100_000, local, world, rank, barrier, max_over_ranks)
+            if rank == 0:
+                extra["other_configs"] = [line5]
     barrier()
     if rank == 0:
         Ff, FJ = count_ops(b.source())
