@@ -50,6 +50,11 @@ void CvodeSettings_setError(cvodeSettings_t *, double);
 void CvodeSettings_setRError(cvodeSettings_t *, double);
 void CvodeSettings_setMxstep(cvodeSettings_t *, int);
 void CvodeSettings_setDetectNegState(cvodeSettings_t *, int);
+/* cvodeSettings_t.StepResolution (reference integratorSettings.h:61-63: a documented field without a setter): 1 events at the
+   output times (the reference's behaviour); k > 1: k sub-steps per print step; k < 0: events located inside the internal steps
+    */
+void CvodeSettings_setStepResolution(cvodeSettings_t *, int);
+int CvodeSettings_getStepResolution(const cvodeSettings_t *);
 void CvodeSettings_setTStop(cvodeSettings_t *, int);
 void CvodeSettings_setCompileFunctions(cvodeSettings_t *, int);
 void CvodeSettings_setMethod(cvodeSettings_t *, int, int);

@@ -69,6 +69,7 @@ _SIGS = {
     "CvodeSettings_setTStop": (None, [c_p, c_i]), "CvodeSettings_setJacobian": (None, [c_p, c_i]),
     "CvodeSettings_setErrors": (None, [c_p, c_d, c_d, c_i]),
     "CvodeSettings_setHaltOnSteadyState": (None, [c_p, c_i]), "CvodeSettings_setSteadyStateThreshold": (None, [c_p, c_d]),
+    "CvodeSettings_setStepResolution": (None, [c_p, c_i]), "CvodeSettings_getStepResolution": (c_i, [c_p]),
     "IntegratorInstance_create": (c_p, [c_p, c_p]), "IntegratorInstance_free": (None, [c_p]),
     "IntegratorInstance_integrate": (c_i, [c_p]), "IntegratorInstance_integrateOneStep": (c_i, [c_p]),
     "IntegratorInstance_timeCourseCompleted": (c_i, [c_p]), "IntegratorInstance_getTime": (c_d, [c_p]),
@@ -223,7 +224,7 @@ class Model:
 
 
 def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, halt_on_event=0, store_results=1, steady_state=0, ss_threshold=None,
-             sensitivity=0, sens_ids=None, sens_method=0, method=0, iter_method=0):
+             sensitivity=0, sens_ids=None, sens_method=0, method=0, iter_method=0, step_resolution=None):
     """CvodeSettings_createWith(Time, PrintStep, Error, RError, Mxstep, Method (0 BDF, 1 Adams-Moulton), Iter=Newton, ...).
     sensitivity=1 switches forward sensitivity analysis on (sens_method 0: simultaneous corrector, 1: staggered); sens_ids: ids of the parameters /
     variables (CvodeSettings_setSensParams), None = all constants of the model."""
@@ -234,6 +235,8 @@ def settings(end_time, print_step, atol, rtol, mxstep=10000, use_jacobian=1, hal
         lib().CvodeSettings_setSensParams(opt, arr, len(sens_ids))
     if ss_threshold is not None:
         lib().CvodeSettings_setSteadyStateThreshold(opt, ss_threshold)
+    if step_resolution is not None:
+        lib().CvodeSettings_setStepResolution(opt, step_resolution)      # k > 1: sub-steps per print step; k < 0: events located inside the steps
     return opt
 
 

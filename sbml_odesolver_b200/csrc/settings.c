@@ -107,6 +107,8 @@ void CvodeSettings_setError(cvodeSettings_t *s, double v) { s->Error = v; }
 void CvodeSettings_setRError(cvodeSettings_t *s, double v) { s->RError = v; }
 void CvodeSettings_setMxstep(cvodeSettings_t *s, int v) { s->Mxstep = v; }
 void CvodeSettings_setDetectNegState(cvodeSettings_t *s, int v) { s->DetectNegState = v; }
+void CvodeSettings_setStepResolution(cvodeSettings_t *s, int v) { s->StepResolution = (v == 0) ? 1 : v; }
+int CvodeSettings_getStepResolution(const cvodeSettings_t *s) { return s->StepResolution; }
 void CvodeSettings_setTStop(cvodeSettings_t *s, int v) { s->SetTStop = v; }
 void CvodeSettings_setCompileFunctions(cvodeSettings_t *s, int v) { s->compileFunctions = v; }
 void CvodeSettings_setMethod(cvodeSettings_t *s, int m, int maxord)

@@ -100,7 +100,7 @@ def test_emulated_step_resolution(monkeypatch, warp):
     vary = [m.index("S1"), m.index("S2")]
     vals = np.array([[1.0, 0.0], [1.7, 0.3], [0.6, 0.1], [0.9, 0.25]])
     opt = so.settings(10.0, nout, 1e-9, 1e-6)
-    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = k            # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    so.lib().CvodeSettings_setStepResolution(opt, k)
     b = so.Batch(m, opt, vary)
     assert "-DODES_STEPRES=4" in b.source().split("\n")[0]
     tp = H.tpoints(opt, nout)
@@ -136,7 +136,7 @@ def test_emulated_event_location_inside_steps(monkeypatch, warp):
     vary = [m.index("S1"), m.index("S2")]
     vals = np.array([[1.0, 0.0], [1.7, 0.3], [0.6, 0.1], [0.9, 0.25]])
     opt = so.settings(10.0, nout, 1e-9, 1e-6)
-    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1           # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    so.lib().CvodeSettings_setStepResolution(opt, -1)
     b = so.Batch(m, opt, vary)
     head = b.source().split("\n")[0]
     assert "-DODES_ROOTFIND=1" in head and ("-DODES_WARP=1" in head) == bool(warp)
@@ -158,7 +158,7 @@ def test_emulated_event_location_inside_steps(monkeypatch, warp):
     assert plain["out"][0, k, 0] == 1.0
     # what the mode cannot be combined with is refused at plan creation
     opt_h = so.settings(10.0, nout, 1e-9, 1e-6, halt_on_event=1)
-    C.cast(opt_h, C.POINTER(C.c_int * 4)).contents[3] = -1
+    so.lib().CvodeSettings_setStepResolution(opt_h, -1)
     with pytest.raises(so.OdesError):
         so.Batch(m, opt_h, vary)
     so.lib().SolverError_clear()

@@ -528,7 +528,7 @@ def test_step_resolution_refines_event_detection(monkeypatch, warp):
     m = w["model"]
     vals = H.workload_values(w, 256, seed=5)
     opt_k = so.settings(w["end"], w["nout"], w["atol"], w["rtol"])
-    C.cast(opt_k, C.POINTER(C.c_int * 4)).contents[3] = k          # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    so.lib().CvodeSettings_setStepResolution(opt_k, k)
     b = so.Batch(m, opt_k, w["vary"])
     assert ("-DODES_WARP=1" in b.source().split("\n")[0]) == bool(warp)
     b.set_values(vals)
@@ -553,7 +553,7 @@ def test_step_resolution_refines_event_detection(monkeypatch, warp):
     assert not np.array_equal(coarse, out, equal_nan=True)
     # halting modes are refused with StepResolution > 1
     opt_h = so.settings(w["end"], w["nout"], w["atol"], w["rtol"], halt_on_event=1)
-    C.cast(opt_h, C.POINTER(C.c_int * 4)).contents[3] = k
+    so.lib().CvodeSettings_setStepResolution(opt_h, k)
     with pytest.raises(so.OdesError):
         so.Batch(m, opt_h, w["vary"])
     L.SolverError_clear()
@@ -590,7 +590,7 @@ def test_event_location_inside_steps_on_gpu(monkeypatch, warp):
     m = w["model"]
     vals = H.workload_values(w, 512, seed=9)
     opt = so.settings(w["end"], nout, w["atol"], w["rtol"])
-    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = -1
+    so.lib().CvodeSettings_setStepResolution(opt, -1)
     b = so.Batch(m, opt, w["vary"])
     head = b.source().split("\n")[0]
     assert "-DODES_ROOTFIND=1" in head and ("-DODES_WARP=1" in head) == bool(warp)

@@ -115,7 +115,7 @@ def test_emulated_step_resolution_with_sensitivities():
     w = H.workload("events", nout=nout, sensitivity=1, sens_ids=ids)
     m = w["model"]
     vals = H.workload_values(w, 6, seed=4)
-    C.cast(w["opt"], C.POINTER(C.c_int * 4)).contents[3] = k          # struct cvodeSettings: double Time; int PrintStep; int StepResolution
+    so.lib().CvodeSettings_setStepResolution(w["opt"], k)
     b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
     assert "-DODES_STEPRES=3" in b.source().split("\n")[0] and b.nsens == 3
     tp = H.tpoints(w["opt"], nout)

@@ -9,7 +9,7 @@ w = H.workload("events")
 vals = H.workload_values(w, n, seed=77)
 for label, k in (("output times (reference semantics)", 1), ("StepResolution 4", 4), ("located inside the steps (StepResolution -1)", -1)):
     opt = so.settings(w["end"], w["nout"], w["atol"], w["rtol"])
-    C.cast(opt, C.POINTER(C.c_int * 4)).contents[3] = k
+    so.lib().CvodeSettings_setStepResolution(opt, k)
     b = so.Batch(w["model"], opt, w["vary"])
     b.set_values(vals); b.integrate(n)
     ms = min(b.integrate(n) for _ in range(2))

@@ -19,7 +19,7 @@ run("mapk", 64, 10, sensitivity=1, sens_ids=["K1", "Ki", "MAPK"])
 run("repressilator", 32, 20, sensitivity=1, sens_ids=["alpha", "beta", "x1"])
 run("goodwin", 32, 10, sensitivity=1)
 w = H.workload("events", nout=20)
-C.cast(w["opt"], C.POINTER(C.c_int * 4)).contents[3] = 3
+so.lib().CvodeSettings_setStepResolution(w["opt"], 3)
 b = so.Batch(w["model"], w["opt"], w["vary"]); b.set_values(H.workload_values(w, 100, seed=1)); b.integrate(100); b.results(100); b.close(); print("stepres ok")
 w = H.workload("mapk", nout=10); m = w["model"]
 ii = L.IntegratorInstance_create(m.om, w["opt"])
