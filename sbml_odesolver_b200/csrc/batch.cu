@@ -412,6 +412,15 @@ static std::string build_source(odesBatch_t *b)
   const int nsjw = usejac ? b->om->sparsesize : neq * np;
   b->laWords = neq * np + 8 * ((nsjw + 7) / 8) + 8 * ((npv + 7) / 8);
   int tmemCols = 32; while (tmemCols < 2 * b->laWords) tmemCols *= 2;
+  /* small models: when the saved Jacobian's non-zeros and the constants TOGETHER need fewer chunks than each padded on its
+     own, and that halves the tensor-memory columns of a lane, they share their chunks (ODES_LA_PACKED in the kernel text):
+     Goodwin 72 -> 64 words = 128 instead of 256 columns, which admits a third resident block per SM */
+  int packed = 0;
+  if (usejac) {
+    const int pk = neq * np + 8 * ((nsjw + npv + 7) / 8);
+    int pkCols = 32; while (pkCols < 2 * pk) pkCols *= 2;
+    if (env_int("ODES_LA_PACKED", 1) && pkCols < tmemCols && pkCols <= 512) { packed = 1; b->laWords = pk; tmemCols = pkCols; }
+  }
   int la = env_int("ODES_LA", -1);
   if (la < 0) la = (tmemCols <= 512 && neq > 0) ? 2 : ((size_t)(chipWords + b->laWords) * 8 * 64 <= 112 * 1024 ? 0 : 1);
   if (la == 2 && tmemCols > 512) la = 1;
@@ -456,13 +465,16 @@ static std::string build_source(odesBatch_t *b)
   b->smemBytes = b->matLocal ? 0 : (size_t)words * 8 * (size_t)b->block;
   int fit = b->smemBytes ? (int)((228 * 1024) / (b->smemBytes + 1024)) : 8;
   if (la == 2 && fit > 512 / tmemCols) fit = 512 / tmemCols;            /* resident blocks share the 512 TMEM columns */
-  int want = env_int("ODES_THREADS_PER_SM", 256) / b->block;
+  /* resident threads per SM asked for: 256 (two blocks of 128) -- a MAPK-sized lane fills the SM's shared and tensor memory
+     with that; small systems whose lanes are half the size get a third block (384: Goodwin 5.13 -> 6.08 M trajectories/s at 10^6 sets) or,
+     up to three equations, a fourth (512: events model 6.44 -> 7.40 M; profiles/r02_small_models.jsonl) */
+  int want = env_int("ODES_THREADS_PER_SM", la != 2 ? 256 : neq <= 3 ? 512 : neq <= 5 ? 384 : 256) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   b->maxBlocksPerSM = (la == 2) ? 512 / tmemCols : 32;
   char head[640];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_LA_PACKED=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
+           env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, packed, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   /* development knob: further -D options for the kernel text (tools/gpu_sweep.py), e.g. ODES_EXTRA_DEFS="-DODES_LU_FORM=1" */
@@ -821,6 +833,15 @@ static int launch(odesBatch_t *b, int nsets, size_t offset, cudaStream_t stream,
   unsigned grid = (unsigned)((nsets + perBlock - 1) / perBlock);
   const unsigned resident = (unsigned)(b->numSMs * b->blocksPerSM);
   if (grid > resident) grid = resident;
+  {
+    /* small batches: lanes balance their load by pulling sets, which needs a few sets per lane -- beyond one block per SM
+       the grid grows only while every lane still gets ODES_MIN_SETS_PER_LANE sets (measured on the events model, 10^5 sets:
+       4 resident blocks per SM 4.2 M trajectories/s, 3 blocks 5.1 M; at 10^6 sets 7.4 M vs 6.4 M) */
+    const unsigned long long per = (unsigned long long)perBlock * (unsigned long long)(env_int("ODES_MIN_SETS_PER_LANE", 2) > 0 ? env_int("ODES_MIN_SETS_PER_LANE", 2) : 1);
+    unsigned cap = (unsigned)(((unsigned long long)nsets + per - 1) / per);
+    if (cap < (unsigned)b->numSMs) cap = (unsigned)b->numSMs;
+    if (grid > cap) grid = cap;
+  }
   CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
   if (timed) CUDA_OK(cudaEventRecord(b->e0, stream));
   g_counters[CNT_LAUNCH]++;

@@ -346,6 +346,20 @@ extern "C" { long odes_emu_swaps = 0; }
 #define NCH (NP / 8)
 #define NSJCH (NSJP / 8)
 #define NPVCH (NPVP / 8)
+/* the buffer the per-trajectory constants are moved in: their own padded region, or -- packed (ODES_LA_PACKED, small models
+   whose words then fit half the tensor-memory columns: a third resident block per SM) -- the chunks of the saved Jacobian,
+   behind its NNZ entries */
+#if ODES_LA_PACKED && HAS_JAC
+#define PVB_WORDS NSJP
+#define PVB_CH NSJCH
+#define PVB_BASE LAJ
+#define PVB_OFF NNZ
+#else
+#define PVB_WORDS NPVP
+#define PVB_CH NPVCH
+#define PVB_BASE LAPV
+#define PVB_OFF 0
+#endif
 #if ODES_LA == 0
 #define ODES_SMEM_WORDS (LAOFF + ODES_LA_WORDS)
 #else
@@ -512,9 +526,9 @@ ODES_NOINLINE double wrms_vec(const double *sm, int off)
    first call, initial-step search, difference-quotient Jacobian) share these instructions. */
 ODES_NOINLINE void f_conv(double *sm, La la, double t, bool act)
 {
-  double yl[A1(NEQ)], fl[A1(NEQ)], pvl[A1(NPVP)];
-  la_load<NPVCH>(la, LAPV, pvl);
-  PvRef pv; pv.p = pvl; pv.s = 1u;
+  double yl[A1(NEQ)], fl[A1(NEQ)], pvl[A1(PVB_WORDS)];
+  la_load<PVB_CH>(la, PVB_BASE, pvl);
+  PvRef pv; pv.p = pvl + PVB_OFF; pv.s = 1u;
   FORI yl[i] = YV(i);
   ode_f(t, yl, pv, fl);
   if (act) { FORI FT(i) = fl[i]; }
@@ -1017,9 +1031,14 @@ struct Solver {
     double jnz[A1(NSJP)];
     la_load<NSJCH>(la, LAJ, jnz);
     if (ODES_WARP_ANY(jbad)) {
-      double yl[A1(NEQ)], jnew[A1(NNZ)], pvl[A1(NPVP)];
-      la_load<NPVCH>(la, LAPV, pvl);
-      PvRef pv; pv.p = pvl; pv.s = 1u;
+      double yl[A1(NEQ)], jnew[A1(NNZ)];
+#if ODES_LA_PACKED
+      PvRef pv; pv.p = jnz + PVB_OFF; pv.s = 1u;          /* the constants came with the Jacobian's chunks */
+#else
+      double pvl[A1(PVB_WORDS)];
+      la_load<PVB_CH>(la, PVB_BASE, pvl);
+      PvRef pv; pv.p = pvl + PVB_OFF; pv.s = 1u;
+#endif
       FORI yl[i] = ZN(0, i);
       if (jbad) {
         jacobi_f(tn, yl, pv, jnew);
@@ -1600,8 +1619,8 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
           const unsigned long long next = odes_take_sets(a.counter, want, nwant);
           const bool take = want && next < (unsigned long long)a.nsets;
           if (want && !take) exhausted = true;
-          double pvl[A1(NPVP)];
-          _Pragma("unroll") for (int k = 0; k < NPVP; k++) pvl[k] = 0.0;
+          double pvl[A1(PVB_WORDS)];
+          _Pragma("unroll") for (int k = 0; k < PVB_WORDS; k++) pvl[k] = 0.0;
           if (take) {
             set = (size_t)next;
             s.init_state();
@@ -1609,7 +1628,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
             t = a.tpoints[0]; tout = t; status = 0; iout = 1;
             double yl[A1(NEQ)];
             FORI yl[i] = 0.0;
-            PvRef pv; pv.p = pvl; pv.s = 1u;
+            PvRef pv; pv.p = pvl + PVB_OFF; pv.s = 1u;
             model_init(yl, pv, a.vary, stride, set);
             store_row0(a.out + set * ODES_ROWS(a) * NSTORE, 1, yl, pv);
             firedacc = 0u;
@@ -1624,7 +1643,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
             s.st = (a.nout >= 1) ? ST_START : ST_FINISH;
           }
           ODES_WARP_SYNC();
-          la_commit<NPVCH>(la, LAPV, pvl, take);
+          la_commit<PVB_CH>(la, PVB_BASE, pvl, take);
         } else if (want) idle++;
         ODES_WARP_SYNC();
       }
@@ -1728,9 +1747,9 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     /* ---- ROOT: which triggers became true over the last step, and where (first crossing in (rlo, tn]) ---- */
     if (ODES_WARP_ANY(s.st == ST_ROOT)) {
       const bool act = (s.st == ST_ROOT);
-      double pvl[A1(NPVP)];
-      la_load<NPVCH>(la, LAPV, pvl);
-      PvRef pv; pv.p = pvl; pv.s = 1u;
+      double pvl[A1(PVB_WORDS)];
+      la_load<PVB_CH>(la, PVB_BASE, pvl);
+      PvRef pv; pv.p = pvl + PVB_OFF; pv.s = 1u;
       if (act) {
         double yl[A1(NEQ)];
         unsigned int known = 0u;
@@ -1760,18 +1779,18 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
     /* ---- OUTPUT: rows covered by the last step ---- */
     if (ODES_WARP_ANY(s.st == ST_OUTPUT)) {
       PROF(7, s.st == ST_OUTPUT);
-      double pvl[A1(NPVP)];
+      double pvl[A1(PVB_WORDS)];
       /* the per-trajectory constants are fetched only where the output-time code reads them: stored assigned values or
          constants, events, the steady-state test (three tensor-memory loads per pass otherwise wasted) */
 #ifndef STORE_NEEDS_PV
 #define STORE_NEEDS_PV 1
 #endif
 #if STORE_NEEDS_PV || NEVENTS > 0 || HALT_ON_STEADY
-      la_load<NPVCH>(la, LAPV, pvl);
+      la_load<PVB_CH>(la, PVB_BASE, pvl);
 #else
-      _Pragma("unroll") for (int k = 0; k < NPVP; k++) pvl[k] = 0.0;
+      _Pragma("unroll") for (int k = 0; k < PVB_WORDS; k++) pvl[k] = 0.0;
 #endif
-      PvRef pv; pv.p = pvl; pv.s = 1u;
+      PvRef pv; pv.p = pvl + PVB_OFF; pv.s = 1u;
       bool wrote = false;
       while (s.st == ST_OUTPUT) {
         double yl[A1(NEQ)];
@@ -1841,7 +1860,7 @@ DEV void integrate_lanes(const OdesArgs &a, double *smem_lane, La la)
       ODES_WARP_SYNC();
 #if NEVENTS > 0
       /* event assignments may have changed per-trajectory constants or refreshed assigned values */
-      la_commit<NPVCH>(la, LAPV, pvl, wrote);
+      la_commit<PVB_CH>(la, PVB_BASE, pvl, wrote);
 #else
       (void)wrote;
 #endif

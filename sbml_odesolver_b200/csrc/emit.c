@@ -1087,7 +1087,10 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
   generateMacros(b);
   /* scatter of the saved sparse Jacobian into column j of M = -gamma*J (the kernel adds the +1 on the diagonal);
      j is warp-uniform at the call site, rows and non-zero indices are compile-time constants */
-  CharBuffer_append(b, "#define NP (8 * ((NEQ + 7) / 8))\n#define NSJW (HAS_JAC ? NNZ : NEQ * NP)\n#define NSJP (8 * ((NSJW + 7) / 8))\n#define NPVP (8 * ((NPV + 7) / 8))\n");
+  /* ODES_LA_PACKED (set by the host where it halves the tensor-memory allocation of a lane): the per-trajectory constants
+     follow the saved Jacobian's non-zeros in the SAME chunks instead of starting a padded region of their own */
+  CharBuffer_append(b, "#ifndef ODES_LA_PACKED\n#define ODES_LA_PACKED 0\n#endif\n#define NP (8 * ((NEQ + 7) / 8))\n#define NSJW (HAS_JAC ? NNZ : NEQ * NP)\n"
+                       "#if ODES_LA_PACKED && HAS_JAC\n#define NSJP (8 * ((NSJW + NPV + 7) / 8))\n#define NPVP 0\n#else\n#define NSJP (8 * ((NSJW + 7) / 8))\n#define NPVP (8 * ((NPV + 7) / 8))\n#endif\n");
   CharBuffer_append(b, "DEV void scatter_col(int j, double (&c)[A1(NP)], const double (&jnz)[A1(NSJP)], double mg)\n{\n  (void)c; (void)jnz; (void)mg;\n  switch (j) {\n");
   if (usejac) {
     for (j = 0; j < om->neq; j++) {
