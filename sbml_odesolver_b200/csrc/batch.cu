@@ -407,7 +407,7 @@ static std::string build_source(odesBatch_t *b)
      words (M with columns padded to NP rows, saved Jacobian, per-trajectory constants; all in chunks of 8) go to
      tensor memory when they fit its 512 columns (2 columns per double), else shared memory, else an L2-resident
      global scratch */
-  const int chipWords = 10 * neq + 19;
+  int chipWords = 10 * neq + 19;
   const int np = 8 * ((neq + 7) / 8);
   const int nsjw = usejac ? b->om->sparsesize : neq * np;
   b->laWords = neq * np + 8 * ((nsjw + 7) / 8) + 8 * ((npv + 7) / 8);
@@ -458,6 +458,19 @@ static std::string build_source(odesBatch_t *b)
   b->block = env_int("ODES_BLOCK", la == 2 ? 128 : 64);
   /* blocks of more than 4 warps: warps w and w+4 share TMEM lanes and take separate column ranges */
   if (la == 2 && b->block > 128) { tmemCols = 32; while (tmemCols < 2 * b->laWords * ((b->block + 127) / 128)) tmemCols *= 2; if (tmemCols > 512) { b->block = 128; tmemCols = 32; while (tmemCols < 2 * b->laWords) tmemCols *= 2; } b->tmemCols = tmemCols; }
+  /* With the analytic Jacobian f can share the words of y (bdf_kernel.cuh: ODES_ALIAS_FY), one vector less per lane.  It
+     serialises a few loads behind stores (Goodwin, which gains no block from it: 164.5 -> 171.0 ms), so it is used where it
+     buys a resident block: a six-equation model drops from 80.9 to 74.8 KB per block and fits three (repressilator, 10^6 sets x
+     1000 output points: 575 -> 479 ms) */
+  int alias = 0;
+  if (usejac && la == 2 && env_int("ODES_ALIAS_FY", 1)) {
+    const int blk = env_int("ODES_BLOCK", 128);
+    const int fitU = (int)((228 * 1024) / ((size_t)chipWords * 8 * (size_t)blk + 1024)), fitA = (int)((228 * 1024) / ((size_t)(chipWords - neq) * 8 * (size_t)blk + 1024));
+    const int lim = 512 / tmemCols, wantBlocks = env_int("ODES_THREADS_PER_SM", neq <= 3 ? 512 : neq <= 6 ? 384 : 256) / blk;
+    const int useU = fitU < lim ? (fitU < wantBlocks ? fitU : wantBlocks) : (lim < wantBlocks ? lim : wantBlocks);
+    const int useA = fitA < lim ? (fitA < wantBlocks ? fitA : wantBlocks) : (lim < wantBlocks ? lim : wantBlocks);
+    if (useA > useU || env_int("ODES_ALIAS_FY", 1) > 1) { alias = 1; chipWords -= neq; }
+  }
   const int words = chipWords + (la == 0 ? b->laWords : 0);
   b->matLocal = env_int("ODES_MAT_LOCAL", 0);
   while (!b->matLocal && (size_t)words * 8 * (size_t)b->block + 1024 > 227 * 1024 && b->block > 32) b->block /= 2;
@@ -468,13 +481,13 @@ static std::string build_source(odesBatch_t *b)
   /* resident threads per SM asked for: 256 (two blocks of 128) -- a MAPK-sized lane fills the SM's shared and tensor memory
      with that; small systems whose lanes are half the size get a third block (384: Goodwin 5.13 -> 6.08 M trajectories/s at 10^6 sets) or,
      up to three equations, a fourth (512: events model 6.44 -> 7.40 M; profiles/r02_small_models.jsonl) */
-  int want = env_int("ODES_THREADS_PER_SM", la != 2 ? 256 : neq <= 3 ? 512 : neq <= 5 ? 384 : 256) / b->block;
+  int want = env_int("ODES_THREADS_PER_SM", la != 2 ? 256 : neq <= 3 ? 512 : neq <= 6 ? 384 : 256) / b->block;
   b->minblocks = env_int("ODES_MINBLOCKS", fit < want ? (fit < 1 ? 1 : fit) : (want < 1 ? 1 : want));
   b->maxBlocksPerSM = (la == 2) ? 512 / tmemCols : 32;
   char head[640];
-  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_LA_PACKED=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
+  snprintf(head, sizeof head, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_MAT_LOCAL=%d -DODES_SETUP_MIN=%d -DODES_SETUP_WAIT=%d -DODES_REFILL_MIN=%d -DODES_REFILL_WAIT=%d -DODES_COL_UNROLL=%d -DODES_LA=%d -DODES_LA_PACKED=%d -DODES_ALIAS_FY=%d -DODES_TMEM_COLS=%d -DODES_LOCKSTEP=%d -DODES_GESL_UNROLL=%d -DODES_ALIGN_MASK=%d%s\n",
            env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->block, b->minblocks, b->matLocal,
-           env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, packed, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
+           env_int("ODES_SETUP_MIN", 10), env_int("ODES_SETUP_WAIT", 3), env_int("ODES_REFILL_MIN", 3), env_int("ODES_REFILL_WAIT", 20), env_int("ODES_COL_UNROLL", 2), la, packed, alias, b->tmemCols, env_int("ODES_LOCKSTEP", 2), env_int("ODES_GESL_UNROLL", 4), env_int("ODES_ALIGN_MASK", 7),
            env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
   std::string src = head;
   /* development knob: further -D options for the kernel text (tools/gpu_sweep.py), e.g. ODES_EXTRA_DEFS="-DODES_LU_FORM=1" */

@@ -335,7 +335,20 @@ extern "C" { long odes_emu_swaps = 0; }
 #define EWOFF (ZOFF + LMAX * NEQ)                 /* error weights                         */
 #define ACOFF (EWOFF + NEQ)                       /* acor: accumulated Newton correction   */
 #define YOFF (ACOFF + NEQ)                        /* y: argument of f; data->value[0..neq) between steps */
-#define FTOFF (YOFF + NEQ)                        /* f(t,y); right-hand side / solution of the linear system; scratch */
+#ifndef ODES_ALIAS_FY
+#define ODES_ALIAS_FY 0
+#endif
+/* f(t,y); right-hand side / solution of the linear system; scratch.  With ODES_ALIAS_FY (set by the host where it buys a
+   resident block, analytic Jacobian only) f SHARES the words of y: the
+   argument is dead once f has been evaluated (f_conv loads all of y before it stores f; the Newton update reads the solved
+   correction of a column before it writes the column's new y; every other writer of y -- predictor, restarts, the initial-step
+   search, the dense output -- comes when the last f is no longer needed).  Only the difference-quotient Jacobian perturbs y
+   while it still holds f(y).  One vector less per lane: a six-equation model fits three blocks per SM. */
+#if HAS_JAC && ODES_ALIAS_FY
+#define FTOFF YOFF
+#else
+#define FTOFF (YOFF + NEQ)
+#endif
 #define TAUOFF (FTOFF + NEQ)                      /* tau[0..6], tq[0..5], l[0..5]          */
 #define LAOFF (TAUOFF + (LMAX + 1) + 6 + LMAX)    /* linear-algebra words when they are in shared memory */
 /* linear-algebra word space (doubles); NP, NSJP, NPVP (multiples of 8) come from the model section */

@@ -166,7 +166,7 @@ class Emu:
         if not os.path.exists(lib):
             open(cu, "w").write(src)
             subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-w"] + extra + (["-DODES_ROOT_POW_LIBM"] if os.environ.get("ODES_EMU_LIBM_POW") else []) +
-                                  [t for t in src.split("\n")[0].split() if t.startswith("-DODES_STEPRES") or t.startswith("-DODES_ROOTFIND") or t.startswith("-DODES_LA_PACKED")] +
+                                  [t for t in src.split("\n")[0].split() if t.startswith("-DODES_STEPRES") or t.startswith("-DODES_ROOTFIND") or t.startswith("-DODES_LA_PACKED") or t.startswith("-DODES_ALIAS_FY")] +
                                   ([t for t in src.split("\n")[0].split() if t.startswith("-DODES_W") or t.startswith("-DODES_ADAMS") or t.startswith("-DODES_FUNCTIONAL")] if "-DODES_WARP=1" in src.split("\n")[0] else []) + [
                                    f'-DODES_MODEL_SOURCE="{cu}"', os.path.join(ROOT, "tests", "emu", "emu_harness.cpp"), "-o", lib])
         self.lib = C.CDLL(lib)

@@ -164,6 +164,25 @@ def test_emulated_event_location_inside_steps(monkeypatch, warp):
     so.lib().SolverError_clear()
 
 
+@pytest.mark.parametrize("name,nsets,nout", [("mapk", 8, None), ("events", 12, None), ("goodwin", 6, None)])
+def test_emulated_f_sharing_the_words_of_y(monkeypatch, name, nsets, nout):
+    """ODES_ALIAS_FY: with the analytic Jacobian the right-hand side can share the shared-memory words of its argument (one
+    vector less per lane; the host switches it on where it buys a resident block, e.g. the six-equation repressilator).
+    Forced on here for models that do not get it by default: bit-identical to the oracle."""
+    monkeypatch.setenv("ODES_ALIAS_FY", "2")
+    w = H.workload(name, nout=nout)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=41)
+    b = so.Batch(m, w["opt"], w["vary"])
+    assert "-DODES_ALIAS_FY=1" in b.source().split("\n")[0]
+    base, trig = b.base_values()
+    got = H.Emu(b, name + "_alias").run(base, trig, vals, H.tpoints(w["opt"], w["nout"]), 10000, w["rtol"], w["atol"])
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], compiled_so=H.compile_c_model(m, name))
+    b.close()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    assert np.array_equal(got["stats"].T, ref["stats"]) and np.array_equal(got["fired"].T, ref["fired"])
+
+
 def test_generated_source_has_single_hot_instances():
     """The block pipeline keeps one instance of the model functions in the instruction stream of the hot loop."""
     w = H.workload("mapk", nout=10)
