@@ -93,6 +93,7 @@ int ODESBatch_getEventLog(odesBatch_t *, int nsets, unsigned int *fired /* [nout
    Rows not reached are not-a-number like the state rows. */
 int ODESBatch_getNsens(const odesBatch_t *);
 int ODESBatch_getSensIndex(const odesBatch_t *, int is);     /* value[] index of sensitivity parameter `is` */
+int ODESBatch_getDifferenceQuotients(const odesBatch_t *);    /* bit 0: difference-quotient sensitivity right-hand sides, bit 1: difference-quotient Jacobian */
 int ODESBatch_getSensitivities(odesBatch_t *, int nsets, double *sens /* [nsets][nout+1][nsens][neq] */);
 double *ODESBatch_deviceSensitivities(odesBatch_t *);
 

@@ -20,6 +20,10 @@
  * ResetCvodeOnEvent) invalidates the solver, which is then re-initialised at the output time from the current values
  * AND the current sensitivities (src/sensSolver.c:268-277: "yS are 0.0 or 1.0 in a new run or old values in case of
  * events") with CVodeReInit + CVodeSensReInit.
+ * Difference quotients (refcvs_sens_dq / refcvs_jac_dq, set by the test helper): src/sensSolver.c:312-321 -- without a
+ * parametric matrix the reference registers no sensitivity right-hand side (CVODES' internal CVSensRhsDQ, centred,
+ * rhomax 0) and lets its f read the sensitivity parameters from the array CVODES perturbs (data->use_p,
+ * src/cvodeSolver.c:981-984); without a Jacobian CVDENSE's CVDenseDQJac is used (src/cvodeSolver.c:620-623).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -39,13 +43,30 @@ typedef void (*c_sens_fn)(int iS, double t, const double *y, const double *yS, d
 
 /* SensMethod of the next batch calls (0 simultaneous, 1 staggered, 2 staggered1); set by the test helper before a run */
 int refcvs_sens_method = 0;
+/* 1: no sensitivity right-hand side is registered (CVSensRhsDQ) and f reads value[refcvs_sens_index[is]] from p[is] */
+int refcvs_sens_dq = 0;
+int refcvs_sens_index[64];
+/* 1: no Jacobian function is registered (CVDenseDQJac) */
+int refcvs_jac_dq = 0;
 
-typedef struct { int neq; double *value; c_ode_fn f; c_jac_fn j; c_sens_fn s; } ctx_t;
+typedef struct { int neq; double *value; c_ode_fn f; c_jac_fn j; c_sens_fn s; int ns; const double *p; double p_orig[64]; } ctx_t;
 
+/* use_p (src/cvodeSolver.c:981-984, :1019-1022, :1060-1063, :1084-1087): the parameters come from the array CVODES
+   perturbs and are put back to their original values after the evaluation, in f and in the Jacobian alike */
 static void f_cb(realtype t, N_Vector y, N_Vector ydot, void *f_data)
-{ ctx_t *c = (ctx_t *)f_data; c->f(t, NV_DATA_S(y), NV_DATA_S(ydot), c->value); }
+{
+  ctx_t *c = (ctx_t *)f_data; int is;
+  if (c->p) for (is = 0; is < c->ns; is++) c->value[refcvs_sens_index[is]] = c->p[is];
+  c->f(t, NV_DATA_S(y), NV_DATA_S(ydot), c->value);
+  if (c->p) for (is = 0; is < c->ns; is++) c->value[refcvs_sens_index[is]] = c->p_orig[is];
+}
 static void jac_cb(long int N, DenseMat J, realtype t, N_Vector y, N_Vector fy, void *jac_data, N_Vector t1, N_Vector t2, N_Vector t3)
-{ ctx_t *c = (ctx_t *)jac_data; (void)N; (void)fy; (void)t1; (void)t2; (void)t3; c->j(t, NV_DATA_S(y), J->data[0], c->value); }
+{
+  ctx_t *c = (ctx_t *)jac_data; int is; (void)N; (void)fy; (void)t1; (void)t2; (void)t3;
+  if (c->p) for (is = 0; is < c->ns; is++) c->value[refcvs_sens_index[is]] = c->p[is];
+  c->j(t, NV_DATA_S(y), J->data[0], c->value);
+  if (c->p) for (is = 0; is < c->ns; is++) c->value[refcvs_sens_index[is]] = c->p_orig[is];
+}
 static void fs_cb(int Ns, realtype t, N_Vector y, N_Vector ydot, int iS, N_Vector yS, N_Vector ySdot, void *fS_data, N_Vector t1, N_Vector t2)
 { ctx_t *c = (ctx_t *)fS_data; (void)Ns; (void)ydot; (void)t1; (void)t2; c->s(iS, t, NV_DATA_S(y), NV_DATA_S(yS), NV_DATA_S(ySdot), c->value); }
 
@@ -64,10 +85,11 @@ static void set_up_solver(void *mem, ctx_t *ctx, job_t *jb, double *p)
 {
   CVodeSetFdata(mem, ctx);
   CVodeSetMaxNumSteps(mem, jb->mxstep);
+  int is;
   CVDense(mem, jb->neq);
-  CVDenseSetJacFn(mem, jac_cb, ctx);
-  CVodeSetSensRhs1Fn(mem, fs_cb);
-  CVodeSetSensFdata(mem, ctx);
+  if (!refcvs_jac_dq) CVDenseSetJacFn(mem, jac_cb, ctx);
+  if (!refcvs_sens_dq) { CVodeSetSensRhs1Fn(mem, fs_cb); CVodeSetSensFdata(mem, ctx); }
+  else for (is = 0; is < jb->nsens; is++) p[is] = ctx->p_orig[is] = ctx->value[refcvs_sens_index[is]];
   CVodeSetSensParams(mem, p, NULL, NULL);
   CVodeSetSensTolerances(mem, CV_EE, 0.0, NULL);
   CVodeSetSensErrCon(mem, FALSE);
@@ -95,7 +117,7 @@ static void *run_range(void *arg)
   N_Vector y = N_VNew_Serial(neq), abstol = N_VNew_Serial(neq);
   N_Vector *yS = N_VNewVectorArray_Serial(ns, neq);
   double *p = (double *)calloc((size_t)ns, sizeof(double));
-  ctx.neq = neq; ctx.value = (double *)malloc((size_t)jb->nvalues * sizeof(double)); ctx.f = jb->f; ctx.j = jb->j; ctx.s = jb->s;
+  ctx.neq = neq; ctx.value = (double *)malloc((size_t)jb->nvalues * sizeof(double)); ctx.f = jb->f; ctx.j = jb->j; ctx.s = jb->s; ctx.ns = ns; ctx.p = refcvs_sens_dq ? p : NULL;
 
   for (s = jb->first; s < jb->last; s++) {
     double t = jb->tpoints[0]; int flag = 0, iout, halted = 0;
@@ -216,7 +238,7 @@ int refcvs_integrate_batch_events(const char *compiled_so, int neq, int nvalues,
   c_ode_fn f; c_jac_fn j; c_sens_fn s;
   if (!so) return -1;
   f = (c_ode_fn)dlsym(so, "ode_f"); j = (c_jac_fn)dlsym(so, "jacobi_f"); s = (c_sens_fn)dlsym(so, "sense_f");
-  if (!f || !j || !s) { dlclose(so); return -1; }
+  if (!f || (!j && !refcvs_jac_dq) || (!s && !refcvs_sens_dq)) { dlclose(so); return -1; }
   if (nthreads < 1) nthreads = 1;
   if (nthreads > nsets) nthreads = nsets > 0 ? nsets : 1;
   jobs = (job_t *)calloc((size_t)nthreads, sizeof *jobs);

@@ -49,7 +49,7 @@ _SIGS = {
     "CvodeSettings_setSensParams": (c_i, [c_p, c_p, c_i]), "CvodeSettings_unsetSensParams": (None, [c_p]),
     "CvodeSettings_setSensitivity": (None, [c_p, c_i]), "CvodeSettings_setSensMethod": (None, [c_p, c_i]),
     "CvodeSettings_getSensitivity": (c_i, [c_p]),
-    "ODESBatch_getNsens": (c_i, [c_p]), "ODESBatch_getSensIndex": (c_i, [c_p, c_i]), "ODESBatch_getSensitivities": (c_i, [c_p, c_i, c_p]),
+    "ODESBatch_getNsens": (c_i, [c_p]), "ODESBatch_getSensIndex": (c_i, [c_p, c_i]), "ODESBatch_getDifferenceQuotients": (c_i, [c_p]), "ODESBatch_getSensitivities": (c_i, [c_p, c_i, c_p]),
     "ODESBatch_deviceSensitivities": (c_p, [c_p]),
     "ODESBatch_runHostSens": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_i]),
     "ODESBatch_runHostAllDevicesSens": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i]),

@@ -432,7 +432,7 @@ static std::string build_source(odesBatch_t *b)
   if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
   if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
   if (b->opt->CvodeMethod == 1 || b->opt->IterMethod == 1) warp = 1;       /* and so do Adams-Moulton and functional iteration */
-  if (warp && !(neq >= 1 && neq <= 32 && usejac)) warp = 0;
+  if (warp && !(neq >= 1 && neq <= 32 && (usejac || b->nsens > 0 || env_int("ODES_WARP", -1) == 1))) warp = 0;   /* without a Jacobian: CVDenseDQJac in either layout; the lane layout stays the default */
   b->warpMode = warp;
   if (warp) {
     const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);
@@ -441,11 +441,11 @@ static std::string build_source(odesBatch_t *b)
        after the solver state left local memory (136 registers unconstrained): 12 warps 227 k, 16 warps (128 registers) 267 k */
     /* with sensitivities a lane carries 10 more vector elements per sensitivity: fewer resident warps, more registers */
     int slabs = 1;                            /* register slabs of the packed layout (bdf_warp_kernel.cuh: W_S) */
-    if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = 32 / neq; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }
+    if (b->nsens > 0) { const int nv = 1 + b->nsens; int g = (usejac && b->os->sensitivity) ? 32 / neq : 1; if (g < 1) g = 1; if (g > nv) g = nv; slabs = (nv + g - 1) / g; }   /* difference quotients: one vector per slab */
     b->minblocks = env_int("ODES_MINBLOCKS", wpb != 4 ? 1 : b->opt->CvodeMethod == 1 ? 3 : slabs == 1 ? 4 : slabs == 2 ? 3 : slabs <= 4 ? 2 : 1); b->maxBlocksPerSM = 32;
     char headw[640];
     snprintf(headw, sizeof headw, "//!opts: --fmad=%s -DODES_STEPRES=%d -DODES_ROOTFIND=%d -DODES_WARP=1 -DODES_ADAMS=%d -DODES_FUNCTIONAL=%d%s -DODES_WARPS_PER_BLOCK=%d -DODES_BLOCK=%d -DODES_MINBLOCKS=%d -DODES_WM_LAUNDER=%d -DODES_WDIV=%d -DODES_WLOCK=%d -DODES_WJE=%d -DODES_WDAG=%d%s\n",
-             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 0), env_int("ODES_WLOCK", (b->nsens > 0 && slabs > 4) ? 1 : 0), env_int("ODES_WJE", -1), env_int("ODES_WDAG", -1),
+             env_int("ODES_FMAD", 0) ? "true" : "false", b->stepRes, b->rootFind, b->opt->CvodeMethod == 1 ? 1 : 0, b->opt->IterMethod == 1 ? 1 : 0, env_int("ODES_WJAC_INLINE", -1) >= 0 ? (env_int("ODES_WJAC_INLINE", 0) ? " -DODES_WJAC_INLINE=1" : " -DODES_WJAC_INLINE=0") : "", wpb, b->block, b->minblocks, env_int("ODES_WM_LAUNDER", 0), env_int("ODES_WDIV", 2), env_int("ODES_WLOCK", (b->nsens > 0 && slabs > 4) ? 1 : 0), env_int("ODES_WJE", -1), env_int("ODES_WDAG", -1),
              env_int("ODES_MAXREG", 0) ? (std::string(" --maxrregcount=") + std::to_string(env_int("ODES_MAXREG", 0))).c_str() : "");
     std::string srcw = headw;
     srcw += model;
@@ -555,18 +555,25 @@ static odesBatch_t *batch_prepare(odeModel_t *om, cvodeSettings_t *opt, int nvar
   else { for (int j = 0; j < b->nvalues; j++) b->store.push_back(j); b->nstore = b->nvalues; }
   if (opt->UseJacobian && !om->jacob && !om->jacobianFailed) ODEModel_constructJacobian(om);
   if (!compute_base(om, opt, b->base, b->trigger0)) { delete b; return NULL; }
-  /* forward sensitivities (src/sensSolver.c:197-346): simultaneous corrector, analytic sense_f, no error control on the
-     sensitivity variables -- the reference's set-up; it needs the Jacobian and the parametric matrix */
+  /* forward sensitivities (src/sensSolver.c:197-346): no error control on the sensitivity variables; the analytic sense_f
+     where the Jacobian and the parametric matrix exist, else CVODES' centred difference quotients over f with the
+     sensitivity parameters read from the perturbed array (src/sensSolver.c:312-321, data->use_p), and CVDENSE's
+     difference-quotient Jacobian where there is none */
   b->os = NULL; b->nsens = 0; b->d_sens = NULL; b->sensFromRow0 = 0;
   if (opt->Sensitivity) {
     const char *why = NULL;
-    if (!(opt->UseJacobian && om->jacobian)) why = "forward sensitivities need the analytic Jacobian";
-    else if (opt->SensMethod < 0 || opt->SensMethod > 2) why = "SensMethod must be 0 (simultaneous), 1 (staggered) or 2 (staggered1)";
+    if (opt->SensMethod < 0 || opt->SensMethod > 2) why = "SensMethod must be 0 (simultaneous), 1 (staggered) or 2 (staggered1)";
     else if (om->neq < 1 || om->neq > 32) why = "forward sensitivities are implemented for 1..32 equations (one trajectory per warp)";
     if (!why) {
       b->os = ODESense_create(om, opt);
-      if (!b->os || !b->os->sensitivity) why = "the parametric matrix could not be constructed";
+      if (b->os && env_int("ODES_FORCE_SENS_DQ", 0)) b->os->sensitivity = 0;     /* test knob: a parametric matrix that could not be constructed */
+      if (!b->os) why = "the sensitivity structures could not be created";
       else if (b->os->nsens < 1 || b->os->nsens > 32) why = "between 1 and 32 sensitivity parameters are supported";
+      else if (!(opt->UseJacobian && om->jacobian && b->os->sensitivity)) {
+        /* the reference's f overwrites value[index_sens[i]] with p[i] for EVERY sensitivity, a variable's included
+           (src/cvodeSolver.c:981-984), which freezes that variable at its initial value inside f: not reproduced */
+        for (int i = 0; i < b->os->nsens; i++) if (b->os->index_sensP[i] == -1) why = "difference-quotient sensitivities (no parametric matrix or no Jacobian) are implemented for parameters, not for initial values";
+      }
     }
     if (why) { SolverError_error(ERROR_ERROR_TYPE, SOLVER_ERROR_BATCH_ARGUMENT, "%s", why); ODESense_free(b->os); delete b; return NULL; }
     b->nsens = b->os->nsens;
@@ -699,6 +706,13 @@ extern "C" int ODESBatch_getNout(const odesBatch_t *b) { return b->nout + 1; }
 extern "C" int ODESBatch_getNstore(const odesBatch_t *b) { return b->nstore; }
 extern "C" int ODESBatch_getNsens(const odesBatch_t *b) { return b->nsens; }
 extern "C" int ODESBatch_getSensIndex(const odesBatch_t *b, int is) { return (b->os && is >= 0 && is < b->nsens) ? b->os->index_sens[is] : -1; }
+/* bit 0: the sensitivity right-hand sides are CVODES' difference quotients (no parametric matrix or no Jacobian,
+   src/sensSolver.c:312-321); bit 1: the Jacobian is CVDENSE's difference quotient (src/cvodeSolver.c:620-623) */
+extern "C" int ODESBatch_getDifferenceQuotients(const odesBatch_t *b)
+{
+  const int usejac = b->opt->UseJacobian && b->om->jacobian;
+  return ((b->nsens > 0 && !(usejac && b->os->sensitivity)) ? 1 : 0) | (usejac ? 0 : 2);
+}
 extern "C" double *ODESBatch_deviceSensitivities(odesBatch_t *b) { return b->d_sens; }
 extern "C" int ODESBatch_getSensitivities(odesBatch_t *b, int nsets, double *sens)
 {

@@ -40,6 +40,9 @@ void CharBuffer_appendInt(charBuffer_t *c, long v) { char t[32]; snprintf(t, siz
 /* the public entry prints like the reference (src/charBuffer.c:103-112, "%g"); the emitters below use cb_double17 */
 void CharBuffer_appendDouble(charBuffer_t *c, double v) { char t[64]; snprintf(t, sizeof t, "%g", v); CharBuffer_append(c, t); }
 /* full precision for generated code: the value is reproduced exactly */
+/* the parametric matrix df/dp exists and every entry could be differentiated */
+#define SENS_OK(os) ((os) && (os)->sensitivity && (os)->sens)
+
 static void cb_double17(charBuffer_t *c, double v)
 {
   char t[64];
@@ -449,7 +452,7 @@ char *ODEModel_generateCSourceSens(odeModel_t *om, const odeSense_t *os)
         cbprintf(b, "  ySdot[%d] += ( ", i); gen(b, nz->ij, &c); cbprintf(b, ") * yS[%d];\n", nz->j);
       }
       for (k = 0; k < os->nsens; k++) {
-        if (os->index_sensP[k] == -1 || !os->sens || !os->sensLogic[i][os->index_sensP[k]]) continue;
+        if (os->index_sensP[k] == -1 || !SENS_OK(os) || !os->sensLogic[i][os->index_sensP[k]]) continue;
         cbprintf(b, "  if ( %d == iS ) ySdot[%d] += ", k, i); gen(b, os->sens[i][os->index_sensP[k]], &c); CharBuffer_append(b, ";\n");
       }
     }
@@ -733,7 +736,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
      name -- all entries of a shape at once, every one with exactly the operations of its emitted expression. */
   {
     int total = usejac ? om->sparsesize : 0, e;
-    if (os && usejac && os->sens) for (i = 0; i < om->neq; i++) for (j = 0; j < os->nsensP; j++) if (os->sensLogic[i][j]) total++;
+    if (usejac && SENS_OK(os)) for (i = 0; i < om->neq; i++) for (j = 0; j < os->nsensP; j++) if (os->sensLogic[i][j]) total++;
     je_n = 0; je_shapes = 0;
     if (usejac && total > 0 && total <= 32 * JE_MAX_ROUNDS) {
       je_total = total;
@@ -875,17 +878,21 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
   CharBuffer_append(b, "  default: break;\n  }\n}\n");
   /* forward sensitivities: which variable a sensitivity belongs to (initial value 1 on that element), and the emitted
      sense_f row by row -- 0, += J_ij * yS[j] over the row's non-zero Jacobian entries, += df_i/dp_is */
-  if (os && usejac) {
+  if (os) {
     CharBuffer_append(b, "DEV int w_sens_variable(int is)\n{\n  switch (is) {\n");
     for (i = 0; i < os->nsens; i++) if (os->index_sensP[i] == -1) cbprintf(b, "  case %d: return %d;\n", i, os->index_sens[i]);
+    CharBuffer_append(b, "  default: return -1;\n  }\n}\n");
+    /* the per-trajectory slot of a sensitivity parameter (the difference quotients perturb it there), -1 for a variable */
+    CharBuffer_append(b, "DEV int w_sens_pvslot(int is)\n{\n  switch (is) {\n");
+    for (i = 0; i < os->nsens; i++) if (os->index_sensP[i] != -1 && k->slot[os->index_sens[i]] >= 0) cbprintf(b, "  case %d: return %d;\n", i, k->slot[os->index_sens[i]]);
     CharBuffer_append(b, "  default: return -1;\n  }\n}\n");
     CharBuffer_append(b, "DEV double w_sens_row(int lane, int is, double t, const double *y, const PvRef pv, const double *jr, const double *ys)\n{\n"
                          "  double r = 0.0; (void)is; (void)t; (void)y; (void)pv; (void)jr; (void)ys;\n  switch (lane) {\n");
     for (i = 0; i < om->neq; i++) {
       int kk, any = 0;
       cbprintf(b, "  case %d:\n", i);
-      for (j = 0; j < om->sparsesize; j++) if (om->jacobSparse[j]->i == i) cbprintf(b, "    r += JR(%d) * ys[%d];\n", om->jacobSparse[j]->j, om->jacobSparse[j]->j);
-      for (kk = 0; kk < os->nsens; kk++) if (os->index_sensP[kk] != -1 && os->sens && os->sensLogic[i][os->index_sensP[kk]]) any = 1;
+      if (usejac) for (j = 0; j < om->sparsesize; j++) if (om->jacobSparse[j]->i == i) cbprintf(b, "    r += JR(%d) * ys[%d];\n", om->jacobSparse[j]->j, om->jacobSparse[j]->j);
+      for (kk = 0; kk < os->nsens; kk++) if (os->index_sensP[kk] != -1 && usejac && SENS_OK(os) && os->sensLogic[i][os->index_sensP[kk]]) any = 1;
       if (any) {
         CharBuffer_append(b, "    switch (is) {\n");
         for (kk = 0; kk < os->nsens; kk++) {
@@ -901,7 +908,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
   /* the entry tasks: word 0 = operands 0..3 (10 bits each), destination (bits 40..51: 32 * column + row in the row-per-lane
      matrix, the parametric columns behind the NEQ Jacobian columns), shape (52..57), negate (62), valid (63); words 1, 2 =
      operands 4..9 and 10..15.  Slots are filled shape by shape so that a round of 32 entries holds few shapes. */
-  cbprintf(b, "#define W_JE_N %d\n#define W_JE_ROUNDS %d\n#define W_NSENSP %d\n", je_n, (je_n + 31) / 32, (os && usejac) ? os->nsensP : 0);
+  cbprintf(b, "#define W_JE_N %d\n#define W_JE_ROUNDS %d\n#define W_NSENSP %d\n", je_n, (je_n + 31) / 32, (usejac && SENS_OK(os)) ? os->nsensP : 0);
   if (je_n > 0) {
     int slot = 0, sh, e, q;
     CharBuffer_append(b, "DEV unsigned long long w_je_task(int slot, int word)\n{\n  switch (3 * slot + word) {\n");
@@ -943,7 +950,7 @@ static void emit_warp_flavour(charBuffer_t *b, const odeModel_t *om, kinfo_t *k,
     CharBuffer_append(b, "DEV int w_sens_pcol(int is)\n{\n  switch (is) {\n");
     if (os) for (i = 0; i < os->nsens; i++) if (os->index_sensP[i] != -1) cbprintf(b, "  case %d: return %d;\n", i, os->index_sensP[i]);
     CharBuffer_append(b, "  default: return -1;\n  }\n}\nDEV unsigned int w_sens_pmask(int i)\n{\n  switch (i) {\n");
-    if (os && os->sens) for (i = 0; i < om->neq; i++) {
+    if (usejac && SENS_OK(os)) for (i = 0; i < om->neq; i++) {
       unsigned int m = 0u;
       for (j = 0; j < os->nsensP && j < 32; j++) if (os->sensLogic[i][j]) m |= 1u << j;
       if (m) cbprintf(b, "  case %d: return 0x%xu;\n", i, m);
@@ -1042,7 +1049,7 @@ char *ODEModel_generateCUDASource(odeModel_t *om, const cvodeSettings_t *opt, in
 char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt, int nvary, const int *vary,
                                       int nstore, const int *store, const double *base, const odeSense_t *os)
 {
-  int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac, store_needs_pv = 0;
+  int nvalues = om->neq + om->nass + om->nconst, i, j, e, npv = 0, usejac, store_needs_pv = 0, static_slots = 0;
   charBuffer_t *b = CharBuffer_create();
   kinfo_t k; emit_ctx_t c; char *out;
   int *used_in_ode = (int *)calloc((size_t)nvalues + 1, sizeof(int));
@@ -1063,10 +1070,17 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
     int idx = om->eventIndex[e][j];
     if (idx >= om->neq + om->nass && k.kind[idx] == K_UNIFORM) { k.kind[idx] = K_THREAD; k.slot[idx] = npv++; }
   }
+  /* difference-quotient sensitivities (no parametric matrix or no Jacobian, src/sensSolver.c:312-321): the kernel perturbs
+     the sensitivity parameters (CVSensRhs1DQ), so they are per-trajectory constants even where the batch does not vary them */
+  if (os && !(opt->UseJacobian && om->jacobian && os->sensitivity))
+    for (i = 0; i < os->nsens; i++) {
+      int idx = os->index_sens[i];
+      if (os->index_sensP[i] != -1 && idx >= om->neq + om->nass && k.kind[idx] == K_UNIFORM) { k.kind[idx] = K_THREAD; k.slot[idx] = npv++; }
+    }
   /* assigned values read by the ODEs but not recomputed before them keep a per-trajectory slot */
   for (i = 0; i < om->neq; i++) mark_refs(om->ode[i], used_in_ode);
   for (i = 0; i < om->nassbeforeodes; i++) { ode_local[om->assignmentsBeforeODEs[i]->i] = 1; mark_refs(om->assignmentsBeforeODEs[i]->ij, used_in_ode); }
-  for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) k.slot[i] = npv++; }
+  for (i = om->neq; i < om->neq + om->nass; i++) { all_local[i] = 1; if (used_in_ode[i] && !ode_local[i]) { k.slot[i] = npv++; static_slots++; } }
 
   c.cuda = 1; c.interp = 0; c.name = name_cuda; c.time = REF_TIME; c.info = &k; c.leaf = NULL;
 
@@ -1075,7 +1089,7 @@ char *ODEModel_generateCUDASourceSens(odeModel_t *om, const cvodeSettings_t *opt
   cbprintf(b, "#define NEQ %d\n#define NASS %d\n#define NVAL %d\n#define NEVENTS %d\n#define NPV %d\n#define NVARY %d\n#define NSTORE %d\n#define NNZ %d\n#define HAS_JAC %d\n#define USE_TSTOP %d\n",
            om->neq, om->nass, nvalues, om->nevents, npv, nvary, nstore, usejac ? om->sparsesize : 0, usejac, (opt->SetTStop || om->npiecewise) ? 1 : 0);
   cbprintf(b, "#define RESET_ON_EVENT %d\n#define HALT_ON_EVENT %d\n", opt->ResetCvodeOnEvent ? 1 : 0, opt->HaltOnEvent ? 1 : 0);
-  cbprintf(b, "#define NSENS %d\n#define SENS_STAGGERED %d\n", (os && usejac) ? os->nsens : 0, (os && usejac) ? opt->SensMethod : 0);
+  cbprintf(b, "#define NSENS %d\n#define SENS_STAGGERED %d\n#define W_SENS_DQ %d\n#define W_STATIC_RULE_SLOTS %d\n", os ? os->nsens : 0, os ? opt->SensMethod : 0, (os && !(usejac && os->sensitivity)) ? 1 : 0, static_slots);
   CharBuffer_append(b, "#define A1(n) ((n) > 0 ? (n) : 1)\n#define DEV __device__ __forceinline__\n");
   /* per-trajectory constants live in strided shared memory (word k of this thread at p[k*s]) */
   CharBuffer_append(b, "#ifndef ODES_BLOCK\n#define ODES_BLOCK 64\n#endif\n#ifndef ODES_MAT_LOCAL\n#define ODES_MAT_LOCAL 0\n#endif\n"

@@ -137,6 +137,12 @@ def sens_ref_run(model, opt, batch, vary, values, tpoints, mxstep, rtol, atol, t
                     ("CvodeMethod", C.c_int), ("IterMethod", C.c_int), ("MaxOrder", C.c_int), ("ResetCvodeOnEvent", C.c_int), ("SetTStop", C.c_int),
                     ("Sensitivity", C.c_int), ("sensIDs", C.c_void_p), ("nsens", C.c_int), ("SensMethod", C.c_int)]
     C.c_int.in_dll(_refs, "refcvs_sens_method").value = C.cast(opt, C.POINTER(_Opt)).contents.SensMethod
+    dq = L.ODESBatch_getDifferenceQuotients(batch.h)          # which of the reference's difference-quotient fallbacks apply
+    C.c_int.in_dll(_refs, "refcvs_sens_dq").value = dq & 1
+    C.c_int.in_dll(_refs, "refcvs_jac_dq").value = (dq >> 1) & 1
+    arr = (C.c_int * 64).in_dll(_refs, "refcvs_sens_index")
+    for k in range(ns):
+        arr[k] = sens_idx[k]
     r = _refs.refcvs_integrate_batch_events(path.encode(), C.c_int(neq), C.c_int(model.nvalues), C.c_int(ns), C.c_void_p(sens_var.ctypes.data),
                                             C.c_void_p(base.ctypes.data), C.c_int(nsets), C.c_int(len(vary)), C.c_void_p(vary.ctypes.data),
                                             C.c_void_p(values.ctypes.data), C.c_void_p(tp.ctypes.data), C.c_int(nout), C.c_double(rtol), C.c_double(atol),

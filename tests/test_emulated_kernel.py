@@ -43,6 +43,28 @@ def test_emulated_kernel_is_bit_identical_to_compiled_oracle(name, nsets, nout):
     assert np.array_equal(got["fired"].T, refi["fired"])
 
 
+@pytest.mark.parametrize("name,nsets,nout,layout", [("mapk", 24, None, "lane"), ("repressilator", 6, 200, "lane"), ("huang", 6, None, "lane"),
+                                                    ("huang", 6, None, "warp"), ("mapk", 12, None, "warp"), ("events", 16, None, "warp")])
+def test_emulated_difference_quotient_jacobian(monkeypatch, name, nsets, nout, layout):
+    """UseJacobian 0 (src/cvodeSolver.c:620-623: no Jacobian function is registered): CVDENSE's CVDenseDQJac
+    (cvdense.c:479-537) in both kernel layouts, against the vendored CVODE running its own difference quotients."""
+    if layout == "warp":
+        monkeypatch.setenv("ODES_WARP", "1")
+    w = H.workload(name, nout=nout, use_jacobian=0)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=7)
+    b = so.Batch(m, w["opt"], w["vary"])
+    assert so.lib().ODESBatch_getDifferenceQuotients(b.h) == 2
+    assert ("-DODES_WARP=1" in b.source().split("\n", 1)[0]) == (layout == "warp")
+    b.close()
+    got = _emulate(w, vals, tag="%s_dqjac_%s" % (name, layout))
+    ref = H.oracle_run(m, w["opt"], w["vary"], vals, w["nout"], backend=H.REF if H.have_ref() else H.PORT, compiled_so=H.compile_c_model(m, name))
+    assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(got["stats"].T, ref["stats"]) and (ref["stats"][:, 3] > 0).all()
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+
+
 def test_emulated_store_selection_and_row0():
     """Only the requested value[] entries are stored; row 0 holds the varied entries (integratorInstance.c:1571-1572)."""
     w = H.workload("mapk", nout=10)

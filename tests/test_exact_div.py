@@ -2,9 +2,12 @@
 the IEEE quotient bit for bit -- the warp kernel's back substitution relies on it to stay bit-identical to the
 reference's gesl, which divides (smalldense.c:150-158)."""
 import ctypes as C
+import os
+import shutil
 import subprocess
 
 import numpy as np
+import pytest
 
 import helpers as H
 
@@ -12,6 +15,7 @@ SRC = r'''
 #include <math.h>
 #include <stdbool.h>
 #define DEV static inline
+#define ODES_HOST_EMULATION 1        /* the device-only sequence of the file is checked on the GPU (below) */
 #include "%(root)s/sbml_odesolver_b200/csrc/exact_div.inc"
 long check(const double *a, const double *d, long n)
 {
@@ -75,3 +79,17 @@ def test_quotient_from_reciprocal_is_the_ieee_quotient(tmp_path):
     sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1e308, -1e-200, 3.0])
     aa, dd = np.meshgrid(sp, sp)
     assert _bad(lib, aa.ravel(), dd.ravel()) == 0
+
+
+@pytest.mark.gpu
+def test_division_sequence_with_kept_reciprocal_is_the_division_on_the_gpu(tmp_path):
+    """odes_div_seq / odes_rcp_seq (the default of the warp kernel's back substitution): the compiler's own division
+    sequence with its reciprocal part kept by the factorisation, against a / d on 6e8 operand pairs on the device
+    (tests/cuda/div_seq_check.cu: random and structured mantissas, range tests, zeros, infinities, NaNs, denormals)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "div_seq_check"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--fmad=false", "-O2", "-o", str(exe),
+                           os.path.join(H.ROOT, "tests", "cuda", "div_seq_check.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe), "2048"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches 0" in out.stdout

@@ -63,6 +63,23 @@ def test_parity_with_oracle(name, nsets, nout):
     assert bitident == 1.0, (bitident, rep)
 
 
+@pytest.mark.parametrize("name,nsets,nout,layout", [("mapk", 512, None, "lane"), ("repressilator", 64, 200, "lane"), ("huang", 64, None, "lane"),
+                                                    ("huang", 64, None, "warp"), ("mapk", 256, None, "warp")])
+def test_difference_quotient_jacobian(monkeypatch, name, nsets, nout, layout):
+    """UseJacobian 0: CVDENSE's CVDenseDQJac (cvdense.c:479-537, src/cvodeSolver.c:620-623) in the lane kernel (default
+    without a Jacobian) and in the warp kernel (ODES_WARP=1), against the vendored CVODE with its own difference quotients."""
+    if layout == "warp":
+        monkeypatch.setenv("ODES_WARP", "1")
+    w = H.workload(name, nout=nout, use_jacobian=0)
+    vals = H.workload_values(w, nsets, seed=31)
+    got = _gpu_run(w, vals)
+    ref = _oracle(w, vals)
+    assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(got["stats"], ref["stats"]) and (ref["stats"][:, 3] > 0).all()
+    assert np.array_equal(got["out"], np.transpose(ref["out"], (1, 2, 0)), equal_nan=True)
+    print(name, layout, got["info"])
+
+
 def test_event_order_identical():
     w = H.workload("events")
     vals = H.workload_values(w, 2048, seed=9)

@@ -235,6 +235,66 @@ def test_sensitivities_agree_with_central_differences():
         assert np.allclose(s[:, 1:], fd[:, 1:], rtol=2e-3, atol=2e-4 * np.abs(fd).max()), (np.abs(s - fd).max(), np.abs(fd).max())
 
 
+# difference quotients: parameters only (the reference's f freezes a VARIABLE listed as a sensitivity at its initial value in
+# this mode, src/cvodeSolver.c:981-984 -- refused by the plan)
+DQ_CASES = {
+    "mapk": ["K1", "Ki", "V1"],
+    "repressilator": ["alpha", "beta"],
+    "huang": ["r_r1a_a1", "r_r10b_k10"],
+    "events": ["compartment"],
+}
+
+
+def _dq_case(name, mode, method, nout=None):
+    """mode 'nojac': UseJacobian 0 -> CVDenseDQJac and CVSensRhsDQ; 'nomatrix': the Jacobian is analytic, the parametric matrix
+    is treated as not constructible (ODES_FORCE_SENS_DQ, a test knob for src/sensSolver.c:312-321 with om->jacobian set)."""
+    return H.workload(name, nout=nout, sensitivity=1, sens_ids=DQ_CASES[name], sens_method=method, use_jacobian=0 if mode == "nojac" else 1)
+
+
+@needs_ref
+@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("mode", ["nojac", "nomatrix"])
+@pytest.mark.parametrize("name,nsets", [("mapk", 12), ("repressilator", 4), ("huang", 3), ("events", 12)])
+def test_emulated_difference_quotient_sensitivities_are_bit_identical_to_vendored_cvodes(monkeypatch, name, nsets, mode, method):
+    """src/sensSolver.c:312-321: without a parametric matrix (or without a Jacobian) the reference registers no sensitivity
+    right-hand side -- CVODES' CVSensRhsDQ (centred, rhomax 0) over f with the parameters read from the perturbed array --
+    and CVDENSE's CVDenseDQJac where there is no Jacobian.  The kernel's sens_dq / dq_jac against the vendored CVODES."""
+    if mode == "nomatrix":
+        monkeypatch.setenv("ODES_FORCE_SENS_DQ", "1")
+    w = _dq_case(name, mode, method)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=13)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    assert b.nsens == len(DQ_CASES[name])
+    assert so.lib().ODESBatch_getDifferenceQuotients(b.h) == (3 if mode == "nojac" else 1)
+    tp = H.tpoints(w["opt"], w["nout"])
+    base, trig = b.base_values()
+    got = H.Emu(b, "%s_dq_%s%d" % (name, mode, method)).run(base, trig, vals, tp, 10000, w["rtol"], w["atol"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], tag="%s_dq_%s%d" % (name, mode, method))
+    b.close()
+    assert np.array_equal(got["status"], ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(got["fired"].T, ref["fired"])
+    assert np.array_equal(got["stats"].T, ref["stats"][:, :7])
+    assert np.array_equal(np.transpose(got["out"], (2, 0, 1)), ref["out"])
+    assert np.array_equal(got["sens"], ref["sens"])
+    assert np.abs(ref["sens"][:, -1]).max() > 0
+
+
+@needs_ref
+def test_difference_quotient_sensitivities_are_close_to_the_analytic_ones():
+    w = H.workload("mapk", nout=10, sensitivity=1, sens_ids=DQ_CASES["mapk"])
+    wd = _dq_case("mapk", "nojac", 0, nout=10)
+    vals = H.workload_values(w, 3, seed=2)
+    tp = H.tpoints(w["opt"], w["nout"])
+    res = []
+    for ww in (w, wd):
+        b = so.Batch(ww["model"], ww["opt"], ww["vary"], store=list(range(ww["model"].neq)))
+        res.append(H.sens_ref_run(ww["model"], ww["opt"], b, ww["vary"], vals, tp, 10000, ww["rtol"], ww["atol"], tag="mapk_dqcmp%d" % len(res)))
+        b.close()
+    scale = np.abs(res[0]["sens"]).max()
+    assert np.abs(res[0]["sens"] - res[1]["sens"]).max() < 1e-3 * scale
+
+
 def test_unsupported_sensitivity_configurations_fail_loudly():
     m2, vary, _ = H.mapk_scan_model()
     opt2 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["K1"])
@@ -242,6 +302,9 @@ def test_unsupported_sensitivity_configurations_fail_loudly():
     opt3 = so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["no_such_symbol"])
     with pytest.raises(so.OdesError):
         so.Batch(m2, opt3, vary)
+    # difference quotients with respect to an initial value: the reference's f would freeze that variable
+    with pytest.raises(so.OdesError, match="initial values"):
+        so.Batch(m2, so.settings(10.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=["K1", "MAPK"], use_jacobian=0), vary)
     b = so.Batch(m2, so.settings(10.0, 10, 1e-9, 1e-6), vary)
     assert b.nsens == 0
     b.close()
@@ -270,6 +333,34 @@ def test_gpu_sensitivities_are_bit_identical_to_vendored_cvodes(name, nsets, met
     assert np.array_equal(stats, ref["stats"][:, :7])
     assert H.parity(sens, ref["sens"], w["rtol"], w["atol"]) <= 1.0                  # the gate
     assert np.array_equal(np.transpose(out, (2, 0, 1)), ref["out"], equal_nan=True)  # and bit for bit
+    assert np.array_equal(sens, ref["sens"], equal_nan=True)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("method", [0, 2])
+@pytest.mark.parametrize("mode", ["nojac", "nomatrix"])
+@pytest.mark.parametrize("name,nsets", [("mapk", 256), ("huang", 48), ("events", 256)])
+def test_gpu_difference_quotient_sensitivities_are_bit_identical_to_vendored_cvodes(monkeypatch, name, nsets, mode, method):
+    """CVSensRhsDQ / CVDenseDQJac of the reference's fallbacks (src/sensSolver.c:312-321) on the device."""
+    if mode == "nomatrix":
+        monkeypatch.setenv("ODES_FORCE_SENS_DQ", "1")
+    w = _dq_case(name, mode, method)
+    m = w["model"]
+    vals = H.workload_values(w, nsets, seed=29)
+    b = so.Batch(m, w["opt"], w["vary"], store=list(range(m.neq)))
+    n = b.set_values(vals)
+    ms = b.integrate(n)
+    out, sens, status, stats = b.results(n), b.sensitivities(n), b.status(n), b.stats(n).T
+    fired = b.event_log(n).T
+    tp = H.tpoints(w["opt"], w["nout"])
+    ref = H.sens_ref_run(m, w["opt"], b, w["vary"], vals, tp, 10000, w["rtol"], w["atol"], threads=8, tag="%s_dq_%s%d" % (name, mode, method))
+    print(name, mode, "method", method, f"{n / ms * 1e3:.0f} trajectories/s", b.kernel_info())
+    b.close()
+    assert np.array_equal(status, ref["status"]) and (ref["status"] == 0).all()
+    assert np.array_equal(fired, ref["fired"])
+    assert np.array_equal(stats, ref["stats"][:, :7])
+    assert np.array_equal(np.transpose(out, (2, 0, 1)), ref["out"], equal_nan=True)
     assert np.array_equal(sens, ref["sens"], equal_nan=True)
 
 

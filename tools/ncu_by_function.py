@@ -18,7 +18,7 @@ rows = list(csv.reader(io.StringIO(txt)))
 h = rows[1]; ix = {n: i for i, n in enumerate(h)}
 base = int(rows[2][0], 16)
 src = open(tu).read().split("\n")
-funcs = [(i, l.strip()[:70]) for i, l in enumerate(src, 1) if re.match(r"\s*(DEV|ODES_NOINLINE) ", l) or "__global__" in l]
+funcs = [(i, l.strip()[:70]) for i, l in enumerate(src, 1) if re.match(r"\s*(template\s*<[^>]*>\s*)?(DEV|ODES_NOINLINE) ", l) or "__global__" in l]
 funcs.append((len(src) + 1, "END"))
 def fn(ln):
     if ln is None: return "(other functions: f_eval, root_pow, division slow paths)"
