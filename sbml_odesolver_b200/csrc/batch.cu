@@ -429,10 +429,12 @@ static std::string build_source(odesBatch_t *b)
   int warp = env_int("ODES_WARP", -1);
   /* crossover measured with tools/gpu_layout_crossover.py (chain models, 10^5 sets): n = 16 lane 1.09 M vs warp 0.69 M,
      n = 20 0.51 M vs 0.56 M, n = 24 0.26 M vs 0.48 M, n = 32 0.11 M vs 0.38 M trajectories/s; huang96 (n = 22) 82 k vs 174 k */
-  if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32 && usejac) ? 1 : 0;
+  /* without a Jacobian (CVDenseDQJac, one right-hand side per column): huang96 lane 62 k vs warp 296 k, MAPK lane 1.91 M vs
+     warp 0.91 M (tools/gpu_dq_layout.py) -- the same crossover */
+  if (warp < 0) warp = (la != 2 && neq >= 19 && neq <= 32) ? 1 : 0;
   if (b->nsens > 0) warp = 1;                   /* the simultaneous corrector lives in the warp-per-trajectory kernel */
   if (b->opt->CvodeMethod == 1 || b->opt->IterMethod == 1) warp = 1;       /* and so do Adams-Moulton and functional iteration */
-  if (warp && !(neq >= 1 && neq <= 32 && (usejac || b->nsens > 0 || env_int("ODES_WARP", -1) == 1))) warp = 0;   /* without a Jacobian: CVDenseDQJac in either layout; the lane layout stays the default */
+  if (warp && !(neq >= 1 && neq <= 32)) warp = 0;
   b->warpMode = warp;
   if (warp) {
     const int wpb = env_int("ODES_WARPS_PER_BLOCK", 4);

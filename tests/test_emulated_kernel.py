@@ -48,8 +48,7 @@ def test_emulated_kernel_is_bit_identical_to_compiled_oracle(name, nsets, nout):
 def test_emulated_difference_quotient_jacobian(monkeypatch, name, nsets, nout, layout):
     """UseJacobian 0 (src/cvodeSolver.c:620-623: no Jacobian function is registered): CVDENSE's CVDenseDQJac
     (cvdense.c:479-537) in both kernel layouts, against the vendored CVODE running its own difference quotients."""
-    if layout == "warp":
-        monkeypatch.setenv("ODES_WARP", "1")
+    monkeypatch.setenv("ODES_WARP", "1" if layout == "warp" else "0")      # default: warp from 19 equations on, as with a Jacobian
     w = H.workload(name, nout=nout, use_jacobian=0)
     m = w["model"]
     vals = H.workload_values(w, nsets, seed=7)

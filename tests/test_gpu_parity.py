@@ -66,10 +66,8 @@ def test_parity_with_oracle(name, nsets, nout):
 @pytest.mark.parametrize("name,nsets,nout,layout", [("mapk", 512, None, "lane"), ("repressilator", 64, 200, "lane"), ("huang", 64, None, "lane"),
                                                     ("huang", 64, None, "warp"), ("mapk", 256, None, "warp")])
 def test_difference_quotient_jacobian(monkeypatch, name, nsets, nout, layout):
-    """UseJacobian 0: CVDENSE's CVDenseDQJac (cvdense.c:479-537, src/cvodeSolver.c:620-623) in the lane kernel (default
-    without a Jacobian) and in the warp kernel (ODES_WARP=1), against the vendored CVODE with its own difference quotients."""
-    if layout == "warp":
-        monkeypatch.setenv("ODES_WARP", "1")
+    """UseJacobian 0: CVDENSE's CVDenseDQJac (cvdense.c:479-537, src/cvodeSolver.c:620-623) in the lane kernel and in the warp kernel (the default from 19 equations on), against the vendored CVODE with its own difference quotients."""
+    monkeypatch.setenv("ODES_WARP", "1" if layout == "warp" else "0")      # default: warp from 19 equations on, as with a Jacobian
     w = H.workload(name, nout=nout, use_jacobian=0)
     vals = H.workload_values(w, nsets, seed=31)
     got = _gpu_run(w, vals)
