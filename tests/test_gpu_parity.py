@@ -78,6 +78,35 @@ def test_difference_quotient_jacobian(monkeypatch, name, nsets, nout, layout):
     print(name, layout, got["info"])
 
 
+def test_entire_headline_batch_is_bit_identical_to_vendored_cvode():
+    """BASELINE configs[1] at its full size: all 10^6 trajectories of the headline batch -- every stored value of every output
+    row, the status flags and CVODE's work counters -- against the vendored CVODE run on the host threads over the same sets
+    in slabs of 10^5 sets (about 30 s on 16 cores; 6.5 GB for the device's result block, 3 GB per oracle slab)."""
+    if not H.have_ref():
+        pytest.skip("oracle/_ref not built")
+    with open("/proc/meminfo") as f:
+        avail_gb = [int(l.split()[1]) for l in f if l.startswith("MemAvailable")][0] / 1048576
+    if avail_gb < 24:
+        pytest.skip("needs 24 GB of host memory")
+    n = 1_000_000
+    m, vary, nominal = H.mapk_scan_model()
+    opt = so.settings(1000.0, 100, 1e-9, 1e-6)
+    b = so.Batch(m, opt, vary, store=list(range(m.neq)))
+    b.reserve(n)
+    b.generate_values(n, 20261019, 0, nominal, -np.ones(len(vary)), np.ones(len(vary)))
+    b.integrate(n)
+    out, status, stats = b.results(n), b.status(n), b.stats(n)
+    vals = np.ascontiguousarray(b.get_values(n))
+    b.close()
+    assert int((status != 0).sum()) == 0
+    cso = H.compile_c_model(m, "mapk_scan")
+    for k in range(0, n, 100_000):
+        ref = H.oracle_run(m, opt, vary, vals[k:k + 100_000], 100, backend=H.REF, compiled_so=cso, threads=os.cpu_count() or 1)
+        assert np.array_equal(status[k:k + 100_000], ref["status"])
+        assert np.array_equal(stats[:, k:k + 100_000].T, ref["stats"])
+        assert np.array_equal(out[:, :, k:k + 100_000], np.transpose(ref["out"][:, :, :m.neq], (1, 2, 0))), k
+
+
 def test_event_order_identical():
     w = H.workload("events")
     vals = H.workload_values(w, 2048, seed=9)
