@@ -444,6 +444,42 @@ def test_model_odesolverbatch_maps_sensitivities_per_design_point():
     L.VarySettings_free(vs)
 
 
+@pytest.mark.gpu
+def test_reference_entries_take_the_difference_quotient_fallback():
+    """Model_odeSolverBatch and the single IntegratorInstance with UseJacobian 0 and sensitivity analysis: no refusal any more,
+    the same numbers as a plan created with the same settings (CVSensRhsDQ + CVDenseDQJac, checked against CVODES above)."""
+    L = so.lib()
+    m = so.Model(H.model_path("mapk_cascade.xml"))
+    ids = ["K1", "Ki"]
+    opt = so.settings(100.0, 10, 1e-9, 1e-6, sensitivity=1, sens_ids=ids, use_jacobian=0)
+    vs = L.VarySettings_allocate(1, 2)
+    L.VarySettings_addParameter(vs, b"K1", None)
+    for x in (5.0, 20.0):
+        L.VarySettings_addDesignPoint(vs, (C.c_double * 1)(x))
+    res = L.Model_odeSolverBatch(m.sbml, opt, vs)
+    assert res and L.SBMLResultsArray_getNumResults(res) == 2
+    b = so.Batch(m, opt, [m.index("K1")], store=list(range(m.neq)))
+    assert L.ODESBatch_getDifferenceQuotients(b.h) == 3
+    b.set_values(np.array([[5.0], [20.0]]))
+    b.integrate(2)
+    sens = b.sensitivities(2)
+    b.close()
+    assert np.abs(sens[:, -1]).max() > 0
+    for k in range(2):
+        r = L.SBMLResultsArray_getResults(res, k)
+        assert L.SBMLResults_getNumSens(r) == 2
+        tc = L.SBMLResults_getTimeCourse(r, b"MKKK_P")
+        got = np.array([[L.TimeCourse_getSensitivity(tc, j, t) for t in range(11)] for j in range(2)])
+        assert np.array_equal(got, sens[k, :, :, 1].T)
+    L.SBMLResultsArray_free(res)
+    L.VarySettings_free(vs)
+    # the single instance: integrate to the end, read the sensitivities of the last row
+    ii = L.IntegratorInstance_create(m.om, opt)
+    assert ii and L.IntegratorInstance_getNsens(ii) == 2
+    assert L.IntegratorInstance_integrate(ii) == 1
+    L.IntegratorInstance_free(ii)
+
+
 @needs_ref
 def test_failed_trajectories_leave_not_a_number_rows_in_states_and_sensitivities():
     """mxstep too small: CV_TOO_MUCH_WORK at the same output interval as the reference, the rows before it identical, the rows
